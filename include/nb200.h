@@ -1,0 +1,214 @@
+/*
+ * nb200.h — C ABI of libnb200.so: the B200-native (sm_100a) value-and-gradient evaluation of libnano's
+ * linear-model objective. Plain pointers and sizes only; no exceptions cross this boundary; every entry point
+ * returns 0 on success and a non-zero nb200_status otherwise (message via nb200_last_error()).
+ *
+ * What it replaces in the reference (/root/reference, all CPU/Eigen):
+ *   nano::function_t::operator()(x, gx)           src/function.cpp:246-272   -> nb200_vgrad
+ *   nano::linear::function_t (ctor, do_eval)      src/linear/function.cpp:21-168 -> nb200_objective_create / nb200_vgrad
+ *   nano::linear::predict                         src/linear/util.cpp:6-21   -> nb200_predict
+ *   nano::loss_t::value / vgrad                   src/loss.cpp:57-71         -> nb200_loss_value / nb200_loss_vgrad
+ *   accumulator_t + sum_reduce                    src/linear/accumulator.cpp, include/nano/core/reduce.h:23-31
+ *                                                 -> nb200_vgrad_partial + (all-reduce) + nb200_vgrad_finish
+ *   flatten_iterator_t::cache_flatten/targets     src/dataset/iterator.cpp:118-147,52-77 -> nb200_dataset_pin
+ *   linear_model_t + function_{ridge,lasso,elasticnet}_t   src/function/mlearn/*  -> flavour NB200_FLAVOUR_SYNTH
+ *
+ * Threading contract (same as the reference's `const do_eval` + `mutable` scratch): one call in
+ * flight per nb200_obj; distinct objects (clones) sharing one nb200_data may be used concurrently.
+ */
+#ifndef NB200_H
+#define NB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NB200_API __attribute__((visibility("default")))
+#else
+#define NB200_API
+#endif
+
+typedef struct nb200_ctx  nb200_ctx;  /* one CUDA device + stream                                  */
+typedef struct nb200_data nb200_data; /* a feature matrix X[N,D] and targets Y[N,T] pinned in HBM  */
+typedef struct nb200_obj  nb200_obj;  /* an objective over a pinned dataset (loss, reg, scratch)   */
+
+typedef enum nb200_status
+{
+    NB200_OK               = 0,
+    NB200_ERR_INVALID      = 1, /* bad argument (size mismatch, unknown loss, null pointer)          */
+    NB200_ERR_CUDA         = 2, /* CUDA runtime error (no device, out of memory, launch failure)     */
+    NB200_ERR_UNSUPPORTED  = 3, /* well-formed request outside the implemented path (e.g. Hessian)   */
+} nb200_status;
+
+/* loss kinds. libnano ids (src/loss.cpp:105-135) map onto them with the s-/m- prefix dropped, because the prefix
+ * only changes error(), never value()/vgrad() (include/nano/loss/flatten.h:103-122). */
+typedef enum nb200_loss
+{
+    NB200_LOSS_MSE            = 0,  /* include/nano/loss/mse.h:19-29                                 */
+    NB200_LOSS_MAE            = 1,  /* include/nano/loss/mae.h:19-29                                 */
+    NB200_LOSS_CAUCHY         = 2,  /* include/nano/loss/cauchy.h                                    */
+    NB200_LOSS_HINGE          = 3,  /* include/nano/loss/hinge.h:19-29                               */
+    NB200_LOSS_SQUARED_HINGE  = 4,  /* include/nano/loss/squared_hinge.h                             */
+    NB200_LOSS_CLASSNLL       = 5,  /* include/nano/loss/classnll.h:19-37                            */
+    NB200_LOSS_SAVAGE         = 6,  /* include/nano/loss/savage.h                                    */
+    NB200_LOSS_TANGENT        = 7,  /* include/nano/loss/tangent.h                                   */
+    NB200_LOSS_LOGISTIC       = 8,  /* include/nano/loss/logistic.h:19-41                            */
+    NB200_LOSS_EXPONENTIAL    = 9,  /* include/nano/loss/exponential.h                               */
+    NB200_LOSS_PINBALL        = 10, /* src/loss/pinball.cpp:24-48 (loss_param = loss::pinball::alpha) */
+    NB200_LOSS_SYNTH_CAUCHY   = 11, /* src/function/mlearn/loss.cpp:50-63 (no 1/2, gradient x2)      */
+    NB200_LOSS_SYNTH_LOGISTIC = 12, /* src/function/mlearn/loss.cpp:97-125 (un-stabilised gradient)  */
+    NB200_LOSS_COUNT          = 13
+} nb200_loss;
+
+typedef enum nb200_flavour
+{
+    /* nano::linear::function_t (src/linear/function.cpp): x = [W (T x D row-major) | b (T)], n = (D+1)*T,
+     * f = mean loss + l1*mean|W| + 0.5*l2*mean(W^2), gW += l1*sign(W)/(T*D) + l2*W/(T*D). */
+    NB200_FLAVOUR_LINEAR = 0,
+    /* function_{ridge,lasso,elasticnet}_t over linear_model_t (src/function/mlearn/): T = 1, x = w (n = D), the
+     * bias is FIXED (fixed_bias), f = mean loss + l1*|x|_1 + 0.5*l2*|x|^2, g += l1*sign(x) + l2*x (un-normalised;
+     * ridge.cpp:69-79, lasso.cpp:69-75, elasticnet.cpp:74-85). */
+    NB200_FLAVOUR_SYNTH = 1
+} nb200_flavour;
+
+typedef enum nb200_synth_kind
+{
+    /* X_ij ~ U[-1,1) from Philox4x32-10 (key = seed, counter = global element index),
+     * w*_j ~ U[-1,1)/sqrt(D), b* = 0.1, y_i = sign(x_i . w* + b* + noise * n_i) in {-1,+1}, T = 1 */
+    NB200_SYNTH_CLASSIFICATION = 0,
+    /* same X, w*, b*; y_i = x_i . w* + b* + noise * n_i, T = 1 */
+    NB200_SYNTH_REGRESSION = 1,
+    /* same X; W*[T,D] ~ U[-1,1)/sqrt(D); targets are -1 everywhere except +1 at argmax_t(x_i . W*_t)
+     * (include/nano/loss/class.h:51-58), T >= 2 */
+    NB200_SYNTH_MULTICLASS = 2
+} nb200_synth_kind;
+
+/* ---- library / device ---------------------------------------------------------------------------------------- */
+
+/* Thread-local message describing the last failure on the calling thread ("" if none). */
+NB200_API const char* nb200_last_error(void);
+
+/* Library version "major.minor.patch". */
+NB200_API const char* nb200_version(void);
+
+/* Number of visible CUDA devices (0 if none / no driver); never fails. */
+NB200_API int nb200_device_count(void);
+
+/* Bind a context to CUDA device `device` (creates a non-blocking stream). Fails loudly (NB200_ERR_CUDA) when
+ * there is no usable GPU: there is no CPU fallback. */
+NB200_API int nb200_init(int device, nb200_ctx** out_ctx);
+NB200_API void nb200_ctx_release(nb200_ctx* ctx);
+
+/* ---- dataset: replaces flatten_iterator_t::cache_flatten/cache_targets ---------------------------------------- */
+
+/* Copy X[N,D] and Y[N,T] (host, row-major, contiguous fp64) into HBM once per fit. */
+NB200_API int nb200_dataset_pin(nb200_ctx* ctx, const double* X, const double* Y, int64_t N, int64_t D, int64_t T,
+                                nb200_data** out_data);
+
+/* Generate rows [row_offset, row_offset + N) of a synthetic dataset directly in HBM (no host staging; the big
+ * BASELINE configs do not fit host RAM). The same (seed, kind, D, T, noise) with different row_offset gives
+ * disjoint shards of ONE dataset, which is how ranks shard it. */
+NB200_API int nb200_dataset_synth(nb200_ctx* ctx, uint64_t seed, int synth_kind, int64_t N, int64_t D, int64_t T,
+                                  int64_t row_offset, double noise, nb200_data** out_data);
+
+/* Read rows [row0, row0 + rows) back to the host (X and/or Y may be NULL). */
+NB200_API int nb200_dataset_read(const nb200_data* data, int64_t row0, int64_t rows, double* X, double* Y);
+
+NB200_API int64_t nb200_dataset_samples(const nb200_data* data);
+NB200_API int64_t nb200_dataset_inputs(const nb200_data* data);
+NB200_API int64_t nb200_dataset_targets(const nb200_data* data);
+
+/* Datasets are reference counted: objectives retain the dataset they were created on. */
+NB200_API void nb200_dataset_retain(nb200_data* data);
+NB200_API void nb200_dataset_release(nb200_data* data);
+
+/* ---- objective: replaces nano::linear::function_t / function_{ridge,lasso,elasticnet}_t ---------------------- */
+
+/* fixed_bias: T doubles (host), used by NB200_FLAVOUR_SYNTH only (may be NULL otherwise). */
+NB200_API int nb200_objective_create(nb200_data* data, int loss, double loss_param, int flavour, double l1,
+                                     double l2, const double* fixed_bias, nb200_obj** out_obj);
+
+/* clone(): shares the pinned dataset (retained), duplicates stream and scratch (src/linear/function.cpp:39-42). */
+NB200_API int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj);
+NB200_API void nb200_objective_release(nb200_obj* obj);
+
+/* n: (D+1)*T for NB200_FLAVOUR_LINEAR, D for NB200_FLAVOUR_SYNTH. */
+NB200_API int64_t nb200_objective_size(const nb200_obj* obj);
+
+/* f(x) and, when gx != NULL, the gradient. x, gx, fx are HOST pointers (what libnano's solvers pass); the call
+ * copies x to the device, evaluates, copies (gx, fx) back and returns when they are valid. `n` must equal
+ * nb200_objective_size() (the reference throws on a size mismatch: src/function.cpp:248-252). Non-finite results
+ * are returned as they are (solver_state_t::valid() decides, src/solver/state.cpp:170-174). */
+NB200_API int nb200_vgrad(nb200_obj* obj, const double* x, int64_t n, double* gx, double* fx);
+
+/* Same evaluation with x / gx / fx resident in HBM; enqueued on the objective's stream, no host sync
+ * (call nb200_objective_sync before reading on the host or from another stream). */
+NB200_API int nb200_vgrad_device(nb200_obj* obj, const double* x_dev, int64_t n, double* gx_dev, double* fx_dev);
+NB200_API int nb200_objective_sync(nb200_obj* obj);
+
+/* Sample-sharded evaluation (one rank per GPU): phase 1 leaves the UN-normalised local sums
+ *   partial = [ sum_i loss_i | sum_i dL_i (T) | sum_i dL_i x_i^T (T*D) ]      (1 + T + T*D doubles, device)
+ * in a device buffer owned by the objective (gradient entries are left untouched when want_grad == 0). The
+ * caller all-reduces (sum) that buffer across ranks on `nb200_objective_stream()` or after
+ * nb200_objective_sync(), then phase 2 divides by the GLOBAL sample count, adds the regularisation terms and
+ * writes (gx, fx) to the host. With one rank the pair is equivalent to nb200_vgrad. */
+NB200_API int nb200_vgrad_partial(nb200_obj* obj, const double* x, int64_t n, int want_grad, double** out_partial_dev,
+                                  int64_t* out_partial_len);
+NB200_API int nb200_vgrad_finish(nb200_obj* obj, int64_t n_global, double* gx, double* fx);
+
+/* The same two phases with x / gx / fx resident in HBM (device-resident solvers; no host copy, no sync). */
+NB200_API int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, int64_t n, int want_grad,
+                                         double** out_partial_dev, int64_t* out_partial_len);
+NB200_API int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, int64_t n_global, double* gx_dev,
+                                        double* fx_dev);
+
+/* cudaStream_t of the objective, as an opaque pointer (so that callers can order collectives after phase 1);
+ * set_stream re-points the objective at a caller-owned stream (NULL: back to its own), e.g. the stream the
+ * caller's NCCL all-reduce is enqueued on, so that phase 1 -> all-reduce -> phase 2 need no host synchronisation. */
+NB200_API void* nb200_objective_stream(const nb200_obj* obj);
+NB200_API int   nb200_objective_set_stream(nb200_obj* obj, void* stream);
+
+/* Kernels launched by this objective since creation (bench.py's `gpu_launches`). */
+NB200_API int64_t nb200_objective_launches(const nb200_obj* obj);
+
+/* Device timing of the main pass (the kernel(s) that stream X), from CUDA events recorded on the objective's
+ * stream around those launches. Off by default. last_pass_ms: most recent evaluation (< 0 if unavailable; syncs
+ * the stream); pass_stats: sum and count over the evaluations since the last reset. */
+NB200_API int    nb200_objective_enable_timing(nb200_obj* obj, int enabled);
+NB200_API double nb200_objective_last_pass_ms(nb200_obj* obj);
+NB200_API int    nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count, int reset);
+
+/* Tuning knob for the fused T == 1 kernel: variant id (see DESIGN.md "kernel variants"), -1 = heuristic,
+ * -2 = force the shape-generic two-kernel path. */
+NB200_API int nb200_objective_set_variant(nb200_obj* obj, int variant);
+
+/* Human-readable launch plan (kernel variant, grid, stages, shared memory) into buffer[size]. */
+NB200_API int nb200_objective_describe(const nb200_obj* obj, char* buffer, int64_t size);
+
+/* ---- building blocks exposed on their own (reference: linear::predict, loss_t::value / loss_t::vgrad) -------- */
+
+/* outputs[N,T] (host) = X * W^T + b over the pinned dataset; W[T,D], b[T] host. */
+NB200_API int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const double* b,
+                            double* outputs);
+
+/* per-sample loss values[N] / gradients vgrads[N,T] for host targets/outputs[N,T]. */
+NB200_API int nb200_loss_value(nb200_ctx* ctx, int loss, double loss_param, const double* targets,
+                               const double* outputs, int64_t N, int64_t T, double* values);
+NB200_API int nb200_loss_vgrad(nb200_ctx* ctx, int loss, double loss_param, const double* targets,
+                               const double* outputs, int64_t N, int64_t T, double* vgrads);
+
+/* Host-side data of the builtin synthetic test functions: the random part of the linear_model_t constructor
+ * (src/function/mlearn/linear.cpp:15-33): rng = std::mt19937_64(seed), u ~ uniform_real_distribution(0, 1);
+ * X[samples, inputs] row-major, then wopt[inputs], then bopt = u - 0.5; wopt is divided by its sum and the columns
+ * with j % modulo != 0 are zeroed. (The targets follow from nb200_predict.) */
+NB200_API int nb200_synth_linear_inputs(int64_t samples, int64_t inputs, uint64_t seed, int64_t modulo, double* X,
+                                        double* wopt, double* bopt);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NB200_H */

@@ -1,0 +1,147 @@
+// common.cuh — error handling and the sm_100a PTX building blocks (mbarrier, 1-D bulk async copy, warp reductions)
+// shared by the kernels of libnb200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace nb200
+{
+// ---------------------------------------------------------------------------------------------------------------
+// host-side error plumbing: no exception crosses the C ABI; the message is kept per thread.
+// ---------------------------------------------------------------------------------------------------------------
+inline thread_local std::string g_last_error;
+
+inline int fail(const int status, const std::string& message)
+{
+    g_last_error = message;
+    return status;
+}
+
+#define NB200_CUDA_TRY(expr)                                                                                           \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const cudaError_t nb200_err_ = (expr);                                                                         \
+        if (nb200_err_ != cudaSuccess)                                                                                 \
+        {                                                                                                              \
+            return ::nb200::fail(2 /*NB200_ERR_CUDA*/, std::string("CUDA error in ") + #expr + ": " +                   \
+                                                           cudaGetErrorName(nb200_err_) + " (" +                       \
+                                                           cudaGetErrorString(nb200_err_) + ")");                      \
+        }                                                                                                              \
+    } while (0)
+
+#define NB200_REQUIRE(cond, message)                                                                                   \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+        {                                                                                                              \
+            return ::nb200::fail(1 /*NB200_ERR_INVALID*/, std::string("critical check failed: ") + (message));          \
+        }                                                                                                              \
+    } while (0)
+
+inline int64_t round_up(const int64_t value, const int64_t multiple)
+{
+    return (value + multiple - 1) / multiple * multiple;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+// mbarrier (shared::cta, 64-bit): init / arrive / arrive+expect_tx / parity wait
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    // make the initialised barriers visible to the async proxy (the bulk-copy engine)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, const uint32_t tx_bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tx_bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity)
+{
+    // try_wait suspends the thread in hardware up to a time limit; loop until the phase with `parity` completed
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "NB200_WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra NB200_DONE_%=;\n\t"
+                 "bra NB200_WAIT_%=;\n\t"
+                 "NB200_DONE_%=:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// L2 eviction policy for data that is streamed exactly once (X tiles)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+// 1-D bulk asynchronous copy global -> shared (the TMA engine without a tensor map; SASS: UBLKCP).
+// dst and src 16-byte aligned, bytes a multiple of 16; completion is signalled on `bar` as transaction bytes.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, const uint32_t bytes,
+                                              uint64_t* bar, const uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, "
+                 "[%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+// named barrier over a subset of the CTA's warps
+__device__ __forceinline__ void named_bar_sync(const uint32_t id, const uint32_t threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// butterfly all-reduce: every lane ends with the same bits (fp add is commutative, so both partners of each
+// exchange compute the identical sum)
+__device__ __forceinline__ double warp_allreduce_sum(double value)
+{
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+    {
+        value += __shfl_xor_sync(0xffffffffu, value, offset);
+    }
+    return value;
+}
+
+__device__ __forceinline__ double warp_allreduce_max(double value)
+{
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1)
+    {
+        const double other = __shfl_xor_sync(0xffffffffu, value, offset);
+        value              = (value < other) ? other : value;
+    }
+    return value;
+}
+
+#endif // __CUDACC__
+} // namespace nb200

@@ -1,0 +1,1141 @@
+// nb200_api.cu — the C ABI of libnb200.so (include/nb200.h): host-side orchestration of the sm_100a kernels.
+//
+// Boundary replaced: nano::function_t::operator() (src/function.cpp:246-272) dispatching into
+// nano::linear::function_t::do_eval (src/linear/function.cpp:44-168) or function_{ridge,lasso,elasticnet}_t::do_eval
+// (src/function/mlearn/). There is no CPU fallback in this file: every evaluation is a CUDA launch.
+#include "../../include/nb200.h"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <random>
+#include <vector>
+
+#include "common.cuh"
+#include "loss.cuh"
+#include "reduce.cuh"
+#include "synth.cuh"
+#include "vgrad_gen.cuh"
+#include "vgrad_t1.cuh"
+
+using namespace nb200;
+
+// ---------------------------------------------------------------------------------------------------------------
+// opaque handles
+// ---------------------------------------------------------------------------------------------------------------
+struct nb200_ctx
+{
+    int          device{0};
+    cudaStream_t stream{nullptr};
+    int          sm_count{0};
+    int          smem_optin{0};
+};
+
+struct nb200_data
+{
+    std::atomic<int> refs{1};
+    int              device{0};
+    int              sm_count{0};
+    int              smem_optin{0};
+    double*          X{nullptr}; // [N, D] + 256 bytes of zeroed slack (bulk copies round tails up to 16 bytes)
+    double*          Y{nullptr}; // [N, T] + slack
+    int64_t          N{0}, D{0}, T{0};
+};
+
+namespace
+{
+using t1_kernel_t = void (*)(const t1_params);
+
+struct t1_variant
+{
+    int         V, KC, WS, NCW;
+    t1_kernel_t grad;
+    t1_kernel_t value;
+};
+
+#define NB200_T1_VARIANT(V, KC, WS, NCW)                                                                               \
+    t1_variant                                                                                                         \
+    {                                                                                                                  \
+        V, KC, WS, NCW, vgrad_t1_kernel<V, KC, WS, NCW, true>, vgrad_t1_kernel<V, KC, WS, NCW, false>                  \
+    }
+
+// Ordered so that the first variant whose column capacity 32*V*KC*WS covers D is the heuristic choice; the extra
+// entries at the end are alternative decompositions selectable with nb200_objective_set_variant.
+const t1_variant kT1Variants[] = {
+    /* 0*/ NB200_T1_VARIANT(2, 1, 1, 8),
+    /* 1*/ NB200_T1_VARIANT(2, 2, 1, 8),
+    /* 2*/ NB200_T1_VARIANT(2, 4, 1, 8),
+    /* 3*/ NB200_T1_VARIANT(2, 8, 1, 8),
+    /* 4*/ NB200_T1_VARIANT(2, 16, 1, 8),
+    /* 5*/ NB200_T1_VARIANT(2, 16, 2, 8),
+    /* 6*/ NB200_T1_VARIANT(2, 16, 4, 8),
+    /* 7*/ NB200_T1_VARIANT(2, 16, 8, 8),
+    /* 8*/ NB200_T1_VARIANT(1, 1, 1, 8),
+    /* 9*/ NB200_T1_VARIANT(1, 2, 1, 8),
+    /*10*/ NB200_T1_VARIANT(1, 4, 1, 8),
+    /*11*/ NB200_T1_VARIANT(1, 8, 1, 8),
+    /*12*/ NB200_T1_VARIANT(1, 16, 1, 8),
+    /*13*/ NB200_T1_VARIANT(1, 32, 1, 8),
+    /*14*/ NB200_T1_VARIANT(1, 32, 2, 8),
+    /*15*/ NB200_T1_VARIANT(1, 32, 4, 8),
+    /*16*/ NB200_T1_VARIANT(1, 32, 8, 8),
+    // alternatives (same coverage, different warp decomposition)
+    /*17*/ NB200_T1_VARIANT(2, 8, 2, 8),
+    /*18*/ NB200_T1_VARIANT(2, 8, 2, 16),
+    /*19*/ NB200_T1_VARIANT(2, 4, 4, 16),
+    /*20*/ NB200_T1_VARIANT(2, 16, 1, 12),
+    /*21*/ NB200_T1_VARIANT(2, 4, 2, 16),
+    /*22*/ NB200_T1_VARIANT(2, 2, 4, 16),
+};
+constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
+constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
+
+struct t1_plan
+{
+    int     variant{-1};
+    int     grid{0};
+    int     rows_per_group{0};
+    int     rows_per_stage{0};
+    int     stages{0};
+    int     stage_stride{0};
+    int     y_offset{0};
+    int     smem_bytes{0};
+    int64_t num_tiles{0};
+};
+
+int env_int(const char* name, const int fallback)
+{
+    const char* value = std::getenv(name);
+    return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
+}
+
+// Shared-memory geometry of variant `v` for a (N, D) problem; false if it cannot cover D or does not fit.
+bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, const int smem_optin, t1_plan& plan)
+{
+    const t1_variant& var = kT1Variants[v];
+    if (var.V == 2 && (D % 2) != 0)
+    {
+        return false;
+    }
+    const int64_t capacity = 32LL * var.V * var.KC * var.WS;
+    if (D > capacity)
+    {
+        return false;
+    }
+    const int     NG       = var.NCW / var.WS;
+    const int64_t w_bytes  = round_up(D * 8, 128);
+    const int64_t avail    = static_cast<int64_t>(smem_optin) - kT1HeaderSize - w_bytes;
+    const int64_t row_b    = D * 8;
+    const int64_t target   = env_int("NB200_STAGE_BYTES", 32768);
+    const int     stages_x = env_int("NB200_STAGES", kT1MaxStages);
+
+    int64_t rpg = std::max<int64_t>(1, target / (NG * row_b));
+    if ((NG * rpg) % 2 != 0)
+    {
+        rpg += 1; // tiles must start on 16-byte boundaries for any D
+    }
+    // the epilogue folds [NG][WS*CPW] partial gradients through the stage area
+    const int64_t epilogue = (static_cast<int64_t>(NG) * capacity + 2 * NG) * 8;
+    for (;;)
+    {
+        const int64_t rps      = NG * rpg;
+        const int64_t x_bytes  = round_up(rps * row_b, 128);
+        const int64_t y_bytes  = round_up(rps * 8, 128);
+        const int64_t stride   = x_bytes + y_bytes;
+        int64_t       stages   = std::min<int64_t>(std::min(kT1MaxStages, stages_x), avail / stride);
+        if (stages >= 2 && stages * stride >= epilogue)
+        {
+            plan.variant        = v;
+            plan.rows_per_group = static_cast<int>(rpg);
+            plan.rows_per_stage = static_cast<int>(rps);
+            plan.stages         = static_cast<int>(stages);
+            plan.stage_stride   = static_cast<int>(stride);
+            plan.y_offset       = static_cast<int>(x_bytes);
+            plan.smem_bytes     = static_cast<int>(kT1HeaderSize + w_bytes + stages * stride);
+            plan.num_tiles      = (N + rps - 1) / rps;
+            plan.grid           = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+            return plan.grid > 0;
+        }
+        // shrink the stage (keeping NG * rpg even) until it fits
+        const int64_t step = (NG % 2 == 0) ? 1 : 2;
+        if (rpg <= step)
+        {
+            return false;
+        }
+        rpg -= step;
+        if ((NG * rpg) % 2 != 0)
+        {
+            return false;
+        }
+    }
+}
+} // namespace
+
+struct nb200_obj
+{
+    nb200_data*  data{nullptr};
+    int          device{0};
+    cudaStream_t stream{nullptr};     // the stream every launch and copy of this objective is ordered on
+    cudaStream_t own_stream{nullptr}; // created with the objective; `stream` may be re-pointed at a caller's stream
+    int          loss{0};
+    double       loss_param{0.0};
+    int          flavour{0};
+    double       l1{0.0}, l2{0.0};
+    int64_t      n{0};
+
+    // device scratch
+    double* d_x{nullptr};          // [n] parameters
+    double* d_fixed_bias{nullptr}; // [T] (SYNTH)
+    double* d_out{nullptr};        // [n + 1] gradient, then the function value
+    double* d_reduced{nullptr};    // [1 + T + T*D]
+    double* d_partials{nullptr};   // T1: [grid, D + 2]; generic: forward [blocks, 1 + T]
+    double* d_partials_gw{nullptr}; // generic: [splits, T*D]
+    double* d_dL{nullptr};         // generic: [N, T]
+    // pinned host staging
+    double* h_x{nullptr};
+    double* h_out{nullptr};
+    std::vector<double> fixed_bias;
+
+    // plan
+    bool    use_t1{false};
+    t1_plan t1{};
+    int     gen_blocks{0};
+    int     gen_splits{0};
+    int     gen_smem{0};
+
+    // state of a two-phase evaluation
+    bool    partial_has_grad{false};
+    const double* partial_x{nullptr};
+
+    // statistics
+    int64_t     launches{0};
+    bool        timing{false};
+    bool        pass_pending{false};
+    cudaEvent_t ev0{nullptr}, ev1{nullptr};
+    double      last_pass_ms{-1.0};
+    double      pass_ms_total{0.0};
+    int64_t     pass_count{0};
+};
+
+namespace
+{
+void free_obj(nb200_obj* obj)
+{
+    if (obj == nullptr)
+    {
+        return;
+    }
+    cudaSetDevice(obj->device);
+    cudaFree(obj->d_x);
+    cudaFree(obj->d_fixed_bias);
+    cudaFree(obj->d_out);
+    cudaFree(obj->d_reduced);
+    cudaFree(obj->d_partials);
+    cudaFree(obj->d_partials_gw);
+    cudaFree(obj->d_dL);
+    cudaFreeHost(obj->h_x);
+    cudaFreeHost(obj->h_out);
+    if (obj->ev0 != nullptr)
+    {
+        cudaEventDestroy(obj->ev0);
+    }
+    if (obj->ev1 != nullptr)
+    {
+        cudaEventDestroy(obj->ev1);
+    }
+    if (obj->own_stream != nullptr)
+    {
+        cudaStreamDestroy(obj->own_stream);
+    }
+    if (obj->data != nullptr)
+    {
+        nb200_dataset_release(obj->data);
+    }
+    delete obj;
+}
+
+int setup_plan(nb200_obj* obj, const int forced_variant)
+{
+    const nb200_data* data = obj->data;
+    const int64_t     N = data->N, D = data->D, T = data->T;
+
+    // release the previous plan's scratch
+    cudaFree(obj->d_partials);
+    cudaFree(obj->d_partials_gw);
+    cudaFree(obj->d_dL);
+    obj->d_partials = obj->d_partials_gw = obj->d_dL = nullptr;
+    obj->use_t1 = false;
+
+    const bool force_generic = forced_variant == -2 || env_int("NB200_FORCE_GENERIC", 0) != 0;
+    if (T == 1 && !force_generic && D <= (1 << 20))
+    {
+        t1_plan plan;
+        bool    ok = false;
+        if (forced_variant >= 0)
+        {
+            NB200_REQUIRE(forced_variant < kNumT1Variants, "objective: unknown kernel variant");
+            ok = plan_t1(forced_variant, N, D, data->sm_count, data->smem_optin, plan);
+            NB200_REQUIRE(ok, "objective: the requested kernel variant cannot cover this (N, D)");
+        }
+        else
+        {
+            for (int v = 0; v < kNumT1Heuristic && !ok; ++v)
+            {
+                ok = plan_t1(v, N, D, data->sm_count, data->smem_optin, plan);
+            }
+        }
+        if (ok)
+        {
+            const t1_variant& var = kT1Variants[plan.variant];
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(plan.grid) * (D + 2) * sizeof(double)));
+            obj->t1     = plan;
+            obj->use_t1 = true;
+            return NB200_OK;
+        }
+    }
+
+    // generic path
+    const int64_t smem = (2 * kGenWarps * T + kGenWarps) * 8;
+    if (smem > data->smem_optin)
+    {
+        return fail(NB200_ERR_UNSUPPORTED, "objective: too many targets for the generic forward kernel");
+    }
+    obj->gen_smem   = static_cast<int>(smem);
+    obj->gen_blocks = static_cast<int>(
+        std::max<int64_t>(1, std::min<int64_t>((N + kGenWarps - 1) / kGenWarps, 4LL * data->sm_count)));
+    const int64_t col_tiles = (D + kBwdCols - 1) / kBwdCols;
+    const int64_t t_tiles   = (T + kBwdTB - 1) / kBwdTB;
+    int64_t       splits    = (4LL * data->sm_count + col_tiles * t_tiles - 1) / (col_tiles * t_tiles);
+    splits                  = std::max<int64_t>(1, std::min<int64_t>(splits, std::min<int64_t>(256, (N + 255) / 256)));
+    obj->gen_splits         = static_cast<int>(splits);
+    if (smem > 48 * 1024)
+    {
+        NB200_CUDA_TRY(cudaFuncSetAttribute(gen_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            obj->gen_smem));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(gen_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            obj->gen_smem));
+    }
+    NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(obj->gen_blocks) * (1 + T) * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(splits) * T * D * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
+    return NB200_OK;
+}
+
+int make_objective(nb200_data* data, const int loss, const double loss_param, const int flavour, const double l1,
+                   const double l2, const double* fixed_bias, const int variant, nb200_obj** out_obj)
+{
+    NB200_REQUIRE(data != nullptr && out_obj != nullptr, "objective: null argument");
+    NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "objective: unknown loss");
+    NB200_REQUIRE(flavour == NB200_FLAVOUR_LINEAR || flavour == NB200_FLAVOUR_SYNTH, "objective: unknown flavour");
+    NB200_REQUIRE(flavour != NB200_FLAVOUR_SYNTH || (data->T == 1 && fixed_bias != nullptr),
+                  "objective: the synthetic flavour needs one target and a fixed bias");
+    NB200_REQUIRE(data->N > 0 && data->D > 0 && data->T > 0, "objective: empty dataset");
+
+    NB200_CUDA_TRY(cudaSetDevice(data->device));
+    auto* obj = new (std::nothrow) nb200_obj{};
+    NB200_REQUIRE(obj != nullptr, "objective: out of host memory");
+    nb200_dataset_retain(data);
+    obj->data       = data;
+    obj->device     = data->device;
+    obj->loss       = loss;
+    obj->loss_param = loss_param;
+    obj->flavour    = flavour;
+    obj->l1         = l1;
+    obj->l2         = l2;
+    obj->n          = (flavour == NB200_FLAVOUR_LINEAR) ? (data->D + 1) * data->T : data->D;
+
+    const auto guard = [&](const int status)
+    {
+        if (status != NB200_OK)
+        {
+            const std::string message = g_last_error;
+            free_obj(obj);
+            g_last_error = message;
+        }
+        return status;
+    };
+    const auto alloc = [&]() -> int
+    {
+        const size_t n = static_cast<size_t>(obj->n);
+        NB200_CUDA_TRY(cudaStreamCreateWithFlags(&obj->own_stream, cudaStreamNonBlocking));
+        obj->stream = obj->own_stream;
+        NB200_CUDA_TRY(cudaEventCreate(&obj->ev0));
+        NB200_CUDA_TRY(cudaEventCreate(&obj->ev1));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_x, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_out, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_reduced, static_cast<size_t>(1 + data->T + data->T * data->D) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMemset(obj->d_reduced, 0, static_cast<size_t>(1 + data->T + data->T * data->D) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMallocHost(&obj->h_x, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMallocHost(&obj->h_out, (n + 2) * sizeof(double)));
+        if (flavour == NB200_FLAVOUR_SYNTH)
+        {
+            obj->fixed_bias.assign(fixed_bias, fixed_bias + data->T);
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_fixed_bias, static_cast<size_t>(data->T) * sizeof(double)));
+            NB200_CUDA_TRY(cudaMemcpy(obj->d_fixed_bias, fixed_bias, static_cast<size_t>(data->T) * sizeof(double),
+                                      cudaMemcpyHostToDevice));
+        }
+        return setup_plan(obj, variant);
+    };
+    const int status = guard(alloc());
+    if (status == NB200_OK)
+    {
+        *out_obj = obj;
+    }
+    return status;
+}
+
+// enqueue the pass over X: leaves [sum loss | sum dL | sum dL x^T] (un-normalised) in obj->d_reduced
+int enqueue_partial(nb200_obj* obj, const double* x_dev, const bool want_grad)
+{
+    const nb200_data* data = obj->data;
+    const int64_t     N = data->N, D = data->D, T = data->T;
+    const double*     W    = x_dev;
+    const double*     bias = (obj->flavour == NB200_FLAVOUR_LINEAR) ? (x_dev + T * D) : obj->d_fixed_bias;
+
+    if (obj->timing)
+    {
+        NB200_CUDA_TRY(cudaEventRecord(obj->ev0, obj->stream));
+    }
+
+    if (obj->use_t1)
+    {
+        const t1_variant& var = kT1Variants[obj->t1.variant];
+        t1_params         p{};
+        p.X              = data->X;
+        p.Y              = data->Y;
+        p.w              = W;
+        p.bias           = bias;
+        p.partials       = obj->d_partials;
+        p.N              = N;
+        p.num_tiles      = obj->t1.num_tiles;
+        p.D              = static_cast<int>(D);
+        p.rows_per_stage = obj->t1.rows_per_stage;
+        p.rows_per_group = obj->t1.rows_per_group;
+        p.stages         = obj->t1.stages;
+        p.stage_stride   = obj->t1.stage_stride;
+        p.y_offset       = obj->t1.y_offset;
+        p.loss           = obj->loss;
+        p.loss_param     = obj->loss_param;
+
+        const dim3 block((var.NCW + 1) * 32);
+        (want_grad ? var.grad : var.value)<<<obj->t1.grid, block, obj->t1.smem_bytes, obj->stream>>>(p);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        if (obj->timing)
+        {
+            NB200_CUDA_TRY(cudaEventRecord(obj->ev1, obj->stream));
+        }
+
+        const int64_t cols = want_grad ? (D + 2) : 2;
+        reduce_partials_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials, obj->t1.grid, D + 2, cols, obj->d_reduced);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+    }
+    else
+    {
+        gen_params p{};
+        p.X           = data->X;
+        p.Y           = data->Y;
+        p.W           = W;
+        p.b           = bias;
+        p.dL          = want_grad ? obj->d_dL : nullptr;
+        p.partials_fb = obj->d_partials;
+        p.N           = N;
+        p.D           = D;
+        p.T           = T;
+        p.loss        = obj->loss;
+        p.loss_param  = obj->loss_param;
+        if (want_grad)
+        {
+            gen_forward_kernel<true><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
+        }
+        else
+        {
+            gen_forward_kernel<false><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
+        }
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        if (want_grad)
+        {
+            const dim3 grid(static_cast<unsigned>((D + kBwdCols - 1) / kBwdCols),
+                            static_cast<unsigned>((T + kBwdTB - 1) / kBwdTB), static_cast<unsigned>(obj->gen_splits));
+            gen_backward_kernel<<<grid, kBwdCols, 0, obj->stream>>>(data->X, obj->d_dL, N, D, T, obj->d_partials_gw);
+            NB200_CUDA_TRY(cudaGetLastError());
+            obj->launches += 1;
+        }
+        if (obj->timing)
+        {
+            NB200_CUDA_TRY(cudaEventRecord(obj->ev1, obj->stream));
+        }
+
+        const int64_t cols_fb = want_grad ? (1 + T) : 1;
+        reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials, obj->gen_blocks, 1 + T, cols_fb, obj->d_reduced);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        if (want_grad)
+        {
+            reduce_partials_kernel<<<static_cast<unsigned>((T * D + 127) / 128), 128, 0, obj->stream>>>(
+                obj->d_partials_gw, obj->gen_splits, T * D, T * D, obj->d_reduced + 1 + T);
+            NB200_CUDA_TRY(cudaGetLastError());
+            obj->launches += 1;
+        }
+    }
+    obj->pass_pending = obj->timing;
+    return NB200_OK;
+}
+
+int enqueue_finish(nb200_obj* obj, const double* x_dev, const int64_t n_global, double* gx_dev, double* fx_dev)
+{
+    finish_params p{};
+    p.reduced  = obj->d_reduced;
+    p.x        = x_dev;
+    p.gx       = gx_dev;
+    p.fx       = fx_dev;
+    p.D        = obj->data->D;
+    p.T        = obj->data->T;
+    p.n_global = n_global;
+    p.flavour  = obj->flavour;
+    p.l1       = obj->l1;
+    p.l2       = obj->l2;
+    const int64_t blocks = (gx_dev != nullptr) ? (obj->n + 255) / 256 : 1;
+    finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, obj->stream>>>(p);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    return NB200_OK;
+}
+
+void collect_timing(nb200_obj* obj)
+{
+    if (obj->pass_pending)
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, obj->ev0, obj->ev1) == cudaSuccess)
+        {
+            obj->last_pass_ms = ms;
+            obj->pass_ms_total += ms;
+            obj->pass_count += 1;
+        }
+        obj->pass_pending = false;
+    }
+}
+
+int upload_x(nb200_obj* obj, const double* x, const int64_t n)
+{
+    NB200_REQUIRE(n == obj->n, "function: invalid input size, expecting (" + std::to_string(obj->n) + ",), got (" +
+                                   std::to_string(n) + ",) instead!");
+    std::memcpy(obj->h_x, x, static_cast<size_t>(n) * sizeof(double));
+    NB200_CUDA_TRY(cudaMemcpyAsync(obj->d_x, obj->h_x, static_cast<size_t>(n) * sizeof(double),
+                                   cudaMemcpyHostToDevice, obj->stream));
+    return NB200_OK;
+}
+
+int download_result(nb200_obj* obj, double* gx, double* fx)
+{
+    const size_t n = static_cast<size_t>(obj->n);
+    if (gx != nullptr)
+    {
+        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out, obj->d_out, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost,
+                                       obj->stream));
+    }
+    else
+    {
+        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out + n, obj->d_out + n, sizeof(double), cudaMemcpyDeviceToHost,
+                                       obj->stream));
+    }
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    collect_timing(obj);
+    if (gx != nullptr)
+    {
+        std::memcpy(gx, obj->h_out, n * sizeof(double));
+    }
+    *fx = obj->h_out[n];
+    return NB200_OK;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* nb200_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+const char* nb200_version(void)
+{
+    return "0.1.0";
+}
+
+int nb200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+int nb200_init(const int device, nb200_ctx** out_ctx)
+{
+    NB200_REQUIRE(out_ctx != nullptr, "init: null argument");
+    int count = 0;
+    NB200_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (count <= 0)
+    {
+        return fail(NB200_ERR_CUDA, "init: no CUDA device is visible; libnb200 has no CPU fallback");
+    }
+    NB200_REQUIRE(device >= 0 && device < count, "init: invalid device index");
+    NB200_CUDA_TRY(cudaSetDevice(device));
+
+    cudaDeviceProp prop{};
+    NB200_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        return fail(NB200_ERR_CUDA, std::string("init: libnb200 is built for sm_100a (B200) only, found ") + prop.name);
+    }
+
+    auto* ctx = new (std::nothrow) nb200_ctx{};
+    NB200_REQUIRE(ctx != nullptr, "init: out of host memory");
+    ctx->device     = device;
+    ctx->sm_count   = prop.multiProcessorCount;
+    ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    const cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess)
+    {
+        delete ctx;
+        return fail(NB200_ERR_CUDA, std::string("init: cannot create a stream: ") + cudaGetErrorString(err));
+    }
+    *out_ctx = ctx;
+    return NB200_OK;
+}
+
+void nb200_ctx_release(nb200_ctx* ctx)
+{
+    if (ctx != nullptr)
+    {
+        cudaSetDevice(ctx->device);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    }
+}
+
+static int alloc_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const int64_t T, nb200_data** out_data)
+{
+    NB200_REQUIRE(ctx != nullptr && out_data != nullptr, "dataset: null argument");
+    NB200_REQUIRE(N > 0 && D > 0 && T > 0, "dataset: sizes must be positive");
+    NB200_REQUIRE(D < (1LL << 31) && T < (1LL << 31), "dataset: too many columns");
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+
+    auto* data = new (std::nothrow) nb200_data{};
+    NB200_REQUIRE(data != nullptr, "dataset: out of host memory");
+    data->device     = ctx->device;
+    data->sm_count   = ctx->sm_count;
+    data->smem_optin = ctx->smem_optin;
+    data->N          = N;
+    data->D          = D;
+    data->T          = T;
+    const size_t      x_bytes = static_cast<size_t>(N) * D * sizeof(double);
+    const size_t      y_bytes = static_cast<size_t>(N) * T * sizeof(double);
+    constexpr size_t  slack   = 256;
+    cudaError_t       err     = cudaMalloc(&data->X, x_bytes + slack);
+    if (err == cudaSuccess)
+    {
+        err = cudaMalloc(&data->Y, y_bytes + slack);
+    }
+    if (err == cudaSuccess)
+    {
+        err = cudaMemset(reinterpret_cast<unsigned char*>(data->X) + x_bytes, 0, slack);
+    }
+    if (err == cudaSuccess)
+    {
+        err = cudaMemset(reinterpret_cast<unsigned char*>(data->Y) + y_bytes, 0, slack);
+    }
+    if (err != cudaSuccess)
+    {
+        cudaFree(data->X);
+        cudaFree(data->Y);
+        delete data;
+        return fail(NB200_ERR_CUDA, std::string("dataset: cannot allocate HBM: ") + cudaGetErrorString(err));
+    }
+    *out_data = data;
+    return NB200_OK;
+}
+
+int nb200_dataset_pin(nb200_ctx* ctx, const double* X, const double* Y, const int64_t N, const int64_t D,
+                      const int64_t T, nb200_data** out_data)
+{
+    NB200_REQUIRE(X != nullptr && Y != nullptr, "dataset: null inputs or targets");
+    nb200_data* data   = nullptr;
+    const int   status = alloc_dataset(ctx, N, D, T, &data);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    cudaError_t err = cudaMemcpy(data->X, X, static_cast<size_t>(N) * D * sizeof(double), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+    {
+        err = cudaMemcpy(data->Y, Y, static_cast<size_t>(N) * T * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (err != cudaSuccess)
+    {
+        nb200_dataset_release(data);
+        return fail(NB200_ERR_CUDA, std::string("dataset: host to device copy failed: ") + cudaGetErrorString(err));
+    }
+    *out_data = data;
+    return NB200_OK;
+}
+
+int nb200_dataset_synth(nb200_ctx* ctx, const uint64_t seed, const int synth_kind, const int64_t N, const int64_t D,
+                        const int64_t T, const int64_t row_offset, const double noise, nb200_data** out_data)
+{
+    NB200_REQUIRE(synth_kind >= 0 && synth_kind <= 2, "dataset: unknown synthetic kind");
+    NB200_REQUIRE(synth_kind == NB200_SYNTH_MULTICLASS ? T >= 2 : T == 1,
+                  "dataset: classification/regression are single-target, multiclass needs T >= 2");
+    NB200_REQUIRE(row_offset >= 0, "dataset: negative row offset");
+    nb200_data* data   = nullptr;
+    int         status = alloc_dataset(ctx, N, D, T, &data);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    double*    W   = nullptr;
+    double*    b   = nullptr;
+    const auto run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&W, static_cast<size_t>(T) * D * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&b, static_cast<size_t>(T) * sizeof(double)));
+        const int blocks = ctx->sm_count * 8;
+        synth_inputs_kernel<<<blocks, 256, 0, ctx->stream>>>(seed, N, D, row_offset, data->X);
+        NB200_CUDA_TRY(cudaGetLastError());
+        synth_weights_kernel<<<static_cast<unsigned>((T * D + 255) / 256), 256, 0, ctx->stream>>>(seed, D, T, W, b);
+        NB200_CUDA_TRY(cudaGetLastError());
+        predict_kernel<<<blocks, 256, 0, ctx->stream>>>(data->X, W, b, N, D, T, data->Y);
+        NB200_CUDA_TRY(cudaGetLastError());
+        synth_targets_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, ctx->stream>>>(seed, synth_kind, N, T,
+                                                                                               row_offset, noise, data->Y);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    };
+    status = run();
+    cudaFree(W);
+    cudaFree(b);
+    if (status != NB200_OK)
+    {
+        const std::string message = g_last_error;
+        nb200_dataset_release(data);
+        g_last_error = message;
+        return status;
+    }
+    *out_data = data;
+    return NB200_OK;
+}
+
+int nb200_dataset_read(const nb200_data* data, const int64_t row0, const int64_t rows, double* X, double* Y)
+{
+    NB200_REQUIRE(data != nullptr, "dataset: null argument");
+    NB200_REQUIRE(row0 >= 0 && rows >= 0 && row0 + rows <= data->N, "dataset: row range out of bounds");
+    NB200_CUDA_TRY(cudaSetDevice(data->device));
+    if (X != nullptr && rows > 0)
+    {
+        NB200_CUDA_TRY(cudaMemcpy(X, data->X + row0 * data->D, static_cast<size_t>(rows) * data->D * sizeof(double),
+                                  cudaMemcpyDeviceToHost));
+    }
+    if (Y != nullptr && rows > 0)
+    {
+        NB200_CUDA_TRY(cudaMemcpy(Y, data->Y + row0 * data->T, static_cast<size_t>(rows) * data->T * sizeof(double),
+                                  cudaMemcpyDeviceToHost));
+    }
+    return NB200_OK;
+}
+
+int64_t nb200_dataset_samples(const nb200_data* data)
+{
+    return data != nullptr ? data->N : 0;
+}
+
+int64_t nb200_dataset_inputs(const nb200_data* data)
+{
+    return data != nullptr ? data->D : 0;
+}
+
+int64_t nb200_dataset_targets(const nb200_data* data)
+{
+    return data != nullptr ? data->T : 0;
+}
+
+void nb200_dataset_retain(nb200_data* data)
+{
+    if (data != nullptr)
+    {
+        data->refs.fetch_add(1, std::memory_order_relaxed);
+    }
+}
+
+void nb200_dataset_release(nb200_data* data)
+{
+    if (data != nullptr && data->refs.fetch_sub(1, std::memory_order_acq_rel) == 1)
+    {
+        cudaSetDevice(data->device);
+        cudaFree(data->X);
+        cudaFree(data->Y);
+        delete data;
+    }
+}
+
+int nb200_objective_create(nb200_data* data, const int loss, const double loss_param, const int flavour,
+                           const double l1, const double l2, const double* fixed_bias, nb200_obj** out_obj)
+{
+    return make_objective(data, loss, loss_param, flavour, l1, l2, fixed_bias, -1, out_obj);
+}
+
+int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj)
+{
+    NB200_REQUIRE(obj != nullptr && out_obj != nullptr, "objective: null argument");
+    const int status = make_objective(obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
+                                      obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
+                                      obj->use_t1 ? obj->t1.variant : -2, out_obj);
+    if (status == NB200_OK)
+    {
+        (*out_obj)->timing = obj->timing;
+    }
+    return status;
+}
+
+void nb200_objective_release(nb200_obj* obj)
+{
+    free_obj(obj);
+}
+
+int64_t nb200_objective_size(const nb200_obj* obj)
+{
+    return obj != nullptr ? obj->n : 0;
+}
+
+int nb200_vgrad(nb200_obj* obj, const double* x, const int64_t n, double* gx, double* fx)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    int status = upload_x(obj, x, n);
+    if (status == NB200_OK)
+    {
+        status = enqueue_partial(obj, obj->d_x, gx != nullptr);
+    }
+    if (status == NB200_OK)
+    {
+        status = enqueue_finish(obj, obj->d_x, obj->data->N, gx != nullptr ? obj->d_out : nullptr, obj->d_out + obj->n);
+    }
+    if (status == NB200_OK)
+    {
+        status = download_result(obj, gx, fx);
+    }
+    return status;
+}
+
+int nb200_vgrad_device(nb200_obj* obj, const double* x_dev, const int64_t n, double* gx_dev, double* fx_dev)
+{
+    NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
+    NB200_REQUIRE(n == obj->n, "function: invalid input size");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    int status = enqueue_partial(obj, x_dev, gx_dev != nullptr);
+    if (status == NB200_OK)
+    {
+        status = enqueue_finish(obj, x_dev, obj->data->N, gx_dev, fx_dev);
+    }
+    return status;
+}
+
+int nb200_objective_sync(nb200_obj* obj)
+{
+    NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    collect_timing(obj);
+    return NB200_OK;
+}
+
+int nb200_vgrad_partial(nb200_obj* obj, const double* x, const int64_t n, const int want_grad,
+                        double** out_partial_dev, int64_t* out_partial_len)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && out_partial_dev != nullptr && out_partial_len != nullptr,
+                  "function: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    int status = upload_x(obj, x, n);
+    if (status == NB200_OK)
+    {
+        status = enqueue_partial(obj, obj->d_x, want_grad != 0);
+    }
+    if (status == NB200_OK)
+    {
+        obj->partial_has_grad = want_grad != 0;
+        *out_partial_dev      = obj->d_reduced;
+        *out_partial_len      = 1 + obj->data->T + obj->data->T * obj->data->D;
+    }
+    return status;
+}
+
+int nb200_vgrad_finish(nb200_obj* obj, const int64_t n_global, double* gx, double* fx)
+{
+    NB200_REQUIRE(obj != nullptr && fx != nullptr, "function: null argument");
+    NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
+    NB200_REQUIRE(gx == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    int status = enqueue_finish(obj, obj->d_x, n_global, gx != nullptr ? obj->d_out : nullptr, obj->d_out + obj->n);
+    if (status == NB200_OK)
+    {
+        status = download_result(obj, gx, fx);
+    }
+    return status;
+}
+
+int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, const int64_t n, const int want_grad,
+                               double** out_partial_dev, int64_t* out_partial_len)
+{
+    NB200_REQUIRE(obj != nullptr && x_dev != nullptr && out_partial_dev != nullptr && out_partial_len != nullptr,
+                  "function: null argument");
+    NB200_REQUIRE(n == obj->n, "function: invalid input size");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    const int status = enqueue_partial(obj, x_dev, want_grad != 0);
+    if (status == NB200_OK)
+    {
+        obj->partial_has_grad = want_grad != 0;
+        *out_partial_dev      = obj->d_reduced;
+        *out_partial_len      = 1 + obj->data->T + obj->data->T * obj->data->D;
+    }
+    return status;
+}
+
+int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, const int64_t n_global, double* gx_dev,
+                              double* fx_dev)
+{
+    NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
+    NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
+    NB200_REQUIRE(gx_dev == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    return enqueue_finish(obj, x_dev, n_global, gx_dev, fx_dev);
+}
+
+void* nb200_objective_stream(const nb200_obj* obj)
+{
+    return obj != nullptr ? static_cast<void*>(obj->stream) : nullptr;
+}
+
+int nb200_objective_set_stream(nb200_obj* obj, void* stream)
+{
+    NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    obj->stream = (stream != nullptr) ? static_cast<cudaStream_t>(stream) : obj->own_stream;
+    return NB200_OK;
+}
+
+int64_t nb200_objective_launches(const nb200_obj* obj)
+{
+    return obj != nullptr ? obj->launches : 0;
+}
+
+int nb200_objective_enable_timing(nb200_obj* obj, const int enabled)
+{
+    NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    obj->timing = enabled != 0;
+    return NB200_OK;
+}
+
+double nb200_objective_last_pass_ms(nb200_obj* obj)
+{
+    if (obj == nullptr)
+    {
+        return -1.0;
+    }
+    if (obj->pass_pending)
+    {
+        cudaSetDevice(obj->device);
+        if (cudaStreamSynchronize(obj->stream) != cudaSuccess)
+        {
+            return -1.0;
+        }
+        collect_timing(obj);
+    }
+    return obj->last_pass_ms;
+}
+
+int nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count, const int reset)
+{
+    NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    if (total_ms != nullptr)
+    {
+        *total_ms = obj->pass_ms_total;
+    }
+    if (count != nullptr)
+    {
+        *count = obj->pass_count;
+    }
+    if (reset != 0)
+    {
+        obj->pass_ms_total = 0.0;
+        obj->pass_count    = 0;
+    }
+    return NB200_OK;
+}
+
+int nb200_objective_set_variant(nb200_obj* obj, const int variant)
+{
+    NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    return setup_plan(obj, variant);
+}
+
+int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t size)
+{
+    NB200_REQUIRE(obj != nullptr && buffer != nullptr && size > 0, "objective: null argument");
+    std::string text;
+    if (obj->use_t1)
+    {
+        const t1_variant& var = kT1Variants[obj->t1.variant];
+        text = "t1 variant=" + std::to_string(obj->t1.variant) + " V=" + std::to_string(var.V) +
+               " KC=" + std::to_string(var.KC) + " WS=" + std::to_string(var.WS) + " NCW=" + std::to_string(var.NCW) +
+               " grid=" + std::to_string(obj->t1.grid) + " rows_per_stage=" + std::to_string(obj->t1.rows_per_stage) +
+               " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
+               " smem=" + std::to_string(obj->t1.smem_bytes);
+    }
+    else
+    {
+        text = "generic blocks=" + std::to_string(obj->gen_blocks) + " splits=" + std::to_string(obj->gen_splits) +
+               " smem=" + std::to_string(obj->gen_smem);
+    }
+    std::strncpy(buffer, text.c_str(), static_cast<size_t>(size) - 1);
+    buffer[size - 1] = '\0';
+    return NB200_OK;
+}
+
+int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const double* b, double* outputs)
+{
+    NB200_REQUIRE(ctx != nullptr && data != nullptr && W != nullptr && b != nullptr && outputs != nullptr,
+                  "predict: null argument");
+    NB200_REQUIRE(ctx->device == data->device, "predict: context and dataset live on different devices");
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t N = data->N, D = data->D, T = data->T;
+    double *      dW = nullptr, *db = nullptr, *dO = nullptr;
+    const auto    run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&dW, static_cast<size_t>(T) * D * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&db, static_cast<size_t>(T) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&dO, static_cast<size_t>(N) * T * sizeof(double)));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dW, W, static_cast<size_t>(T) * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        NB200_CUDA_TRY(cudaMemcpyAsync(db, b, static_cast<size_t>(T) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        predict_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(data->X, dW, db, N, D, T, dO);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaMemcpyAsync(outputs, dO, static_cast<size_t>(N) * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(dW);
+    cudaFree(db);
+    cudaFree(dO);
+    return status;
+}
+
+static int loss_rows(nb200_ctx* ctx, const int loss, const double loss_param, const double* targets,
+                     const double* outputs, const int64_t N, const int64_t T, double* values, double* vgrads)
+{
+    NB200_REQUIRE(ctx != nullptr && targets != nullptr && outputs != nullptr, "loss: null argument");
+    NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "loss: unknown loss");
+    NB200_REQUIRE(N >= 0 && T > 0, "loss: invalid dimensions");
+    if (N == 0)
+    {
+        return NB200_OK;
+    }
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t bytes = static_cast<size_t>(N) * T * sizeof(double);
+    double *     dT = nullptr, *dO = nullptr, *dV = nullptr, *dG = nullptr;
+    const auto   run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&dT, bytes));
+        NB200_CUDA_TRY(cudaMalloc(&dO, bytes));
+        if (values != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMalloc(&dV, static_cast<size_t>(N) * sizeof(double)));
+        }
+        if (vgrads != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMalloc(&dG, bytes));
+        }
+        NB200_CUDA_TRY(cudaMemcpyAsync(dT, targets, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dO, outputs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        loss_rows_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, ctx->stream>>>(loss, loss_param, dT, dO, N,
+                                                                                           T, dV, dG);
+        NB200_CUDA_TRY(cudaGetLastError());
+        if (values != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMemcpyAsync(values, dV, static_cast<size_t>(N) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (vgrads != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMemcpyAsync(vgrads, dG, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(dT);
+    cudaFree(dO);
+    cudaFree(dV);
+    cudaFree(dG);
+    return status;
+}
+
+int nb200_loss_value(nb200_ctx* ctx, const int loss, const double loss_param, const double* targets,
+                     const double* outputs, const int64_t N, const int64_t T, double* values)
+{
+    NB200_REQUIRE(values != nullptr, "loss: null value buffer");
+    return loss_rows(ctx, loss, loss_param, targets, outputs, N, T, values, nullptr);
+}
+
+int nb200_loss_vgrad(nb200_ctx* ctx, const int loss, const double loss_param, const double* targets,
+                     const double* outputs, const int64_t N, const int64_t T, double* vgrads)
+{
+    NB200_REQUIRE(vgrads != nullptr, "loss: null gradient buffer");
+    return loss_rows(ctx, loss, loss_param, targets, outputs, N, T, nullptr, vgrads);
+}
+
+int nb200_synth_linear_inputs(const int64_t samples, const int64_t inputs, const uint64_t seed, const int64_t modulo,
+                              double* X, double* wopt, double* bopt)
+{
+    NB200_REQUIRE(samples > 0 && inputs > 0 && modulo > 0, "synthetic model: sizes must be positive");
+    NB200_REQUIRE(X != nullptr && wopt != nullptr && bopt != nullptr, "synthetic model: null argument");
+    std::mt19937_64                        rng(seed);
+    std::uniform_real_distribution<double> udist(0.0, 1.0);
+    for (int64_t k = 0; k < samples * inputs; ++k)
+    {
+        X[k] = udist(rng);
+    }
+    for (int64_t j = 0; j < inputs; ++j)
+    {
+        wopt[j] = udist(rng);
+    }
+    *bopt = udist(rng) - 0.5;
+
+    double sum = 0.0;
+    for (int64_t j = 0; j < inputs; ++j)
+    {
+        sum += wopt[j];
+    }
+    for (int64_t j = 0; j < inputs; ++j)
+    {
+        wopt[j] = (j % modulo != 0) ? 0.0 : wopt[j] / sum;
+    }
+    return NB200_OK;
+}
+
+} // extern "C"

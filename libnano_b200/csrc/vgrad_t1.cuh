@@ -1,0 +1,307 @@
+// vgrad_t1.cuh — the hot kernel: ONE pass over X for a single-target linear model.
+//
+// Replaces, for T == 1, the per-batch body of linear::function_t::do_eval (src/linear/function.cpp:53-72):
+//   predict (src/linear/util.cpp:19-20)  o_i = x_i . w + b
+//   loss value + vgrad (flatten.h:69-86) l_i, dL_i
+//   accumulation (function.cpp:62,69-70) sum l_i ; sum dL_i ; sum dL_i * x_i
+// and likewise linear_model_t::eval (src/function/mlearn/linear.h:21-38, two passes over X in the reference).
+//
+// Design (HBM-bound: 8 bytes of X per 4 flops):
+//   * persistent CTAs (one per SM), static round-robin tiles of RPS consecutive rows => fixed summation order;
+//   * a producer warp streams tiles into a ring of shared-memory stages with 1-D bulk async copies
+//     (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP) — rows are contiguous, so a tile is one flat copy;
+//   * consumer warps own rows: 128-bit conflict-free LDS of the row into REGISTERS, dot with w (shared memory),
+//     butterfly all-reduce, loss + dL in registers, then dL * x is accumulated into per-lane column slices — X is
+//     read from shared memory exactly once and from HBM exactly once;
+//   * the stage is released as soon as its rows sit in registers, before the loss math;
+//   * per-CTA partials [loss | gb | gW] are reduced across the grid by a second, fixed-order kernel (reduce.cuh).
+//
+// Template knobs: V = doubles per lane per 32-lane chunk (2 => 128-bit loads, needs even D; 1 => any D),
+// KC = chunks per warp (a warp covers 32*V*KC columns), WS = warps cooperating on one row (row split in WS
+// column slices), GRAD = accumulate the gradient (false: value-only call, function(x) without gx).
+#pragma once
+
+#include "common.cuh"
+#include "loss.cuh"
+
+namespace nb200
+{
+constexpr int kT1MaxStages  = 8;
+constexpr int kT1HeaderSize = 1024; // barriers + dot-exchange slots
+
+struct t1_params
+{
+    const double* X;        // [N, D] row-major, padded by >= 16 bytes at the end
+    const double* Y;        // [N], padded likewise
+    const double* w;        // [D] device
+    const double* bias;     // 1 double, device
+    double*       partials; // [grid, D + 2] : [loss sum | dL sum | dL*x sums]
+    int64_t       N;
+    int64_t       num_tiles;
+    int           D;
+    int           rows_per_stage; // RPS: even, = (NCW / WS) * rows_per_group
+    int           rows_per_group; // rows each warp-group handles per stage
+    int           stages;
+    int           stage_stride; // bytes between stages (multiple of 128)
+    int           y_offset;     // byte offset of the Y tile inside a stage (multiple of 128)
+    int           loss;
+    double        loss_param;
+};
+
+#ifdef __CUDACC__
+
+template <int V, int KC, int WS, int NCW, bool GRAD>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_params p)
+{
+    static_assert(V == 1 || V == 2, "V is 1 (64-bit loads) or 2 (128-bit loads)");
+    static_assert(NCW % WS == 0, "consumer warps must split evenly into row groups");
+    constexpr int NG  = NCW / WS; // row groups
+    constexpr int CPW = 32 * V * KC; // columns per warp
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + kT1MaxStages;
+    double*   exchange  = reinterpret_cast<double*>(smem + 2 * kT1MaxStages * sizeof(uint64_t)); // [NG][2][WS]
+    const int w_bytes   = static_cast<int>((static_cast<int64_t>(p.D) * 8 + 127) / 128 * 128);
+    double*   w_s       = reinterpret_cast<double*>(smem + kT1HeaderSize);
+    unsigned char* stage_base = smem + kT1HeaderSize + w_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int D    = p.D;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < p.stages; ++s)
+        {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, NCW);
+        }
+        mbar_fence_init();
+    }
+    for (int j = threadIdx.x; j < D; j += blockDim.x)
+    {
+        w_s[j] = p.w[j];
+    }
+    __syncthreads();
+
+    const int64_t rps = p.rows_per_stage;
+
+    if (warp == NCW)
+    {
+        // ===== producer warp: one lane feeds the ring =====
+        if (lane == 0)
+        {
+            const uint64_t policy = l2_policy_evict_first();
+            int            it     = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
+            {
+                const int      s     = it % p.stages;
+                const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+                mbar_wait(empty_bar + s, phase ^ 1u); // passes at once on the first lap
+
+                const int64_t  row0    = tile * rps;
+                const int64_t  rows    = min(rps, p.N - row0);
+                const uint32_t bytes_x = static_cast<uint32_t>((rows * D * 8 + 15) / 16 * 16);
+                const uint32_t bytes_y = static_cast<uint32_t>((rows * 8 + 15) / 16 * 16);
+                unsigned char* stage   = stage_base + static_cast<int64_t>(s) * p.stage_stride;
+
+                mbar_arrive_expect_tx(full_bar + s, bytes_x + bytes_y);
+                bulk_copy_g2s(stage, p.X + row0 * D, bytes_x, full_bar + s, policy);
+                bulk_copy_g2s(stage + p.y_offset, p.Y + row0, bytes_y, full_bar + s, policy);
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int group = warp / WS;          // which rows of a stage
+    const int slice = warp % WS;          // which columns of a row
+    const int cbase = slice * CPW;        // first column of this warp's slice
+
+    double g[V * KC];  // per-lane slice of sum dL_i * x_i
+#pragma unroll
+    for (int k = 0; k < V * KC; ++k)
+    {
+        g[k] = 0.0;
+    }
+    double fsum = 0.0, gbsum = 0.0;
+
+    const double bias = *p.bias;
+    const int    rpg  = p.rows_per_group;
+
+    int it       = 0;
+    int exparity = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
+    {
+        const int      s     = it % p.stages;
+        const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+        mbar_wait(full_bar + s, phase);
+
+        const unsigned char* stage = stage_base + static_cast<int64_t>(s) * p.stage_stride;
+        const double*        xs    = reinterpret_cast<const double*>(stage);
+        const double*        ys    = reinterpret_cast<const double*>(stage + p.y_offset);
+
+        const int rows  = static_cast<int>(min(rps, p.N - tile * rps));
+        const int first = group * rpg;
+        const int count = max(0, min(rpg, rows - first)); // rows of this stage owned by this warp group
+
+        if (count == 0)
+        {
+            if (lane == 0)
+            {
+                mbar_arrive(empty_bar + s);
+            }
+            continue;
+        }
+
+        for (int i = 0; i < count; ++i)
+        {
+            const int     r   = first + i;
+            const double* row = xs + static_cast<int64_t>(r) * D;
+
+            // row slice -> registers; partial dot with w
+            double x[V * KC];
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+            {
+                const int col = cbase + (k * 32 + lane) * V;
+                if constexpr (V == 2)
+                {
+                    double2 xv = make_double2(0.0, 0.0), wv = make_double2(0.0, 0.0);
+                    if (col < D)
+                    {
+                        xv = *reinterpret_cast<const double2*>(row + col);
+                        wv = *reinterpret_cast<const double2*>(w_s + col);
+                    }
+                    x[2 * k]     = xv.x;
+                    x[2 * k + 1] = xv.y;
+                    acc0         = fma(xv.x, wv.x, acc0);
+                    acc1         = fma(xv.y, wv.y, acc1);
+                }
+                else
+                {
+                    double xv = 0.0, wv = 0.0;
+                    if (col < D)
+                    {
+                        xv = row[col];
+                        wv = w_s[col];
+                    }
+                    x[k] = xv;
+                    if (k & 1)
+                    {
+                        acc1 = fma(xv, wv, acc1);
+                    }
+                    else
+                    {
+                        acc0 = fma(xv, wv, acc0);
+                    }
+                }
+            }
+            const double y = ys[r];
+
+            // the stage can be refilled as soon as the last row this warp owns is in registers
+            if (i == count - 1)
+            {
+                __syncwarp();
+                if (lane == 0)
+                {
+                    mbar_arrive(empty_bar + s);
+                }
+            }
+
+            double dot = warp_allreduce_sum(acc0 + acc1);
+            if constexpr (WS > 1)
+            {
+                // combine the column slices of the WS warps sharing this row, in slice order
+                double* slot = exchange + (group * 2 + exparity) * WS;
+                if (lane == 0)
+                {
+                    slot[slice] = dot;
+                }
+                named_bar_sync(1 + group, WS * 32);
+                dot = 0.0;
+#pragma unroll
+                for (int q = 0; q < WS; ++q)
+                {
+                    dot += slot[q];
+                }
+                exparity ^= 1;
+            }
+
+            // predict + loss + dL, identical on every lane (src/linear/util.cpp:19-20: product first, then + bias)
+            const double o = dot + bias;
+            double       term, dl;
+            loss_term<GRAD>(p.loss, p.loss_param, y, o, term, dl);
+            fsum += loss_post(p.loss, term);
+
+            if constexpr (GRAD)
+            {
+                gbsum += dl;
+#pragma unroll
+                for (int k = 0; k < V * KC; ++k)
+                {
+                    g[k] = fma(dl, x[k], g[k]);
+                }
+            }
+        }
+    }
+
+    // ===== epilogue: fixed-order reduction of the row groups inside the CTA, through the (now idle) stages =====
+    named_bar_sync(15, NCW * 32); // every consumer left the main loop; all issued copies have been consumed
+
+    const int dpad = WS * CPW;
+    double*   red  = reinterpret_cast<double*>(stage_base);          // [NG][dpad]
+    double*   redf = red + static_cast<int64_t>(NG) * dpad;          // [NG] loss sums, then [NG] dL sums
+
+    if constexpr (GRAD)
+    {
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+        {
+            const int col = cbase + (k * 32 + lane) * V;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+            {
+                red[static_cast<int64_t>(group) * dpad + col + v] = g[k * V + v];
+            }
+        }
+    }
+    if (slice == 0 && lane == 0)
+    {
+        redf[group]      = fsum;
+        redf[NG + group] = gbsum;
+    }
+    named_bar_sync(15, NCW * 32);
+
+    double* out = p.partials + static_cast<int64_t>(blockIdx.x) * (D + 2);
+    if constexpr (GRAD)
+    {
+        for (int col = threadIdx.x; col < D; col += NCW * 32)
+        {
+            double sum = 0.0;
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+            {
+                sum += red[static_cast<int64_t>(q) * dpad + col];
+            }
+            out[2 + col] = sum;
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        double f = 0.0, b = 0.0;
+#pragma unroll
+        for (int q = 0; q < NG; ++q)
+        {
+            f += redf[q];
+            b += redf[NG + q];
+        }
+        out[0] = f;
+        out[1] = b;
+    }
+}
+
+#endif // __CUDACC__
+} // namespace nb200

@@ -1,0 +1,124 @@
+"""Sample-sharded objective: one process per GPU, rows of (X, Y) split in contiguous blocks, ONE all-reduce of the
+(loss, gradient) vector per evaluation.
+
+The objective is a sum over independent samples; the reference already shards it — across the threads of one
+process: per-thread accumulators (src/linear/function.cpp:51-57) folded by sum_reduce (include/nano/core/reduce.h:
+23-31). Here each rank plays the role of one accumulator:
+
+    phase 1  local pass over the rank's rows      -> un-normalised [sum loss | sum dL | sum dL x^T] in HBM
+    all-reduce (sum) over ranks                    (torch.distributed: NCCL over NVLink on GPUs, gloo in CPU tests)
+    phase 2  / N_global + regularisation           -> (f, g), identical on every rank
+
+No other collective exists on this path: W and b are replicated (<= 1.6 MB), the regularisers are O(T*D).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .function import Function, critical
+
+
+def shard_rows(n_global: int, world_size: int, rank: int):
+    """Contiguous, balanced row blocks: (row0, rows) of `rank`; the first n_global % world_size ranks hold one more."""
+    critical(world_size > 0 and 0 <= rank < world_size, "sharding: invalid rank ", rank, " of ", world_size)
+    base, extra = divmod(int(n_global), int(world_size))
+    rows = base + (1 if rank < extra else 0)
+    row0 = rank * base + min(rank, extra)
+    return row0, rows
+
+
+class _CudaBufferView:
+    """Zero-copy view of a device buffer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, length: int):
+        self.__cuda_array_interface__ = {
+            "shape": (int(length),),
+            "typestr": "<f8",
+            "data": (int(ptr), False),
+            "version": 2,
+            "strides": None,
+        }
+
+
+class DeviceShard:
+    """Adapter of a LinearFunction / SyntheticFunction (the rank's local objective) to the sharded protocol.
+
+    The local objective is re-pointed at torch's current CUDA stream so that phase 1, the NCCL all-reduce and phase 2
+    are ordered on ONE stream without host synchronisation in between."""
+
+    def __init__(self, local):
+        import torch
+
+        self.local = local
+        self._torch = torch
+        self._stream = torch.cuda.current_stream()
+        local.set_stream(self._stream.cuda_stream)
+        self._view = None
+
+    def size(self) -> int:
+        return self.local.size()
+
+    def _view_for(self, ptr: int, length: int):
+        """torch tensor aliasing the objective's reduced-sums buffer (cached: the buffer never moves)."""
+        if self._view is None or self._view[0] != (ptr, length):
+            tensor = self._torch.as_tensor(_CudaBufferView(ptr, length), device=self._torch.device("cuda"))
+            self._view = ((ptr, length), tensor)
+        return self._view[1]
+
+    def partial(self, x, want_grad: bool):
+        ptr, length = self.local.partial(x, want_grad)
+        view = self._view_for(ptr, length)
+        # value-only evaluations leave the gradient entries untouched: reduce [loss | gb] only
+        return view if want_grad else view[: 1 + self.local._dataset.targets]
+
+    def finish(self, n_global: int, gx):
+        return self.local.finish(n_global, gx)
+
+
+class ShardedFunction(Function):
+    """function_t over ALL samples of a dataset whose rows are spread over the ranks of a process group.
+
+    `shard` is the rank-local evaluator (DeviceShard in production; tests drive the same logic with a CPU double
+    over gloo). Every rank must call the function with the same x (the solver state is replicated)."""
+
+    def __init__(self, shard, n_global: int, group=None, type_id: str = "linear", convex=False, smooth=False,
+                 strong_convexity: float = 0.0):
+        import torch.distributed as dist
+
+        super().__init__(type_id, shard.size())
+        critical(n_global > 0, "sharded function: the global sample count must be positive")
+        self._shard = shard
+        self._n_global = int(n_global)
+        self._group = group
+        self._dist = dist
+        self._convex, self._smooth, self._strong_convexity = bool(convex), bool(smooth), float(strong_convexity)
+
+    @classmethod
+    def from_local(cls, local, n_global: int, group=None) -> "ShardedFunction":
+        return cls(DeviceShard(local), n_global, group, local.type_id(), local.convex(), local.smooth(),
+                   local.strong_convexity())
+
+    def world_size(self) -> int:
+        return self._dist.get_world_size(self._group) if self._dist.is_initialized() else 1
+
+    def do_eval(self, x, gx) -> float:
+        buffer = self._shard.partial(x, gx is not None)
+        if self._dist.is_initialized() and self._dist.get_world_size(self._group) > 1:
+            self._dist.all_reduce(buffer, op=self._dist.ReduceOp.SUM, group=self._group)
+        return self._shard.finish(self._n_global, gx)
+
+
+def broadcast_x(x: np.ndarray, src: int = 0, group=None) -> np.ndarray:
+    """Replicate the solver state from `src` (used once at start; iterates stay identical because (f, g) are)."""
+    import torch
+    import torch.distributed as dist
+
+    tensor = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl":
+            tensor = tensor.cuda()
+            dist.broadcast(tensor, src=src, group=group)
+            tensor = tensor.cpu()
+        else:
+            dist.broadcast(tensor, src=src, group=group)
+    return tensor.numpy()

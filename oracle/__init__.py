@@ -1,0 +1,232 @@
+"""CPU ORACLE bindings (ctypes over oracle/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+package. The product (libnano_b200/) never does: it fails loudly when its CUDA library is missing.
+
+Every function here is a thin view of the C++ restatement in oracle.cpp; see oracle.h for the reference
+file:line each one follows and for the list of reference known-answers the oracle is pinned against.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+LOSS_KINDS = {
+    "mse": 0,
+    "mae": 1,
+    "cauchy": 2,
+    "hinge": 3,
+    "squared-hinge": 4,
+    "classnll": 5,
+    "savage": 6,
+    "tangent": 7,
+    "logistic": 8,
+    "exponential": 9,
+    "pinball": 10,
+}
+
+SYNTH_LOSSES = {"mse": 0, "mae": 1, "cauchy": 2, "hinge": 3, "logistic": 4}
+SYNTH_REGRESSION = {"mse": True, "mae": True, "cauchy": True, "hinge": False, "logistic": False}
+
+
+def loss_kind(loss_id: str) -> int:
+    """Map a libnano loss id (src/loss.cpp:105-135) to the oracle's kind: s-/m- prefixes share value/vgrad."""
+    base = loss_id[2:] if loss_id[:2] in ("s-", "m-") else loss_id
+    return LOSS_KINDS[base]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (building the checker is not using it)."""
+    sources = [os.path.join(_HERE, f) for f in ("oracle.cpp", "solvers.cpp", "oracle.h", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in sources if os.path.exists(s)
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i64 = ctypes.c_int64
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == tuple(shape), f"expected shape {shape}, got {a.shape}"
+    return a
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.oracle_loss_value.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp, _i64, _i64, _dp]
+        L.oracle_loss_vgrad.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp, _i64, _i64, _dp]
+        L.oracle_predict.argtypes = [_dp, _dp, _dp, _i64, _i64, _i64, _dp]
+        L.oracle_sum_reduce.argtypes = [_dp, _i64, _i64, _i64]
+        for name in ("oracle_linear_vgrad", "oracle_linear_vgrad_fast"):
+            fn = getattr(L, name)
+            fn.restype = ctypes.c_double
+            fn.argtypes = [_dp, _dp, _i64, _i64, _i64, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                           ctypes.c_double, _dp, _dp, _i64, ctypes.c_int]
+        L.oracle_linear_vgrad_ld.restype = ctypes.c_double
+        L.oracle_linear_vgrad_ld.argtypes = [_dp, _dp, _i64, _i64, _i64, ctypes.c_int, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_double, _dp, _dp]
+        L.oracle_linear_partial.argtypes = [_dp, _dp, _i64, _i64, _i64, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int,
+                                            _i64, ctypes.c_int, _dp]
+        L.oracle_linear_finish.restype = ctypes.c_double
+        L.oracle_linear_finish.argtypes = [_dp, _i64, _i64, _i64, ctypes.c_double, ctypes.c_double, _dp, _dp]
+        L.oracle_synth_samples.restype = _i64
+        L.oracle_synth_samples.argtypes = [_i64, ctypes.c_double]
+        L.oracle_synth_model.argtypes = [_i64, _i64, ctypes.c_uint64, _i64, ctypes.c_int, _dp, _dp, _dp, _dp]
+        L.oracle_synth_vgrad.restype = ctypes.c_double
+        L.oracle_synth_vgrad.argtypes = [_dp, _dp, ctypes.c_double, _i64, _i64, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_double, _dp, _dp]
+        L.oracle_hardware_threads.restype = ctypes.c_int
+        # restated drivers (solvers.cpp)
+        L.oracle_solver_callback = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_void_p, _dp, _dp)
+        if hasattr(L, "oracle_lbfgs"):
+            L.oracle_lbfgs.restype = ctypes.c_int
+            L.oracle_lbfgs.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
+                                       _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
+        if hasattr(L, "oracle_osga"):
+            L.oracle_osga.restype = ctypes.c_int
+            L.oracle_osga.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
+                                      ctypes.c_double, _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
+        _lib = L
+    return _lib
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loss_t::value / loss_t::vgrad
+# ----------------------------------------------------------------------------------------------------------------
+def loss_value(loss_id: str, targets, outputs, param: float = 0.5):
+    targets = _f64(targets)
+    outputs = _f64(outputs)
+    if targets.shape != outputs.shape:  # src/loss.cpp:10-16 (critical on dims mismatch)
+        raise RuntimeError("critical check failed: loss: incompatible dimension-wise outputs and targets")
+    N = targets.shape[0]
+    T = int(np.prod(targets.shape[1:])) if targets.ndim > 1 else 1
+    values = np.empty(N, dtype=np.float64)
+    lib().oracle_loss_value(loss_kind(loss_id), param, _ptr(targets), _ptr(outputs), N, T, _ptr(values))
+    return values
+
+
+def loss_vgrad(loss_id: str, targets, outputs, param: float = 0.5):
+    targets = _f64(targets)
+    outputs = _f64(outputs)
+    if targets.shape != outputs.shape:
+        raise RuntimeError("critical check failed: loss: incompatible dimension-wise outputs and targets")
+    N = targets.shape[0]
+    T = int(np.prod(targets.shape[1:])) if targets.ndim > 1 else 1
+    vgrads = np.empty_like(targets)
+    lib().oracle_loss_vgrad(loss_kind(loss_id), param, _ptr(targets), _ptr(outputs), N, T, _ptr(vgrads))
+    return vgrads
+
+
+def predict(X, W, b):
+    X = _f64(X)
+    W = _f64(W)
+    b = _f64(b)
+    N, D = X.shape
+    T = W.shape[0]
+    assert W.shape == (T, D) and b.shape == (T,)
+    out = np.empty((N, T), dtype=np.float64)
+    lib().oracle_predict(_ptr(X), _ptr(W), _ptr(b), N, D, T, _ptr(out))
+    return out
+
+
+def sum_reduce(accumulators, samples: int):
+    acc = _f64(accumulators).copy()
+    count, length = acc.shape
+    lib().oracle_sum_reduce(_ptr(acc), count, length, samples)
+    return acc[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# objective (A): nano::linear::function_t
+# ----------------------------------------------------------------------------------------------------------------
+def linear_vgrad(X, Y, loss_id, x, l1=0.0, l2=0.0, want_grad=True, batch=100, threads=1, param=0.5,
+                 mode="plain"):
+    """f, g of linear::function_t::do_eval. mode: 'plain' (oracle), 'fast' (CPU baseline), 'ld' (long double)."""
+    X = _f64(X)
+    N, D = X.shape
+    Y = _f64(Y).reshape(N, -1)
+    T = Y.shape[1]
+    x = _f64(x, ((D + 1) * T,))
+    gx = np.empty_like(x) if want_grad else None
+    kind = loss_kind(loss_id)
+    if mode == "ld":
+        fx = lib().oracle_linear_vgrad_ld(_ptr(X), _ptr(Y), N, D, T, kind, param, l1, l2, _ptr(x), _ptr(gx))
+    else:
+        fn = lib().oracle_linear_vgrad_fast if mode == "fast" else lib().oracle_linear_vgrad
+        fx = fn(_ptr(X), _ptr(Y), N, D, T, kind, param, l1, l2, _ptr(x), _ptr(gx), batch, threads)
+    return fx, gx
+
+
+def linear_partial(X, Y, loss_id, x, want_grad=True, batch=100, threads=1, param=0.5):
+    """Un-normalised [sum loss | sum dL | sum dL x^T] of the given rows (what one rank contributes)."""
+    X = _f64(X)
+    N, D = X.shape
+    Y = _f64(Y).reshape(N, -1)
+    T = Y.shape[1]
+    x = _f64(x, ((D + 1) * T,))
+    partial = np.zeros(1 + T + T * D, dtype=np.float64)
+    lib().oracle_linear_partial(_ptr(X), _ptr(Y), N, D, T, loss_kind(loss_id), param, _ptr(x), int(want_grad), batch,
+                                threads, _ptr(partial))
+    return partial
+
+
+def linear_finish(reduced, n_global, D, T, x, l1=0.0, l2=0.0, want_grad=True):
+    reduced = _f64(reduced, (1 + T + T * D,))
+    x = _f64(x, ((D + 1) * T,))
+    gx = np.empty_like(x) if want_grad else None
+    fx = lib().oracle_linear_finish(_ptr(reduced), n_global, D, T, l1, l2, _ptr(x), _ptr(gx))
+    return fx, gx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# objective (B): function_{ridge,lasso,elasticnet}_t<loss> over linear_model_t
+# ----------------------------------------------------------------------------------------------------------------
+def synth_samples(dims: int, sratio: float = 10.0) -> int:
+    return int(lib().oracle_synth_samples(dims, sratio))
+
+
+def synth_model(dims: int, seed: int = 42, sratio: float = 10.0, modulo: int = 1, loss: str = "mse"):
+    D = max(dims, 2)  # make_inputs (src/function/mlearn/ridge.cpp:13-16)
+    N = synth_samples(dims, sratio)
+    X = np.empty((N, D), dtype=np.float64)
+    Y = np.empty(N, dtype=np.float64)
+    w = np.empty(D, dtype=np.float64)
+    b = np.empty(1, dtype=np.float64)
+    lib().oracle_synth_model(N, D, seed, modulo, int(SYNTH_REGRESSION[loss]), _ptr(X), _ptr(Y), _ptr(w), _ptr(b))
+    return X, Y, w, float(b[0])
+
+
+def synth_vgrad(X, Y, bopt, loss, x, alpha1=0.0, alpha2=0.0, want_grad=True):
+    X = _f64(X)
+    N, D = X.shape
+    Y = _f64(Y, (N,))
+    x = _f64(x, (D,))
+    gx = np.empty_like(x) if want_grad else None
+    fx = lib().oracle_synth_vgrad(_ptr(X), _ptr(Y), bopt, N, D, SYNTH_LOSSES[loss], alpha1, alpha2, _ptr(x), _ptr(gx))
+    return fx, gx
+
+
+def hardware_threads() -> int:
+    return int(lib().oracle_hardware_threads())

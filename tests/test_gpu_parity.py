@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Reference tests mirrored: test/test_linear_function.cpp (check_vgrad identity, flags, strong convexity, size),
+test/test_linear_util.cpp (predict, sum_reduce), test/test_loss.cpp (loss values/gradients, pinball goldens),
+test/test_function_factory.cpp (call counters, same-seed determinism), test/fixture/function.h (FD gradient,
+convexity). Bar: <= 1e-12 relative for f and g (BASELINE.json north_star), stated per test.
+"""
+import numpy as np
+import pytest
+
+from conftest import (CLASSIFICATION_LOSSES, EPSILON0, NORTH_STAR_LOSSES, PARITY, REGRESSION_LOSSES,
+                      is_classification, make_problem, rel_f, rel_g)
+
+pytestmark = pytest.mark.gpu
+
+ALL_LOSSES = REGRESSION_LOSSES + CLASSIFICATION_LOSSES
+
+
+def gpu_function(ctx, X, Y, loss_id, l1=0.0, l2=0.0, alpha=None):
+    import libnano_b200 as nb
+
+    loss = nb.Loss(loss_id)
+    if alpha is not None:
+        loss.parameter("loss::pinball::alpha", alpha)
+    return nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), loss, l1, l2)
+
+
+def check_against_oracle(oracle, function, X, Y, loss_id, x, l1, l2, param=0.5, tol=PARITY):
+    gx = np.empty_like(x)
+    fx = function(x, gx)
+    f_ref, g_ref = oracle.linear_vgrad(X, Y, loss_id, x, l1=l1, l2=l2, param=param)
+    assert rel_f(fx, f_ref) <= tol, (loss_id, fx, f_ref)
+    assert rel_g(gx, g_ref) <= tol, (loss_id, rel_g(gx, g_ref))
+    # value-only call: same number (function(x) without gx, src/function.cpp:246-272)
+    assert rel_f(function(x), f_ref) <= tol
+    return fx, gx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# single-target fused kernel: every loss, ragged and aligned shapes, with and without regularisation
+# ----------------------------------------------------------------------------------------------------------------
+T1_SHAPES = [(1, 1), (3, 2), (10, 3), (37, 64), (1000, 100), (999, 513), (257, 1024), (4096, 1024), (2500, 512),
+             (5000, 2048), (301, 4096), (64, 8192), (777, 1000), (123, 2047), (50, 10000)]
+
+
+@pytest.mark.parametrize("N,D", T1_SHAPES)
+@pytest.mark.parametrize("loss_id", NORTH_STAR_LOSSES)
+def test_t1_parity_shapes(ctx, oracle, N, D, loss_id):
+    X, Y, x = make_problem(N * 31 + D, N, D, 1, is_classification(loss_id))
+    function = gpu_function(ctx, X, Y, loss_id, 0.0, 0.0)
+    check_against_oracle(oracle, function, X, Y, loss_id, x, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("loss_id", ALL_LOSSES)
+@pytest.mark.parametrize("l1,l2", [(0.0, 0.0), (0.3, 0.0), (0.0, 0.7), (0.2, 0.5)])
+def test_t1_parity_losses_and_regularisers(ctx, oracle, loss_id, l1, l2):
+    N, D = 2000, 256
+    X, Y, x = make_problem(7, N, D, 1, is_classification(loss_id))
+    param = 0.3 if loss_id == "pinball" else 0.5
+    function = gpu_function(ctx, X, Y, loss_id, l1, l2, alpha=0.3 if loss_id == "pinball" else None)
+    check_against_oracle(oracle, function, X, Y, loss_id, x, l1, l2, param=param)
+    # attributes of linear::function_t (src/linear/function.cpp:34-36; test_linear_function.cpp:87-92,142-147)
+    assert function.size() == (D + 1) * 1
+    assert function.convex() == function._loss.convex()
+    assert function.smooth() == (function._loss.smooth() and l1 <= 0.0)
+    assert function.strong_convexity() == l2 / (D * 1)
+
+
+def test_t1_at_zero_and_at_kinks(ctx, oracle):
+    # integer data makes the ties real: o - t == 0 (mae / pinball: sign(0) == 0), t * o == 1 (hinge: gradient -t/2
+    # exactly on the kink, include/nano/loss/hinge.h:24-29), and x = 0 is bench_function's point (bench_function.cpp:16)
+    N, D = 512, 64
+    rng = np.random.default_rng(3)
+    X = rng.integers(-2, 3, (N, D)).astype(np.float64)
+    x = np.concatenate([rng.integers(-1, 2, D).astype(np.float64), [1.0]])
+    o = X @ x[:D] + x[D]
+    assert np.sum(np.abs(o) == 1.0) > 5
+    for loss_id in ("mae", "s-hinge", "s-squared-hinge", "pinball", "mse"):
+        if is_classification(loss_id):
+            Y = np.where(o >= 0, 1.0, -1.0).reshape(N, 1)  # rows with |o| == 1 sit exactly on the kink
+        else:
+            Y = np.where(np.arange(N) % 3 == 0, o, o + rng.integers(-2, 3, N)).reshape(N, 1)  # exact ties on a third
+        function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.1)
+        fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.1, tol=1e-14)
+        check_against_oracle(oracle, function, X, Y, loss_id, np.zeros(D + 1), 0.1, 0.1)
+
+
+def test_t1_non_finite_flows_back(ctx):
+    # numerical failure is not an error: non-finite f/g come back and solver_state_t::valid() decides
+    # (src/solver/state.cpp:170-174)
+    X, Y, x = make_problem(5, 100, 8, 1, False)
+    function = gpu_function(ctx, X, Y, "mse")
+    x[0] = np.inf
+    gx = np.empty_like(x)
+    fx = function(x, gx)
+    assert not np.isfinite(fx)
+    assert not np.all(np.isfinite(gx))
+
+
+def test_t1_every_variant_agrees(ctx, oracle):
+    # all decompositions of the fused kernel that can cover (N, D) give the oracle's answer
+    N, D = 3001, 1024
+    X, Y, x = make_problem(11, N, D, 1, True)
+    function = gpu_function(ctx, X, Y, "s-logistic", 0.0, 1e-2)
+    f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-logistic", x, l2=1e-2)
+    seen = 0
+    for variant in list(range(0, 32)) + [-2]:
+        try:
+            function.set_variant(variant)
+        except RuntimeError:
+            continue
+        seen += 1
+        gx = np.empty_like(x)
+        fx = function(x, gx)
+        assert rel_f(fx, f_ref) <= PARITY, (variant, function.describe())
+        assert rel_g(gx, g_ref) <= PARITY, (variant, function.describe())
+        assert rel_f(function(x), f_ref) <= PARITY
+    assert seen >= 5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# multi-target path (shape-generic kernels)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,T", [(10, 4, 2), (500, 33, 3), (1000, 128, 10), (300, 257, 100), (64, 2048, 7)])
+@pytest.mark.parametrize("loss_id", NORTH_STAR_LOSSES + ("m-hinge", "m-logistic", "cauchy", "pinball"))
+def test_multi_target_parity(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):  # multi-label targets: independent +-1 per output
+        Y = np.where(np.random.default_rng(1).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    for l1, l2 in ((0.0, 0.0), (0.1, 0.2)):
+        function = gpu_function(ctx, X, Y, loss_id, l1, l2)
+        check_against_oracle(oracle, function, X, Y, loss_id, x, l1, l2)
+        assert function.size() == (D + 1) * T
+        assert function.strong_convexity() == l2 / (D * T)
+
+
+def test_generic_path_matches_fused_path(ctx, oracle):
+    N, D = 1500, 300
+    X, Y, x = make_problem(2, N, D, 1, True)
+    function = gpu_function(ctx, X, Y, "s-logistic", 0.0, 0.0)
+    g1, g2 = np.empty_like(x), np.empty_like(x)
+    f1 = function(x, g1)
+    function.set_variant(-2)
+    assert function.describe().startswith("generic")
+    f2 = function(x, g2)
+    assert rel_f(f1, f2) <= 1e-13 and rel_g(g1, g2) <= 1e-13
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# check_vgrad identity (test/test_linear_function.cpp:23-49): f(x) == mean(loss.value(predict(X, W, b)))
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,loss_id", [(2, "mse"), (1, "mae"), (3, "mse"), (4, "s-classnll")])
+def test_check_vgrad_identity(ctx, T, loss_id):
+    import libnano_b200 as nb
+
+    N, D = 50, 13  # the reference fixture: 13 flatten columns (1 + 2 + 4 + 6), size == T * 14
+    X, Y, _ = make_problem(17, N, D, T, is_classification(loss_id))
+    dataset = nb.Dataset.pin(ctx, X, Y)
+    loss = nb.Loss(loss_id)
+    function = nb.LinearFunction(dataset, loss, 0.0, 0.0)
+    assert function.size() == T * (1 + 13)
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        x = rng.uniform(-1, 1, function.size())
+        outputs = dataset.predict(function.weights(x), function.bias(x))
+        values = loss.value(ctx, Y, outputs)
+        assert abs(function(x) - values.mean()) < 1e-10 * (1 + abs(values.mean()))  # epsilon1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# building blocks: predict, loss value / vgrad (incl. the pinball golden vectors)
+# ----------------------------------------------------------------------------------------------------------------
+def test_predict_matches_oracle(ctx, oracle):
+    import libnano_b200 as nb
+
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-1, 1, (11, 5))
+    W = rng.uniform(-1, 1, (3, 5))
+    b = rng.uniform(-1, 1, 3)
+    dataset = nb.Dataset.pin(ctx, X, np.zeros((11, 3)))
+    out = dataset.predict(W, b)
+    assert np.max(np.abs(out - oracle.predict(X, W, b))) < 1e-14
+    for i in range(11):  # test/test_linear_util.cpp:46-61
+        assert np.max(np.abs(out[i] - (W @ X[i] + b))) < 1e-10 * 3
+
+
+@pytest.mark.parametrize("loss_id", ALL_LOSSES)
+def test_loss_value_and_vgrad(ctx, oracle, loss_id):
+    import libnano_b200 as nb
+
+    rng = np.random.default_rng(9)
+    loss = nb.Loss(loss_id)
+    for T in (1, 2, 5):
+        if is_classification(loss_id):
+            targets = -np.ones((40, T))
+            targets[np.arange(40), rng.integers(0, T, 40)] = 1.0
+        else:
+            targets = rng.uniform(-1, 1, (40, T))
+        for scale in (1.0, np.e ** 3):  # test/test_loss.cpp:102-148 sweeps output scales
+            outputs = rng.uniform(-1, 1, (40, T)) * scale
+            v, v_ref = loss.value(ctx, targets, outputs), oracle.loss_value(loss_id, targets, outputs)
+            g, g_ref = loss.vgrad(ctx, targets, outputs), oracle.loss_vgrad(loss_id, targets, outputs)
+            assert np.max(np.abs(v - v_ref) / (1 + np.abs(v_ref))) <= PARITY
+            assert np.max(np.abs(g - g_ref) / (1 + np.abs(g_ref))) <= PARITY
+    with pytest.raises(RuntimeError):  # src/loss.cpp:10-16
+        loss.value(ctx, np.zeros((3, 2)), np.zeros((3, 3)))
+
+
+def test_pinball_golden_vectors(ctx):
+    # test/test_loss.cpp:271-307
+    import libnano_b200 as nb
+
+    targets = np.array([0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]).reshape(5, 2)
+    outputs = np.array([0.1, 0.0, 0.2, 0.4, 0.2, 0.3, 0.7, 0.9, 0.9, 0.6]).reshape(5, 2)
+    loss = nb.Loss("pinball")
+    for alpha, expected in ((0.5, [0.10, 0.05, 0.20, 0.15, 0.20]), (0.2, [0.10, 0.08, 0.08, 0.24, 0.14]),
+                            (0.8, [0.10, 0.02, 0.32, 0.06, 0.26])):
+        loss.parameter("loss::pinball::alpha", alpha)
+        values = loss.value(ctx, targets, outputs)
+        expected = np.array(expected)
+        assert np.all(np.abs(values - expected) < 1e-12 * (1 + np.abs(values) + np.abs(expected)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# function_t contract: counters, size checks, clone, determinism
+# ----------------------------------------------------------------------------------------------------------------
+def test_function_contract(ctx):
+    X, Y, x = make_problem(1, 200, 16, 2, False)
+    function = gpu_function(ctx, X, Y, "mse", 0.0, 0.1)
+    assert (function.fcalls(), function.gcalls()) == (0, 0)
+    gx = np.empty_like(x)
+    f1 = function(x)
+    f2 = function(x, gx)
+    assert (function.fcalls(), function.gcalls(), function.hcalls()) == (2, 1, 0)  # test_function_factory.cpp:53-90
+    assert f1 == f2
+    with pytest.raises(RuntimeError, match="invalid input size"):
+        function(x[:-1])
+    with pytest.raises(RuntimeError, match="invalid gradient size"):
+        function(x, np.empty(3))
+    with pytest.raises(RuntimeError):
+        function(x, gx, np.empty((x.size, x.size)))  # Hessian: outside the hot path
+    function.clear_statistics()
+    assert (function.fcalls(), function.gcalls()) == (0, 0)
+    assert function.name() == f"linear[{x.size}D]"
+
+    clone = function.clone()
+    assert clone.size() == function.size()
+    g2 = np.empty_like(x)
+    assert clone(x, g2) == f2 and np.array_equal(g2, gx)  # bit-identical: same data, same launch geometry
+
+
+@pytest.mark.parametrize("N,D,T", [(5000, 1024, 1), (3000, 100, 1), (700, 64, 5)])
+def test_same_input_same_bits(ctx, N, D, T):
+    # the reference demands |df|, |dg| < 1e-15 for repeated evaluation (test_function_factory.cpp:204-231);
+    # the fixed launch geometry and fixed-order reductions give exact equality.
+    X, Y, x = make_problem(8, N, D, T, True)
+    function = gpu_function(ctx, X, Y, "s-logistic" if T == 1 else "s-classnll", 0.0, 0.0)
+    g1, g2 = np.empty_like(x), np.empty_like(x)
+    f1 = function(x, g1)
+    for _ in range(3):
+        f2 = function(x, g2)
+        assert f1 == f2 and np.array_equal(g1, g2)
+    assert abs(f1 - f2) < EPSILON0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# property checks of test/fixture/function.h:39-83 driven through the GPU objective
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loss_id,T,l1,l2", [("mse", 2, 0.0, 0.0), ("mae", 1, 1.0, 0.0), ("mse", 3, 0.0, 1.0),
+                                             ("s-logistic", 1, 0.0, 0.5), ("s-classnll", 3, 0.0, 0.0),
+                                             ("s-hinge", 1, 0.0, 0.0)])
+def test_check_function_properties(ctx, loss_id, T, l1, l2):
+    N, D = 10, 13
+    X, Y, _ = make_problem(23, N, D, T, is_classification(loss_id))
+    function = gpu_function(ctx, X, Y, loss_id, l1, l2)
+    rng = np.random.default_rng(5)
+    n = function.size()
+    for _ in range(5):
+        x, z = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        # convexity along [x, z] (src/function/util.cpp:235-262), violation < 1e-14 relative
+        f1, f2 = function(x), function(z)
+        dx = float(np.dot(x - z, x - z))
+        for step in range(1, 20):
+            t1 = step / 20.0
+            t2 = 1.0 - t1
+            gap = t1 * f1 + t2 * f2 - t1 * t2 * function.strong_convexity() * 0.5 * dx - function(t1 * x + t2 * z)
+            assert gap > -1e-14 * (1 + 0.5 * (abs(f1) + abs(f2)))
+        # analytic gradient vs central differences (src/function/util.cpp:134-180), < 1e-8 at smooth points
+        if function.smooth():
+            gx = np.empty(n)
+            fx = function(x, gx)
+            eta = np.sqrt(np.finfo(float).eps)
+            best = np.inf
+            for deta in (1e-2, 3e-2, 1e-1, 3e-1, 1.0, 3.0, 10.0):
+                approx = np.empty(n)
+                for i in range(n):
+                    h = deta * eta * (1 + abs(x[i]))
+                    xp, xn = x.copy(), x.copy()
+                    xp[i] += h
+                    xn[i] -= h
+                    approx[i] = (function(xp) - function(xn)) / (2 * h)
+                best = min(best, np.max(np.abs(gx - approx)) / (1 + abs(fx)))
+                if best < 1e-8:
+                    break
+            assert best < 1e-8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# objective (B): the builtin synthetic test functions (config 1)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loss", ["mse", "mae", "cauchy", "hinge", "logistic"])
+@pytest.mark.parametrize("reg", ["ridge", "lasso", "elasticnet"])
+def test_synthetic_functions(ctx, oracle, loss, reg):
+    import libnano_b200 as nb
+
+    dims, seed, sratio = 37, 42, 10.0
+    function = nb.SyntheticFunction(ctx, loss, reg, dims, seed=seed, alpha1=0.7, alpha2=1.3, sratio=sratio)
+    X_ref, Y_ref, w_ref, b_ref = oracle.synth_model(dims, seed=seed, sratio=sratio, modulo=1, loss=loss)
+    X, Y = function.dataset.read()
+    assert np.array_equal(X, X_ref)  # same mt19937_64 stream (src/function/mlearn/linear.cpp:15-20)
+    assert function._boptimum == b_ref and np.array_equal(function._woptimum, w_ref)
+    assert np.max(np.abs(Y[:, 0] - Y_ref)) <= (1e-14 if loss in ("mse", "mae", "cauchy") else 0.0)
+    assert function.size() == dims and function.name() .startswith(f"{loss}+{reg}[")
+
+    a1 = 0.7 if reg in ("lasso", "elasticnet") else 0.0
+    a2 = 1.3 if reg in ("ridge", "elasticnet") else 0.0
+    rng = np.random.default_rng(2)
+    for x in (np.zeros(dims), rng.uniform(-1, 1, dims), w_ref.copy()):
+        if loss == "logistic":
+            x = x * 0.5
+        gx = np.empty(dims)
+        fx = function(x, gx)
+        f_ref, g_ref = oracle.synth_vgrad(X, Y[:, 0], b_ref, loss, x, alpha1=a1, alpha2=a2)
+        assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY
+        assert rel_f(function(x), f_ref) <= PARITY
+    # flags: ridge.cpp:40-42, lasso.cpp:40-42, elasticnet.cpp:42-44
+    smooth = {"mse": True, "mae": False, "cauchy": False, "hinge": False, "logistic": True}[loss]
+    assert function.convex() == (loss != "cauchy")
+    assert function.smooth() == {"ridge": smooth, "lasso": False, "elasticnet": False}[reg]
+    assert function.strong_convexity() == a2
+
+
+def test_synthetic_config1_sizes(ctx, oracle):
+    # BASELINE config 1: mse+ridge, seed 42, alpha2 = 1; D=100 x sratio 100 -> N=10000; bench_function default D=1024
+    import libnano_b200 as nb
+
+    for dims, sratio in ((100, 100.0), (1024, 10.0)):
+        function = nb.SyntheticFunction(ctx, "mse", "ridge", dims, seed=42, alpha2=1.0, sratio=sratio)
+        X, Y = function.dataset.read()
+        assert X.shape == (int(max(sratio * dims, 10)), dims)
+        b_ref = oracle.synth_model(dims, seed=42, sratio=sratio, loss="mse")[3]
+        rng = np.random.default_rng(0)
+        for x in (np.zeros(dims), rng.uniform(-1, 1, dims)):
+            gx = np.empty(dims)
+            fx = function(x, gx)
+            f_ref, g_ref = oracle.synth_vgrad(X, Y[:, 0], b_ref, "mse", x, alpha2=1.0)
+            assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY
+        # same seed => same bits, different seed => different values (test_function_factory.cpp:172-253)
+        twin = nb.SyntheticFunction(ctx, "mse", "ridge", dims, seed=42, alpha2=1.0, sratio=sratio)
+        other = nb.SyntheticFunction(ctx, "mse", "ridge", dims, seed=43, alpha2=1.0, sratio=sratio)
+        g2, g3 = np.empty(dims), np.empty(dims)
+        assert twin(x, g2) == fx and np.array_equal(g2, gx)
+        assert abs(other(x, g3) - fx) > 1e2 * EPSILON0 and np.max(np.abs(g3 - gx)) > 1e-10
