@@ -100,14 +100,12 @@ def lib():
         L.oracle_hardware_threads.restype = ctypes.c_int
         # restated drivers (solvers.cpp)
         L.oracle_solver_callback = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_void_p, _dp, _dp)
-        if hasattr(L, "oracle_lbfgs"):
-            L.oracle_lbfgs.restype = ctypes.c_int
-            L.oracle_lbfgs.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
-                                       _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
-        if hasattr(L, "oracle_osga"):
-            L.oracle_osga.restype = ctypes.c_int
-            L.oracle_osga.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
-                                      ctypes.c_double, _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
+        L.oracle_lbfgs.restype = ctypes.c_int
+        L.oracle_lbfgs.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double, _i64, _i64,
+                                   _dp, _dp, ctypes.POINTER(_i64)]
+        L.oracle_osga.restype = ctypes.c_int
+        L.oracle_osga.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
+                                  ctypes.c_double, _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
         _lib = L
     return _lib
 
@@ -230,3 +228,48 @@ def synth_vgrad(X, Y, bopt, loss, x, alpha1=0.0, alpha2=0.0, want_grad=True):
 
 def hardware_threads() -> int:
     return int(lib().oracle_hardware_threads())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# restated drivers (solvers.cpp): L-BFGS + CG-DESCENT and OSGA over any `function(x, gx=None) -> fx` callable
+# ----------------------------------------------------------------------------------------------------------------
+SOLVER_STATUS = {0: "max_iters", 1: "gradient_test", 2: "value_test", 3: "specific_test", 4: "failed"}
+
+
+def _make_callback(function, n):
+    def trampoline(_ctx, x_ptr, g_ptr):
+        x = np.ctypeslib.as_array(x_ptr, shape=(n,)).copy()
+        if g_ptr:
+            gx = np.empty(n, dtype=np.float64)
+            fx = function(x, gx)
+            ctypes.memmove(g_ptr, gx.ctypes.data, 8 * n)
+            return float(fx)
+        return float(function(x))
+
+    return lib().oracle_solver_callback(trampoline)
+
+
+def lbfgs(function, x0, epsilon=1e-8, max_evals=1000, history=50):
+    """solver_lbfgs_t::minimize with the reference defaults (src/solver.cpp:45-51, src/solver/lbfgs.cpp:9-12)."""
+    x = _f64(x0).copy()
+    n = x.size
+    fx, gtest = ctypes.c_double(), ctypes.c_double()
+    stats = (_i64 * 3)()
+    callback = _make_callback(function, n)
+    status = lib().oracle_lbfgs(callback, None, n, _ptr(x), epsilon, max_evals, history, ctypes.byref(fx),
+                                ctypes.byref(gtest), stats)
+    return {"x": x, "fx": fx.value, "gradient_test": gtest.value, "status": SOLVER_STATUS[status],
+            "fcalls": stats[0], "gcalls": stats[1], "iterations": stats[2]}
+
+
+def osga(function, x0, epsilon=1e-8, strong_convexity=0.0, max_evals=1000, patience=100):
+    """solver_osga_t::minimize (src/solver/osga.cpp:59-147)."""
+    x = _f64(x0).copy()
+    n = x.size
+    fx, eta = ctypes.c_double(), ctypes.c_double()
+    stats = (_i64 * 3)()
+    callback = _make_callback(function, n)
+    status = lib().oracle_osga(callback, None, n, _ptr(x), epsilon, strong_convexity, max_evals, patience,
+                               ctypes.byref(fx), ctypes.byref(eta), stats)
+    return {"x": x, "fx": fx.value, "eta": eta.value, "status": SOLVER_STATUS[status], "fcalls": stats[0],
+            "gcalls": stats[1], "iterations": stats[2]}
