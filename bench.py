@@ -265,10 +265,13 @@ def run_b200(args):
     f_dev = torch.empty(1, dtype=torch.float64, device="cuda")
 
     def step_device():
-        ptr, length = local.partial_device(x_dev.data_ptr(), True)
-        if world > 1:
+        if world == 1:
+            # one cooperative launch: pass over X, cross-CTA reduction, scaling + regularisation
+            local.vgrad_device(x_dev.data_ptr(), g_dev.data_ptr(), f_dev.data_ptr())
+        else:
+            ptr, length = local.partial_device(x_dev.data_ptr(), True)
             dist.all_reduce(function._shard._view_for(ptr, length))
-        local.finish_device(x_dev.data_ptr(), n_global, g_dev.data_ptr(), f_dev.data_ptr())
+            local.finish_device(x_dev.data_ptr(), n_global, g_dev.data_ptr(), f_dev.data_ptr())
 
     for _ in range(max(args.warmup, 3)):
         step_device()

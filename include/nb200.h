@@ -166,10 +166,11 @@ NB200_API int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, int
                                         double* fx_dev);
 
 /* cudaStream_t of the objective, as an opaque pointer (so that callers can order collectives after phase 1);
- * set_stream re-points the objective at a caller-owned stream (NULL: back to its own), e.g. the stream the
- * caller's NCCL all-reduce is enqueued on, so that phase 1 -> all-reduce -> phase 2 need no host synchronisation. */
+ * set_stream re-points the objective at a caller-owned stream (a NULL handle is the legacy default stream), e.g. the
+ * stream the caller's NCCL all-reduce is enqueued on, so that phase 1 -> all-reduce -> phase 2 need no host
+ * synchronisation; use_own != 0 goes back to the objective's own stream. */
 NB200_API void* nb200_objective_stream(const nb200_obj* obj);
-NB200_API int   nb200_objective_set_stream(nb200_obj* obj, void* stream);
+NB200_API int   nb200_objective_set_stream(nb200_obj* obj, void* stream, int use_own);
 
 /* Kernels launched by this objective since creation (bench.py's `gpu_launches`). */
 NB200_API int64_t nb200_objective_launches(const nb200_obj* obj);

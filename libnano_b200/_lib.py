@@ -43,7 +43,7 @@ SIGNATURES = {
     "nb200_vgrad_finish_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64, ctypes.c_void_p,
                                                  ctypes.c_void_p]),
     "nb200_objective_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
-    "nb200_objective_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "nb200_objective_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_launches": (c_i64, [ctypes.c_void_p]),
     "nb200_objective_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_last_pass_ms": (ctypes.c_double, [ctypes.c_void_p]),

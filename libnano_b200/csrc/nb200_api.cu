@@ -91,6 +91,8 @@ const t1_variant kT1Variants[] = {
 constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
 constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
 
+constexpr int kTimingRing = 64; // event pairs kept in flight when pass timing is enabled
+
 struct t1_plan
 {
     int     variant{-1};
@@ -192,9 +194,12 @@ struct nb200_obj
     double* d_partials{nullptr};   // T1: [grid, D + 2]; generic: forward [blocks, 1 + T]
     double* d_partials_gw{nullptr}; // generic: [splits, T*D]
     double* d_dL{nullptr};         // generic: [N, T]
-    // pinned host staging
+    unsigned long long* d_grid_counter{nullptr}; // arrival counter of the fused kernel's grid barrier
+    unsigned long long  grid_epoch{0};           // launches issued on that counter under the current plan
+    // pinned host staging; h_out is MAPPED: kernels write (g, f) straight into it through h_out_dev
     double* h_x{nullptr};
     double* h_out{nullptr};
+    double* h_out_dev{nullptr};
     std::vector<double> fixed_bias;
 
     // plan
@@ -211,8 +216,8 @@ struct nb200_obj
     // statistics
     int64_t     launches{0};
     bool        timing{false};
-    bool        pass_pending{false};
-    cudaEvent_t ev0{nullptr}, ev1{nullptr};
+    int         pass_pending{0}; // event pairs recorded and not yet read back
+    std::vector<cudaEvent_t> ev0, ev1;
     double      last_pass_ms{-1.0};
     double      pass_ms_total{0.0};
     int64_t     pass_count{0};
@@ -234,15 +239,16 @@ void free_obj(nb200_obj* obj)
     cudaFree(obj->d_partials);
     cudaFree(obj->d_partials_gw);
     cudaFree(obj->d_dL);
+    cudaFree(obj->d_grid_counter);
     cudaFreeHost(obj->h_x);
     cudaFreeHost(obj->h_out);
-    if (obj->ev0 != nullptr)
+    for (cudaEvent_t event : obj->ev0)
     {
-        cudaEventDestroy(obj->ev0);
+        cudaEventDestroy(event);
     }
-    if (obj->ev1 != nullptr)
+    for (cudaEvent_t event : obj->ev1)
     {
-        cudaEventDestroy(obj->ev1);
+        cudaEventDestroy(event);
     }
     if (obj->own_stream != nullptr)
     {
@@ -266,6 +272,8 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     cudaFree(obj->d_dL);
     obj->d_partials = obj->d_partials_gw = obj->d_dL = nullptr;
     obj->use_t1 = false;
+    NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter, 0, sizeof(unsigned long long)));
+    obj->grid_epoch = 0;
 
     const bool force_generic = forced_variant == -2 || env_int("NB200_FORCE_GENERIC", 0) != 0;
     if (T == 1 && !force_generic && D <= (1 << 20))
@@ -362,14 +370,21 @@ int make_objective(nb200_data* data, const int loss, const double loss_param, co
         const size_t n = static_cast<size_t>(obj->n);
         NB200_CUDA_TRY(cudaStreamCreateWithFlags(&obj->own_stream, cudaStreamNonBlocking));
         obj->stream = obj->own_stream;
-        NB200_CUDA_TRY(cudaEventCreate(&obj->ev0));
-        NB200_CUDA_TRY(cudaEventCreate(&obj->ev1));
+        obj->ev0.assign(kTimingRing, nullptr);
+        obj->ev1.assign(kTimingRing, nullptr);
+        for (int i = 0; i < kTimingRing; ++i)
+        {
+            NB200_CUDA_TRY(cudaEventCreate(&obj->ev0[i]));
+            NB200_CUDA_TRY(cudaEventCreate(&obj->ev1[i]));
+        }
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_grid_counter, sizeof(unsigned long long)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_x, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_out, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_reduced, static_cast<size_t>(1 + data->T + data->T * data->D) * sizeof(double)));
         NB200_CUDA_TRY(cudaMemset(obj->d_reduced, 0, static_cast<size_t>(1 + data->T + data->T * data->D) * sizeof(double)));
         NB200_CUDA_TRY(cudaMallocHost(&obj->h_x, (n + 2) * sizeof(double)));
-        NB200_CUDA_TRY(cudaMallocHost(&obj->h_out, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaHostAlloc(&obj->h_out, (n + 2) * sizeof(double), cudaHostAllocMapped));
+        NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->h_out_dev, obj->h_out, 0));
         if (flavour == NB200_FLAVOUR_SYNTH)
         {
             obj->fixed_bias.assign(fixed_bias, fixed_bias + data->T);
@@ -387,105 +402,42 @@ int make_objective(nb200_data* data, const int loss, const double loss_param, co
     return status;
 }
 
-// enqueue the pass over X: leaves [sum loss | sum dL | sum dL x^T] (un-normalised) in obj->d_reduced
-int enqueue_partial(nb200_obj* obj, const double* x_dev, const bool want_grad)
+void collect_timing(nb200_obj* obj)
 {
-    const nb200_data* data = obj->data;
-    const int64_t     N = data->N, D = data->D, T = data->T;
-    const double*     W    = x_dev;
-    const double*     bias = (obj->flavour == NB200_FLAVOUR_LINEAR) ? (x_dev + T * D) : obj->d_fixed_bias;
+    for (int i = 0; i < obj->pass_pending; ++i)
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, obj->ev0[i], obj->ev1[i]) == cudaSuccess)
+        {
+            obj->last_pass_ms = ms;
+            obj->pass_ms_total += ms;
+            obj->pass_count += 1;
+        }
+    }
+    obj->pass_pending = 0;
+}
 
+int timing_begin(nb200_obj* obj)
+{
     if (obj->timing)
     {
-        NB200_CUDA_TRY(cudaEventRecord(obj->ev0, obj->stream));
+        if (obj->pass_pending == kTimingRing)
+        {
+            NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+            collect_timing(obj);
+        }
+        NB200_CUDA_TRY(cudaEventRecord(obj->ev0[obj->pass_pending], obj->stream));
     }
+    return NB200_OK;
+}
 
-    if (obj->use_t1)
+int timing_end(nb200_obj* obj)
+{
+    if (obj->timing)
     {
-        const t1_variant& var = kT1Variants[obj->t1.variant];
-        t1_params         p{};
-        p.X              = data->X;
-        p.Y              = data->Y;
-        p.w              = W;
-        p.bias           = bias;
-        p.partials       = obj->d_partials;
-        p.N              = N;
-        p.num_tiles      = obj->t1.num_tiles;
-        p.D              = static_cast<int>(D);
-        p.rows_per_stage = obj->t1.rows_per_stage;
-        p.rows_per_group = obj->t1.rows_per_group;
-        p.stages         = obj->t1.stages;
-        p.stage_stride   = obj->t1.stage_stride;
-        p.y_offset       = obj->t1.y_offset;
-        p.loss           = obj->loss;
-        p.loss_param     = obj->loss_param;
-
-        const dim3 block((var.NCW + 1) * 32);
-        (want_grad ? var.grad : var.value)<<<obj->t1.grid, block, obj->t1.smem_bytes, obj->stream>>>(p);
-        NB200_CUDA_TRY(cudaGetLastError());
-        obj->launches += 1;
-        if (obj->timing)
-        {
-            NB200_CUDA_TRY(cudaEventRecord(obj->ev1, obj->stream));
-        }
-
-        const int64_t cols = want_grad ? (D + 2) : 2;
-        reduce_partials_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, obj->stream>>>(
-            obj->d_partials, obj->t1.grid, D + 2, cols, obj->d_reduced);
-        NB200_CUDA_TRY(cudaGetLastError());
-        obj->launches += 1;
+        NB200_CUDA_TRY(cudaEventRecord(obj->ev1[obj->pass_pending], obj->stream));
+        obj->pass_pending += 1;
     }
-    else
-    {
-        gen_params p{};
-        p.X           = data->X;
-        p.Y           = data->Y;
-        p.W           = W;
-        p.b           = bias;
-        p.dL          = want_grad ? obj->d_dL : nullptr;
-        p.partials_fb = obj->d_partials;
-        p.N           = N;
-        p.D           = D;
-        p.T           = T;
-        p.loss        = obj->loss;
-        p.loss_param  = obj->loss_param;
-        if (want_grad)
-        {
-            gen_forward_kernel<true><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
-        }
-        else
-        {
-            gen_forward_kernel<false><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
-        }
-        NB200_CUDA_TRY(cudaGetLastError());
-        obj->launches += 1;
-        if (want_grad)
-        {
-            const dim3 grid(static_cast<unsigned>((D + kBwdCols - 1) / kBwdCols),
-                            static_cast<unsigned>((T + kBwdTB - 1) / kBwdTB), static_cast<unsigned>(obj->gen_splits));
-            gen_backward_kernel<<<grid, kBwdCols, 0, obj->stream>>>(data->X, obj->d_dL, N, D, T, obj->d_partials_gw);
-            NB200_CUDA_TRY(cudaGetLastError());
-            obj->launches += 1;
-        }
-        if (obj->timing)
-        {
-            NB200_CUDA_TRY(cudaEventRecord(obj->ev1, obj->stream));
-        }
-
-        const int64_t cols_fb = want_grad ? (1 + T) : 1;
-        reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, obj->stream>>>(
-            obj->d_partials, obj->gen_blocks, 1 + T, cols_fb, obj->d_reduced);
-        NB200_CUDA_TRY(cudaGetLastError());
-        obj->launches += 1;
-        if (want_grad)
-        {
-            reduce_partials_kernel<<<static_cast<unsigned>((T * D + 127) / 128), 128, 0, obj->stream>>>(
-                obj->d_partials_gw, obj->gen_splits, T * D, T * D, obj->d_reduced + 1 + T);
-            NB200_CUDA_TRY(cudaGetLastError());
-            obj->launches += 1;
-        }
-    }
-    obj->pass_pending = obj->timing;
     return NB200_OK;
 }
 
@@ -509,19 +461,115 @@ int enqueue_finish(nb200_obj* obj, const double* x_dev, const int64_t n_global, 
     return NB200_OK;
 }
 
-void collect_timing(nb200_obj* obj)
+// Enqueue one evaluation on obj->stream.
+//   finish == false: stop at the un-normalised [sum loss | sum dL | sum dL x^T] in obj->d_reduced (phase 1 of a
+//                    sample-sharded evaluation);
+//   finish == true:  also divide by n_global, add the regularisation terms and write gx_out (nullable) / fx_out.
+// The single-target path does all of it in ONE cooperative launch; the generic path takes 3-6 small launches.
+int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, const bool finish, const int64_t n_global,
+                 double* gx_out, double* fx_out)
 {
-    if (obj->pass_pending)
+    const nb200_data* data = obj->data;
+    const int64_t     N = data->N, D = data->D, T = data->T;
+    const double*     W    = x_dev;
+    const double*     bias = (obj->flavour == NB200_FLAVOUR_LINEAR) ? (x_dev + T * D) : obj->d_fixed_bias;
+
+    int status = timing_begin(obj);
+    if (status != NB200_OK)
     {
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, obj->ev0, obj->ev1) == cudaSuccess)
-        {
-            obj->last_pass_ms = ms;
-            obj->pass_ms_total += ms;
-            obj->pass_count += 1;
-        }
-        obj->pass_pending = false;
+        return status;
     }
+
+    if (obj->use_t1)
+    {
+        const t1_variant& var = kT1Variants[obj->t1.variant];
+        obj->grid_epoch += 1;
+
+        t1_params p{};
+        p.X              = data->X;
+        p.Y              = data->Y;
+        p.w              = W;
+        p.bias           = bias;
+        p.partials       = obj->d_partials;
+        p.N              = N;
+        p.num_tiles      = obj->t1.num_tiles;
+        p.D              = static_cast<int>(D);
+        p.rows_per_stage = obj->t1.rows_per_stage;
+        p.rows_per_group = obj->t1.rows_per_group;
+        p.stages         = obj->t1.stages;
+        p.stage_stride   = obj->t1.stage_stride;
+        p.y_offset       = obj->t1.y_offset;
+        p.loss           = obj->loss;
+        p.loss_param     = obj->loss_param;
+        p.grid_counter   = obj->d_grid_counter;
+        p.grid_target    = obj->grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
+        p.reduced        = obj->d_reduced;
+        p.fuse_finish    = finish ? 1 : 0;
+        p.flavour        = obj->flavour;
+        p.gx_out         = finish ? gx_out : nullptr;
+        p.fx_out         = fx_out;
+        p.n_global       = n_global;
+        p.l1             = obj->l1;
+        p.l2             = obj->l2;
+
+        // cooperative launch: the grid barrier of the fused tail needs every CTA resident (grid <= #SMs, 1 CTA/SM)
+        void*       args[] = {&p};
+        const void* kernel = reinterpret_cast<const void*>(want_grad ? var.grad : var.value);
+        NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32), args,
+                                                   static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
+        obj->launches += 1;
+        return timing_end(obj);
+    }
+
+    gen_params p{};
+    p.X           = data->X;
+    p.Y           = data->Y;
+    p.W           = W;
+    p.b           = bias;
+    p.dL          = want_grad ? obj->d_dL : nullptr;
+    p.partials_fb = obj->d_partials;
+    p.N           = N;
+    p.D           = D;
+    p.T           = T;
+    p.loss        = obj->loss;
+    p.loss_param  = obj->loss_param;
+    if (want_grad)
+    {
+        gen_forward_kernel<true><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
+    }
+    else
+    {
+        gen_forward_kernel<false><<<obj->gen_blocks, kGenWarps * 32, obj->gen_smem, obj->stream>>>(p);
+    }
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    if (want_grad)
+    {
+        const dim3 grid(static_cast<unsigned>((D + kBwdCols - 1) / kBwdCols),
+                        static_cast<unsigned>((T + kBwdTB - 1) / kBwdTB), static_cast<unsigned>(obj->gen_splits));
+        gen_backward_kernel<<<grid, kBwdCols, 0, obj->stream>>>(data->X, obj->d_dL, N, D, T, obj->d_partials_gw);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+    }
+    status = timing_end(obj);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+
+    const int64_t cols_fb = want_grad ? (1 + T) : 1;
+    reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, obj->stream>>>(
+        obj->d_partials, obj->gen_blocks, 1 + T, cols_fb, obj->d_reduced);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    if (want_grad)
+    {
+        reduce_partials_kernel<<<static_cast<unsigned>((T * D + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials_gw, obj->gen_splits, T * D, T * D, obj->d_reduced + 1 + T);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+    }
+    return finish ? enqueue_finish(obj, x_dev, n_global, gx_out, fx_out) : NB200_OK;
 }
 
 int upload_x(nb200_obj* obj, const double* x, const int64_t n)
@@ -534,19 +582,10 @@ int upload_x(nb200_obj* obj, const double* x, const int64_t n)
     return NB200_OK;
 }
 
-int download_result(nb200_obj* obj, double* gx, double* fx)
+// the kernels wrote (g, f) into the mapped pinned buffer: wait for the stream, hand the values to the caller
+int collect_result(nb200_obj* obj, double* gx, double* fx)
 {
     const size_t n = static_cast<size_t>(obj->n);
-    if (gx != nullptr)
-    {
-        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out, obj->d_out, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost,
-                                       obj->stream));
-    }
-    else
-    {
-        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out + n, obj->d_out + n, sizeof(double), cudaMemcpyDeviceToHost,
-                                       obj->stream));
-    }
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
     collect_timing(obj);
     if (gx != nullptr)
@@ -828,15 +867,12 @@ int nb200_vgrad(nb200_obj* obj, const double* x, const int64_t n, double* gx, do
     int status = upload_x(obj, x, n);
     if (status == NB200_OK)
     {
-        status = enqueue_partial(obj, obj->d_x, gx != nullptr);
+        status = enqueue_eval(obj, obj->d_x, gx != nullptr, true, obj->data->N,
+                              gx != nullptr ? obj->h_out_dev : nullptr, obj->h_out_dev + obj->n);
     }
     if (status == NB200_OK)
     {
-        status = enqueue_finish(obj, obj->d_x, obj->data->N, gx != nullptr ? obj->d_out : nullptr, obj->d_out + obj->n);
-    }
-    if (status == NB200_OK)
-    {
-        status = download_result(obj, gx, fx);
+        status = collect_result(obj, gx, fx);
     }
     return status;
 }
@@ -846,12 +882,7 @@ int nb200_vgrad_device(nb200_obj* obj, const double* x_dev, const int64_t n, dou
     NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
     NB200_REQUIRE(n == obj->n, "function: invalid input size");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    int status = enqueue_partial(obj, x_dev, gx_dev != nullptr);
-    if (status == NB200_OK)
-    {
-        status = enqueue_finish(obj, x_dev, obj->data->N, gx_dev, fx_dev);
-    }
-    return status;
+    return enqueue_eval(obj, x_dev, gx_dev != nullptr, true, obj->data->N, gx_dev, fx_dev);
 }
 
 int nb200_objective_sync(nb200_obj* obj)
@@ -872,7 +903,7 @@ int nb200_vgrad_partial(nb200_obj* obj, const double* x, const int64_t n, const 
     int status = upload_x(obj, x, n);
     if (status == NB200_OK)
     {
-        status = enqueue_partial(obj, obj->d_x, want_grad != 0);
+        status = enqueue_eval(obj, obj->d_x, want_grad != 0, false, 0, nullptr, nullptr);
     }
     if (status == NB200_OK)
     {
@@ -889,10 +920,11 @@ int nb200_vgrad_finish(nb200_obj* obj, const int64_t n_global, double* gx, doubl
     NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
     NB200_REQUIRE(gx == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    int status = enqueue_finish(obj, obj->d_x, n_global, gx != nullptr ? obj->d_out : nullptr, obj->d_out + obj->n);
+    int status = enqueue_finish(obj, obj->d_x, n_global, gx != nullptr ? obj->h_out_dev : nullptr,
+                                obj->h_out_dev + obj->n);
     if (status == NB200_OK)
     {
-        status = download_result(obj, gx, fx);
+        status = collect_result(obj, gx, fx);
     }
     return status;
 }
@@ -904,7 +936,7 @@ int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, const int64_
                   "function: null argument");
     NB200_REQUIRE(n == obj->n, "function: invalid input size");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    const int status = enqueue_partial(obj, x_dev, want_grad != 0);
+    const int status = enqueue_eval(obj, x_dev, want_grad != 0, false, 0, nullptr, nullptr);
     if (status == NB200_OK)
     {
         obj->partial_has_grad = want_grad != 0;
@@ -929,12 +961,14 @@ void* nb200_objective_stream(const nb200_obj* obj)
     return obj != nullptr ? static_cast<void*>(obj->stream) : nullptr;
 }
 
-int nb200_objective_set_stream(nb200_obj* obj, void* stream)
+int nb200_objective_set_stream(nb200_obj* obj, void* stream, const int use_own)
 {
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
-    obj->stream = (stream != nullptr) ? static_cast<cudaStream_t>(stream) : obj->own_stream;
+    collect_timing(obj);
+    // a null handle with use_own == 0 is the legacy default stream (what torch.cuda.current_stream() is by default)
+    obj->stream = (use_own != 0) ? obj->own_stream : static_cast<cudaStream_t>(stream);
     return NB200_OK;
 }
 
@@ -956,7 +990,7 @@ double nb200_objective_last_pass_ms(nb200_obj* obj)
     {
         return -1.0;
     }
-    if (obj->pass_pending)
+    if (obj->pass_pending > 0)
     {
         cudaSetDevice(obj->device);
         if (cudaStreamSynchronize(obj->stream) != cudaSuccess)

@@ -1,10 +1,12 @@
-// vgrad_t1.cuh — the hot kernel: ONE pass over X for a single-target linear model.
+// vgrad_t1.cuh — the hot kernel: ONE pass over X for a single-target linear model, ONE launch per evaluation.
 //
 // Replaces, for T == 1, the per-batch body of linear::function_t::do_eval (src/linear/function.cpp:53-72):
 //   predict (src/linear/util.cpp:19-20)  o_i = x_i . w + b
 //   loss value + vgrad (flatten.h:69-86) l_i, dL_i
 //   accumulation (function.cpp:62,69-70) sum l_i ; sum dL_i ; sum dL_i * x_i
-// and likewise linear_model_t::eval (src/function/mlearn/linear.h:21-38, two passes over X in the reference).
+// the reduction over workers (sum_reduce, include/nano/core/reduce.h:23-31) and the regularisation block
+// (function.cpp:127-143,158-167); likewise linear_model_t::eval (src/function/mlearn/linear.h:21-38, two passes
+// over X in the reference) with the regularisers of ridge.cpp:63-80 / lasso.cpp:63-76 / elasticnet.cpp:67-86.
 //
 // Design (HBM-bound: 8 bytes of X per 4 flops):
 //   * persistent CTAs (one per SM), static round-robin tiles of RPS consecutive rows => fixed summation order;
@@ -14,11 +16,14 @@
 //     butterfly all-reduce, loss + dL in registers, then dL * x is accumulated into per-lane column slices — X is
 //     read from shared memory exactly once and from HBM exactly once;
 //   * the stage is released as soon as its rows sit in registers, before the loss math;
-//   * per-CTA partials [loss | gb | gW] are reduced across the grid by a second, fixed-order kernel (reduce.cuh).
+//   * per-CTA partials [loss | gb | gW] are folded IN THE SAME LAUNCH: a grid-wide barrier (cooperative launch), then
+//     every CTA reduces a slice of columns over all CTAs in a fixed order and — single-rank case — applies 1/N and the
+//     regularisation terms and writes (g, f) straight to the output (which may be mapped host memory).
+//     Sample-sharded ranks stop at the un-normalised sums and all-reduce them (sharded.py).
 //
 // Template knobs: V = doubles per lane per 32-lane chunk (2 => 128-bit loads, needs even D; 1 => any D),
 // KC = chunks per warp (a warp covers 32*V*KC columns), WS = warps cooperating on one row (row split in WS
-// column slices), GRAD = accumulate the gradient (false: value-only call, function(x) without gx).
+// column slices), NCW = consumer warps, GRAD = accumulate the gradient (false: value-only call).
 #pragma once
 
 #include "common.cuh"
@@ -27,7 +32,7 @@
 namespace nb200
 {
 constexpr int kT1MaxStages  = 8;
-constexpr int kT1HeaderSize = 1024; // barriers + dot-exchange slots
+constexpr int kT1HeaderSize = 1024; // barriers + dot-exchange slots + tail scratch
 
 struct t1_params
 {
@@ -46,80 +51,59 @@ struct t1_params
     int           y_offset;     // byte offset of the Y tile inside a stage (multiple of 128)
     int           loss;
     double        loss_param;
+
+    // fused tail: cross-CTA reduction after a grid-wide barrier, optionally followed by the final scaling
+    unsigned long long* grid_counter; // monotonically increasing arrival counter (never reset between launches)
+    unsigned long long  grid_target;  // counter value at which every CTA of THIS launch has arrived
+    double*             reduced;      // [D + 2] un-normalised sums out (always written)
+    int                 fuse_finish;  // 1: also write gx_out / fx_out (single-rank evaluation)
+    int                 flavour;      // 0 LINEAR, 1 SYNTH
+    double*             gx_out;       // [D + 1] (LINEAR) or [D] (SYNTH); device or mapped host memory
+    double*             fx_out;       // 1 double
+    int64_t             n_global;
+    double              l1;
+    double              l2;
 };
 
 #ifdef __CUDACC__
 
-template <int V, int KC, int WS, int NCW, bool GRAD>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_params p)
+// grid-wide barrier for a cooperative launch (all CTAs co-resident). The counter only grows: launch k of a plan
+// with G CTAs waits for the value k * G, so no reset is needed between launches.
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, const unsigned long long target)
 {
-    static_assert(V == 1 || V == 2, "V is 1 (64-bit loads) or 2 (128-bit loads)");
-    static_assert(NCW % WS == 0, "consumer warps must split evenly into row groups");
-    constexpr int NG  = NCW / WS; // row groups
-    constexpr int CPW = 32 * V * KC; // columns per warp
-
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty_bar = full_bar + kT1MaxStages;
-    double*   exchange  = reinterpret_cast<double*>(smem + 2 * kT1MaxStages * sizeof(uint64_t)); // [NG][2][WS]
-    const int w_bytes   = static_cast<int>((static_cast<int64_t>(p.D) * 8 + 127) / 128 * 128);
-    double*   w_s       = reinterpret_cast<double*>(smem + kT1HeaderSize);
-    unsigned char* stage_base = smem + kT1HeaderSize + w_bytes;
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int D    = p.D;
-
+    __syncthreads();
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < p.stages; ++s)
+        __threadfence(); // publish this CTA's partials device-wide before signalling
+        atomicAdd(counter, 1ULL);
+        unsigned long long seen;
+        do
         {
-            mbar_init(full_bar + s, 1);
-            mbar_init(empty_bar + s, NCW);
-        }
-        mbar_fence_init();
-    }
-    for (int j = threadIdx.x; j < D; j += blockDim.x)
-    {
-        w_s[j] = p.w[j];
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();
     }
     __syncthreads();
+}
 
+// ---------------------------------------------------------------------------------------------------------------
+// consumer role: rows -> registers -> dot -> loss -> gradient slices; leaves this CTA's partial row in HBM
+// ---------------------------------------------------------------------------------------------------------------
+template <int V, int KC, int WS, int NCW, bool GRAD>
+__device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_bar, uint64_t* empty_bar,
+                                             double* exchange, const double* w_s, unsigned char* stage_base,
+                                             const int warp, const int lane)
+{
+    constexpr int NG  = NCW / WS;    // row groups
+    constexpr int CPW = 32 * V * KC; // columns per warp
+    const int     D   = p.D;
     const int64_t rps = p.rows_per_stage;
 
-    if (warp == NCW)
-    {
-        // ===== producer warp: one lane feeds the ring =====
-        if (lane == 0)
-        {
-            const uint64_t policy = l2_policy_evict_first();
-            int            it     = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
-            {
-                const int      s     = it % p.stages;
-                const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
-                mbar_wait(empty_bar + s, phase ^ 1u); // passes at once on the first lap
+    const int group = warp / WS;   // which rows of a stage
+    const int slice = warp % WS;   // which columns of a row
+    const int cbase = slice * CPW; // first column of this warp's slice
 
-                const int64_t  row0    = tile * rps;
-                const int64_t  rows    = min(rps, p.N - row0);
-                const uint32_t bytes_x = static_cast<uint32_t>((rows * D * 8 + 15) / 16 * 16);
-                const uint32_t bytes_y = static_cast<uint32_t>((rows * 8 + 15) / 16 * 16);
-                unsigned char* stage   = stage_base + static_cast<int64_t>(s) * p.stage_stride;
-
-                mbar_arrive_expect_tx(full_bar + s, bytes_x + bytes_y);
-                bulk_copy_g2s(stage, p.X + row0 * D, bytes_x, full_bar + s, policy);
-                bulk_copy_g2s(stage + p.y_offset, p.Y + row0, bytes_y, full_bar + s, policy);
-            }
-        }
-        return;
-    }
-
-    // ===== consumer warps =====
-    const int group = warp / WS;          // which rows of a stage
-    const int slice = warp % WS;          // which columns of a row
-    const int cbase = slice * CPW;        // first column of this warp's slice
-
-    double g[V * KC];  // per-lane slice of sum dL_i * x_i
+    double g[V * KC]; // per-lane slice of sum dL_i * x_i
 #pragma unroll
     for (int k = 0; k < V * KC; ++k)
     {
@@ -162,7 +146,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
 
             // row slice -> registers; partial dot with w
             double x[V * KC];
-            double acc0 = 0.0, acc1 = 0.0;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
             for (int k = 0; k < KC; ++k)
             {
@@ -177,8 +161,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
                     }
                     x[2 * k]     = xv.x;
                     x[2 * k + 1] = xv.y;
-                    acc0         = fma(xv.x, wv.x, acc0);
-                    acc1         = fma(xv.y, wv.y, acc1);
+                    if (k & 1)
+                    {
+                        acc2 = fma(xv.x, wv.x, acc2);
+                        acc3 = fma(xv.y, wv.y, acc3);
+                    }
+                    else
+                    {
+                        acc0 = fma(xv.x, wv.x, acc0);
+                        acc1 = fma(xv.y, wv.y, acc1);
+                    }
                 }
                 else
                 {
@@ -189,13 +181,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
                         wv = w_s[col];
                     }
                     x[k] = xv;
-                    if (k & 1)
+                    switch (k & 3)
                     {
-                        acc1 = fma(xv, wv, acc1);
-                    }
-                    else
-                    {
-                        acc0 = fma(xv, wv, acc0);
+                    case 0: acc0 = fma(xv, wv, acc0); break;
+                    case 1: acc1 = fma(xv, wv, acc1); break;
+                    case 2: acc2 = fma(xv, wv, acc2); break;
+                    default: acc3 = fma(xv, wv, acc3); break;
                     }
                 }
             }
@@ -211,7 +202,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
                 }
             }
 
-            double dot = warp_allreduce_sum(acc0 + acc1);
+            double dot = warp_allreduce_sum((acc0 + acc1) + (acc2 + acc3));
             if constexpr (WS > 1)
             {
                 // combine the column slices of the WS warps sharing this row, in slice order
@@ -248,12 +239,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
         }
     }
 
-    // ===== epilogue: fixed-order reduction of the row groups inside the CTA, through the (now idle) stages =====
+    // fixed-order reduction of the row groups inside the CTA, through the (now idle) stages
     named_bar_sync(15, NCW * 32); // every consumer left the main loop; all issued copies have been consumed
 
     const int dpad = WS * CPW;
-    double*   red  = reinterpret_cast<double*>(stage_base);          // [NG][dpad]
-    double*   redf = red + static_cast<int64_t>(NG) * dpad;          // [NG] loss sums, then [NG] dL sums
+    double*   red  = reinterpret_cast<double*>(stage_base);  // [NG][dpad]
+    double*   redf = red + static_cast<int64_t>(NG) * dpad;  // [NG] loss sums, then [NG] dL sums
 
     if constexpr (GRAD)
     {
@@ -301,6 +292,216 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) vgrad_t1_kernel(const t1_pa
         out[0] = f;
         out[1] = b;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tail (all warps): grid barrier, then this CTA folds its slice of columns over every CTA's partial row
+// (sum_reduce, include/nano/core/reduce.h:23-31) and, when fuse_finish, applies the final scaling and the
+// regularisation terms (src/linear/function.cpp:127-143,158-167 / src/function/mlearn/{ridge,lasso,elasticnet}.cpp).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NWARPS, bool GRAD>
+__device__ __forceinline__ void fold_partials(const t1_params& p, const double* w_s, double* scratch, const int warp,
+                                              const int lane)
+{
+    const int D    = p.D;
+    const int G    = static_cast<int>(gridDim.x);
+    const int cols = GRAD ? (D + 2) : 2;
+
+    grid_barrier(p.grid_counter, p.grid_target);
+
+    // regularisation sums over w, needed by the CTA that owns column 0 (the loss sum)
+    const bool owns_value = blockIdx.x == 0;
+    if (owns_value && p.fuse_finish != 0)
+    {
+        double a = 0.0, q = 0.0;
+        if (p.l1 > 0.0 || p.l2 > 0.0)
+        {
+            const double root = sqrt(p.l2);
+            for (int j = threadIdx.x; j < D; j += NWARPS * 32)
+            {
+                const double w = w_s[j];
+                a += fabs(w);
+                const double sw = __dmul_rn(root, w);
+                q               = __dadd_rn(q, __dmul_rn(sw, sw));
+            }
+        }
+        a = warp_allreduce_sum(a);
+        q = warp_allreduce_sum(q);
+        if (lane == 0)
+        {
+            scratch[warp]          = a;
+            scratch[NWARPS + warp] = q;
+        }
+        __syncthreads();
+    }
+
+    const int     cpc      = (cols + G - 1) / G; // columns per CTA
+    const int     c_begin  = blockIdx.x * cpc;
+    const int     c_end    = min(cols, c_begin + cpc);
+    const int64_t stride   = D + 2;
+    const double  samples  = static_cast<double>(p.n_global);
+    const double  wsize    = static_cast<double>(D); // T == 1
+
+    for (int c = c_begin + warp; c < c_end; c += NWARPS)
+    {
+        // lanes stride over the CTAs, then a butterfly: a fixed order that depends on the grid size only
+        double sum = 0.0;
+        for (int r = lane; r < G; r += 32)
+        {
+            sum += __ldcg(p.partials + static_cast<int64_t>(r) * stride + c);
+        }
+        sum = warp_allreduce_sum(sum);
+        if (lane != 0)
+        {
+            continue;
+        }
+        p.reduced[c] = sum;
+        if (p.fuse_finish == 0)
+        {
+            continue;
+        }
+        if (c == 0)
+        {
+            double sabs = 0.0, ssqr = 0.0;
+            for (int q = 0; q < NWARPS; ++q)
+            {
+                sabs += scratch[q];
+                ssqr += scratch[NWARPS + q];
+            }
+            double fx = __ddiv_rn(sum, samples);
+            if (p.flavour == 0)
+            {
+                if (p.l1 > 0.0)
+                {
+                    fx = __dadd_rn(fx, __dmul_rn(p.l1, __ddiv_rn(sabs, wsize)));
+                }
+                if (p.l2 > 0.0)
+                {
+                    fx = __dadd_rn(fx, __dmul_rn(0.5, __ddiv_rn(ssqr, wsize)));
+                }
+            }
+            else
+            {
+                fx = __dadd_rn(fx, __dadd_rn(__dmul_rn(p.l1, sabs), __dmul_rn(0.5, ssqr)));
+            }
+            *p.fx_out = fx;
+        }
+        else if (c == 1)
+        {
+            if (p.flavour == 0 && p.gx_out != nullptr)
+            {
+                p.gx_out[D] = __ddiv_rn(sum, samples); // gb = acc.m_gb / N
+            }
+        }
+        else if (p.gx_out != nullptr)
+        {
+            const int    j  = c - 2;
+            const double wj = w_s[j];
+            double       gj = __ddiv_rn(sum, samples);
+            if (p.flavour == 0)
+            {
+                if (p.l1 > 0.0)
+                {
+                    gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l1, sign_of(wj)), wsize));
+                }
+                if (p.l2 > 0.0)
+                {
+                    gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l2, wj), wsize));
+                }
+            }
+            else
+            {
+                gj = __dadd_rn(gj, __dadd_rn(__dmul_rn(p.l1, sign_of(wj)), __dmul_rn(p.l2, wj)));
+            }
+            p.gx_out[j] = gj;
+        }
+    }
+}
+
+// Warp roles: NCW consumer warps (whole warpgroups) + one producer warpgroup (its first warp feeds the ring, the
+// other three idle until the tail). The producer warpgroup hands its registers to the consumers (setmaxnreg): the
+// 128-register row + gradient slices of the widest variant then fit without spilling.
+constexpr int kT1ProducerWarps = 4;
+constexpr int kT1ProducerRegs  = 40;
+
+template <int NCW>
+struct t1_consumer_regs
+{
+    static constexpr int kBudget = ((65536 - kT1ProducerWarps * 32 * kT1ProducerRegs) / (NCW * 32)) / 8 * 8;
+    static constexpr int value   = kBudget > 232 ? 232 : kBudget;
+};
+
+template <int V, int KC, int WS, int NCW, bool GRAD>
+__global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_kernel(const t1_params p)
+{
+    static_assert(V == 1 || V == 2, "V is 1 (64-bit loads) or 2 (128-bit loads)");
+    static_assert(NCW % WS == 0, "consumer warps must split evenly into row groups");
+    static_assert(NCW % 4 == 0, "consumer warps must form whole warpgroups (setmaxnreg is per warpgroup)");
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + kT1MaxStages;
+    double*   exchange  = reinterpret_cast<double*>(smem + 2 * kT1MaxStages * sizeof(uint64_t)); // [NG][2][WS]
+    double*   scratch   = reinterpret_cast<double*>(smem + 512);                                 // tail: [2][warps]
+    const int w_bytes   = static_cast<int>((static_cast<int64_t>(p.D) * 8 + 127) / 128 * 128);
+    double*   w_s       = reinterpret_cast<double*>(smem + kT1HeaderSize);
+    unsigned char* stage_base = smem + kT1HeaderSize + w_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int D    = p.D;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < p.stages; ++s)
+        {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, NCW);
+        }
+        mbar_fence_init();
+    }
+    for (int j = threadIdx.x; j < D; j += blockDim.x)
+    {
+        w_s[j] = p.w[j];
+    }
+    __syncthreads();
+
+    if (warp >= NCW)
+    {
+        // ===== producer warpgroup: one lane of its first warp feeds the ring =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT1ProducerRegs));
+        if (warp == NCW && lane == 0)
+        {
+            const int64_t  rps    = p.rows_per_stage;
+            const uint64_t policy = l2_policy_evict_first();
+            int            it     = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
+            {
+                const int      s     = it % p.stages;
+                const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+                mbar_wait(empty_bar + s, phase ^ 1u); // passes at once on the first lap
+
+                const int64_t  row0    = tile * rps;
+                const int64_t  rows    = min(rps, p.N - row0);
+                const uint32_t bytes_x = static_cast<uint32_t>((rows * D * 8 + 15) / 16 * 16);
+                const uint32_t bytes_y = static_cast<uint32_t>((rows * 8 + 15) / 16 * 16);
+                unsigned char* stage   = stage_base + static_cast<int64_t>(s) * p.stage_stride;
+
+                mbar_arrive_expect_tx(full_bar + s, bytes_x + bytes_y);
+                bulk_copy_g2s(stage, p.X + row0 * D, bytes_x, full_bar + s, policy);
+                bulk_copy_g2s(stage + p.y_offset, p.Y + row0, bytes_y, full_bar + s, policy);
+            }
+        }
+        __syncwarp();
+    }
+    else
+    {
+        // ===== consumer warpgroups =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(t1_consumer_regs<NCW>::value));
+        consume_rows<V, KC, WS, NCW, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
+    }
+
+    fold_partials<NCW + kT1ProducerWarps, GRAD>(p, w_s, scratch, warp, lane);
 }
 
 #endif // __CUDACC__

@@ -261,7 +261,10 @@ class _DeviceFunction(Function):
         return int(_lib.lib().nb200_objective_stream(self.handle) or 0)
 
     def set_stream(self, stream: int | None) -> None:
-        _lib.check(_lib.lib().nb200_objective_set_stream(self.handle, ctypes.c_void_p(stream or 0)))
+        """Order every launch of this objective on the given cudaStream_t (0 = the legacy default stream);
+        None goes back to the objective's own stream."""
+        _lib.check(_lib.lib().nb200_objective_set_stream(self.handle, ctypes.c_void_p(stream or 0),
+                                                         int(stream is None)))
 
     # -- introspection -------------------------------------------------------------------------------------------------
     def launches(self) -> int:

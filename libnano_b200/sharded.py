@@ -74,6 +74,10 @@ class DeviceShard:
     def finish(self, n_global: int, gx):
         return self.local.finish(n_global, gx)
 
+    def eval(self, x, gx):
+        """Single-rank shortcut: the fused one-launch evaluation (no all-reduce to wait for)."""
+        return self.local.do_eval(x, gx)
+
 
 class ShardedFunction(Function):
     """function_t over ALL samples of a dataset whose rows are spread over the ranks of a process group.
@@ -102,8 +106,10 @@ class ShardedFunction(Function):
         return self._dist.get_world_size(self._group) if self._dist.is_initialized() else 1
 
     def do_eval(self, x, gx) -> float:
+        if self.world_size() == 1 and hasattr(self._shard, "eval"):
+            return self._shard.eval(x, gx)
         buffer = self._shard.partial(x, gx is not None)
-        if self._dist.is_initialized() and self._dist.get_world_size(self._group) > 1:
+        if self.world_size() > 1:
             self._dist.all_reduce(buffer, op=self._dist.ReduceOp.SUM, group=self._group)
         return self._shard.finish(self._n_global, gx)
 

@@ -102,7 +102,8 @@ def test_partial_finish_and_logical_shards(ctx, oracle, N, D, T, loss_id):
     assert length == 1 + T + T * D
     g = np.empty_like(x)
     f = whole.finish(N, g)
-    assert f == f_ref and np.array_equal(g, g_ref)
+    # same sums; only the order of the O(D) regulariser sums differs between the fused tail and finish_kernel
+    assert rel_f(f, f_ref) <= 1e-15 and rel_g(g, g_ref) <= 1e-15
 
     # (2) k logical shards, partial sums added on the host in rank order, finished with N_global
     for k in (2, 3, 8):
