@@ -11,7 +11,7 @@
  *   accumulator_t + sum_reduce                    src/linear/accumulator.cpp, include/nano/core/reduce.h:23-31
  *                                                 -> nb200_vgrad_partial + (all-reduce) + nb200_vgrad_finish
  *   flatten_iterator_t::cache_flatten/targets     src/dataset/iterator.cpp:118-147,52-77 -> nb200_dataset_pin
- *   linear_model_t + function_{ridge,lasso,elasticnet}_t   src/function/mlearn/*  -> flavour NB200_FLAVOUR_SYNTH
+ *   linear_model_t + function_{ridge,lasso,elasticnet}_t   src/function/mlearn/   -> flavour NB200_FLAVOUR_SYNTH
  *
  * Threading contract (same as the reference's `const do_eval` + `mutable` scratch): one call in
  * flight per nb200_obj; distinct objects (clones) sharing one nb200_data may be used concurrently.

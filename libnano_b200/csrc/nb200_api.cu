@@ -129,7 +129,7 @@ bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, 
     const int64_t w_bytes  = round_up(D * 8, 128);
     const int64_t avail    = static_cast<int64_t>(smem_optin) - kT1HeaderSize - w_bytes;
     const int64_t row_b    = D * 8;
-    const int64_t target   = env_int("NB200_STAGE_BYTES", 32768);
+    const int64_t target   = env_int("NB200_STAGE_BYTES", 65536);
     const int     stages_x = env_int("NB200_STAGES", kT1MaxStages);
 
     int64_t rpg = std::max<int64_t>(1, target / (NG * row_b));
@@ -301,6 +301,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
             NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(plan.grid) * (D + 2) * sizeof(double)));
             obj->t1     = plan;
             obj->use_t1 = true;
+            NB200_CUDA_TRY(cudaDeviceSynchronize()); // the memsets above ran on the legacy stream
             return NB200_OK;
         }
     }
@@ -329,6 +330,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(obj->gen_blocks) * (1 + T) * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(splits) * T * D * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
+    NB200_CUDA_TRY(cudaDeviceSynchronize()); // the memsets above ran on the legacy stream; launches use obj->stream
     return NB200_OK;
 }
 

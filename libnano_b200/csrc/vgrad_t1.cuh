@@ -427,8 +427,15 @@ constexpr int kT1ProducerRegs  = 40;
 template <int NCW>
 struct t1_consumer_regs
 {
-    static constexpr int kBudget = ((65536 - kT1ProducerWarps * 32 * kT1ProducerRegs) / (NCW * 32)) / 8 * 8;
-    static constexpr int value   = kBudget > 232 ? 232 : kBudget;
+    // ptxas allocates the launch-bound maximum per thread when a kernel uses setmaxnreg (checked with -Xptxas -v:
+    // 168 / 128 / 96 registers for 8 / 12 / 16 consumer warps); the CTA's pool is that times the thread count, and
+    // asking for more than the pool holds would block setmaxnreg.inc forever.
+    static constexpr int kThreads    = (NCW + kT1ProducerWarps) * 32;
+    static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+    static constexpr int kPool       = kThreads * kLaunchRegs;
+    static constexpr int kBudget     = ((kPool - kT1ProducerWarps * 32 * kT1ProducerRegs) / (NCW * 32)) / 8 * 8;
+    static constexpr int value       = kBudget > 232 ? 232 : kBudget;
+    static_assert(kLaunchRegs <= 255 && value >= kLaunchRegs, "register hand-over must not shrink the consumers");
 };
 
 template <int V, int KC, int WS, int NCW, bool GRAD>

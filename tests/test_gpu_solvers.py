@@ -1,0 +1,89 @@
+"""End-to-end on the GPU: the restated libnano drivers (oracle/solvers.cpp: L-BFGS + CG-DESCENT, OSGA) minimise the
+GPU objective and the CPU oracle objective from the same start; the optima agree within the solver's epsilon
+(BASELINE.json north_star). Mirrors test/test_linear_function.cpp:51-65,152-188 (minimize_noreg: lbfgs + cgdescent,
+epsilon 1e-10, recovers the generating weights) and the non-smooth cases driven by OSGA."""
+import numpy as np
+import pytest
+
+from conftest import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_objective(oracle, X, Y, loss_id, l1, l2):
+    def function(x, gx=None):
+        fx, g = oracle.linear_vgrad(X, Y, loss_id, x, l1, l2, want_grad=gx is not None)
+        if gx is not None:
+            gx[:] = g
+        return fx
+
+    return function
+
+
+def test_minimize_noreg_recovers_ground_truth(ctx, oracle):
+    # noise-free linear targets: the unregularised mse objective has its minimum (0) at the generating (W, b)
+    import libnano_b200 as nb
+
+    rng = np.random.default_rng(0)
+    N, D, T = 50, 4, 1
+    X = rng.uniform(-1, 1, (N, D))
+    W, b = rng.uniform(-1, 1, (T, D)), rng.uniform(-1, 1, T)
+    Y = X @ W.T + b
+    function = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss("mse"), 0.0, 0.0)
+    result = oracle.lbfgs(function, np.zeros(function.size()), epsilon=1e-10, max_evals=10000)
+    assert result["status"] == "gradient_test"
+    assert abs(result["fx"]) < 1e-7 and function.fcalls() > 5
+    assert np.max(np.abs(function.weights(result["x"]) - W)) < 1e-7
+    assert np.max(np.abs(function.bias(result["x"]) - b)) < 1e-7
+    # call counters seen by the solver == the function's own (test/fixture/solver.h:178-294)
+    assert (result["fcalls"], result["gcalls"]) == (function.fcalls(), function.gcalls())
+
+
+@pytest.mark.parametrize("N,D,T,loss_id,l2", [(20000, 64, 1, "s-logistic", 1e-2), (5000, 32, 3, "s-classnll", 1e-2),
+                                              (8000, 100, 1, "mse", 0.0)])
+def test_lbfgs_reaches_the_same_optimum_on_gpu_and_cpu(ctx, oracle, N, D, T, loss_id, l2):
+    import libnano_b200 as nb
+
+    X, Y, _ = make_problem(1, N, D, T, loss_id != "mse")
+    gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss(loss_id), 0.0, l2)
+    cpu = oracle_objective(oracle, X, Y, loss_id, 0.0, l2)
+    x0 = np.zeros(gpu.size())
+    epsilon = 1e-8
+    r_gpu = oracle.lbfgs(gpu, x0, epsilon=epsilon, max_evals=1000)
+    r_cpu = oracle.lbfgs(cpu, x0, epsilon=epsilon, max_evals=1000)
+    assert r_gpu["status"] == r_cpu["status"] == "gradient_test"
+    assert r_gpu["gradient_test"] < epsilon and r_cpu["gradient_test"] < epsilon
+    assert abs(r_gpu["fx"] - r_cpu["fx"]) <= epsilon * (1 + abs(r_cpu["fx"]))
+    # strongly convex (l2 > 0) => the minimiser is unique: the iterates end within the solver's epsilon of each other
+    if l2 > 0:
+        mu = l2 / (D * T)
+        assert np.max(np.abs(r_gpu["x"] - r_cpu["x"])) <= 10 * epsilon / mu
+    assert abs(r_gpu["fcalls"] - r_cpu["fcalls"]) <= max(3, r_cpu["fcalls"] // 4)
+    # the GPU optimum is a stationary point of the CPU objective too
+    g = np.empty_like(x0)
+    f = cpu(r_gpu["x"], g)
+    assert np.max(np.abs(g)) / max(1.0, abs(f)) < 10 * epsilon
+
+
+@pytest.mark.parametrize("loss_id,l1,l2", [("s-hinge", 1e-2, 0.0), ("s-hinge", 1e-2, 1e-2), ("mae", 0.0, 1e-2)])
+def test_osga_on_nonsmooth_objectives(ctx, oracle, loss_id, l1, l2):
+    # BASELINE config 5 in small: hinge + lasso / elastic-net are non-smooth => OSGA through the GPU vgrad
+    import libnano_b200 as nb
+
+    N, D = 4000, 24
+    X, Y, _ = make_problem(2, N, D, 1, loss_id != "mae")
+    gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss(loss_id), l1, l2)
+    assert not gpu.smooth() and gpu.convex()
+    cpu = oracle_objective(oracle, X, Y, loss_id, l1, l2)
+    x0 = np.zeros(gpu.size())
+    kwargs = dict(epsilon=1e-6, strong_convexity=gpu.strong_convexity(), max_evals=5000, patience=100)
+    r_gpu = oracle.osga(gpu, x0, **kwargs)
+    r_cpu = oracle.osga(cpu, x0, **kwargs)
+    assert r_gpu["status"] in ("specific_test", "value_test", "max_iters")
+    f0 = cpu(x0)
+    assert r_gpu["fx"] < f0 and r_cpu["fx"] < f0  # progress from the start (test_linear_function.cpp l1/l2 variants)
+    # same driver, same objective up to 1e-12 => optima within OSGA's (loose) precision of each other
+    assert abs(r_gpu["fx"] - r_cpu["fx"]) <= 1e-4 * (1 + abs(r_cpu["fx"]))
+    assert abs(cpu(r_gpu["x"]) - r_gpu["fx"]) <= 1e-12 * (1 + abs(r_gpu["fx"]))
+    # one f(x, g) + one f(x') per iteration (src/solver/osga.cpp:101,112)
+    assert r_gpu["fcalls"] == 2 * r_gpu["iterations"] + 1 and r_gpu["gcalls"] == r_gpu["iterations"] + 1

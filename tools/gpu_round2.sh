@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 tail -3 gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -m gpu -q --timeout 300 --maxfail=40 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q --timeout 240 -o timeout_method=thread --maxfail=40 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -12 gpurun_out/pytest_gpu.log
 {
   echo "# 2^20 x 1024 logistic"; timeout 600 python tools/sweep_t1.py --variants 4,17,20 --stage-bytes 65536 --stages 2,3
