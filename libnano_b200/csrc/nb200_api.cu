@@ -17,6 +17,7 @@
 #include "reduce.cuh"
 #include "synth.cuh"
 #include "vgrad_gen.cuh"
+#include "vgrad_mt.cuh"
 #include "vgrad_t1.cuh"
 
 using namespace nb200;
@@ -90,6 +91,28 @@ const t1_variant kT1Variants[] = {
 };
 constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
 constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
+
+using mt_fwd_kernel_t = void (*)(const mt_forward_params);
+using mt_bwd_kernel_t = void (*)(const mt_backward_params);
+
+struct mt_variant
+{
+    int             NT8; // target tiles of 8: covers T <= 8 * NT8
+    mt_fwd_kernel_t grad;
+    mt_fwd_kernel_t value;
+    mt_bwd_kernel_t backward;
+};
+
+#define NB200_MT_VARIANT(NT8)                                                                                          \
+    mt_variant                                                                                                         \
+    {                                                                                                                  \
+        NT8, mt_forward_kernel<NT8, true>, mt_forward_kernel<NT8, false>, mt_backward_kernel<NT8>                      \
+    }
+
+const mt_variant kMtVariants[] = {NB200_MT_VARIANT(1), NB200_MT_VARIANT(2),  NB200_MT_VARIANT(3),
+                                  NB200_MT_VARIANT(4), NB200_MT_VARIANT(6),  NB200_MT_VARIANT(8),
+                                  NB200_MT_VARIANT(10), NB200_MT_VARIANT(13), NB200_MT_VARIANT(16)};
+constexpr int    kNumMtVariants = static_cast<int>(sizeof(kMtVariants) / sizeof(kMtVariants[0]));
 
 constexpr int kTimingRing = 64; // event pairs kept in flight when pass timing is enabled
 
@@ -208,6 +231,11 @@ struct nb200_obj
     int     gen_blocks{0};
     int     gen_splits{0};
     int     gen_smem{0};
+    // many-target tensor-pipe plan (vgrad_mt.cuh)
+    bool    use_mt{false};
+    int     mt_variant{0}; // index into kMtVariants
+    int     mt_fwd_grid{0}, mt_fwd_stages{0}, mt_fwd_smem{0};
+    int     mt_splits{0}, mt_bwd_grid{0}, mt_bwd_stages{0}, mt_bwd_smem{0}, mt_t_ld{0};
 
     // state of a two-phase evaluation
     bool    partial_has_grad{false};
@@ -302,6 +330,55 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
             obj->t1     = plan;
             obj->use_t1 = true;
             NB200_CUDA_TRY(cudaDeviceSynchronize()); // the memsets above ran on the legacy stream
+            return NB200_OK;
+        }
+    }
+
+    // many-target tensor-pipe path: T in [2, 128] even (16-byte row copies of dL), D a multiple of 128
+    obj->use_mt = false;
+    if (T >= 2 && T <= 128 && T % 2 == 0 && D % kMtBwdCols == 0 && !force_generic && forced_variant != -3)
+    {
+        int v = 0;
+        while (v < kNumMtVariants && kMtVariants[v].NT8 * 8 < T)
+        {
+            ++v;
+        }
+        const mt_variant& var = kMtVariants[v];
+        const int64_t     TP  = var.NT8 * 8;
+        // forward: header (barriers + fold area + alignment slack) + stages of (128 + TP) rows x 20 doubles
+        const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + TP);
+        const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
+        const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (data->smem_optin - fwd_header) / fwd_stage);
+        // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
+        int64_t t_ld = T;
+        while (t_ld % 16 != 4)
+        {
+            t_ld += 2;
+        }
+        const int64_t bwd_stage  = (round_up(kMtBwdRows * t_ld, 16) + kMtBwdRows * kMtBwdLd) * 8;
+        const int64_t bwd_stages = std::min<int64_t>(kMtMaxStages, (data->smem_optin - 256) / bwd_stage);
+        const int64_t ctiles     = D / kMtBwdCols;
+        const int64_t chunks     = (N + kMtBwdRows - 1) / kMtBwdRows;
+        const int64_t splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, data->sm_count / ctiles));
+        if (fwd_stages >= 2 && bwd_stages >= 2 && ctiles <= data->sm_count)
+        {
+            obj->mt_variant    = v;
+            obj->mt_fwd_grid   = static_cast<int>(std::min<int64_t>((N + kMtBM - 1) / kMtBM, data->sm_count));
+            obj->mt_fwd_stages = static_cast<int>(fwd_stages);
+            obj->mt_fwd_smem   = static_cast<int>(fwd_header + fwd_stages * fwd_stage);
+            obj->mt_splits     = static_cast<int>(splits);
+            obj->mt_bwd_grid   = static_cast<int>(ctiles * splits);
+            obj->mt_bwd_stages = static_cast<int>(bwd_stages);
+            obj->mt_bwd_smem   = static_cast<int>(256 + bwd_stages * bwd_stage);
+            obj->mt_t_ld       = static_cast<int>(t_ld);
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_fwd_smem));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_fwd_smem));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_bwd_smem));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(obj->mt_fwd_grid) * (1 + T) * sizeof(double)));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(splits) * T * D * sizeof(double)));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
+            NB200_CUDA_TRY(cudaDeviceSynchronize());
+            obj->use_mt = true;
             return NB200_OK;
         }
     }
@@ -521,6 +598,61 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
                                                    static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
         obj->launches += 1;
         return timing_end(obj);
+    }
+
+    if (obj->use_mt)
+    {
+        const mt_variant& var = kMtVariants[obj->mt_variant];
+        mt_forward_params f{};
+        f.X           = data->X;
+        f.Y           = data->Y;
+        f.W           = W;
+        f.b           = bias;
+        f.dL          = want_grad ? obj->d_dL : nullptr;
+        f.partials_fb = obj->d_partials;
+        f.N           = N;
+        f.D           = static_cast<int>(D);
+        f.T           = static_cast<int>(T);
+        f.stages      = obj->mt_fwd_stages;
+        f.loss        = obj->loss;
+        f.loss_param  = obj->loss_param;
+        (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        if (want_grad)
+        {
+            mt_backward_params b{};
+            b.X           = data->X;
+            b.dL          = obj->d_dL;
+            b.partials_gw = obj->d_partials_gw;
+            b.N           = N;
+            b.D           = static_cast<int>(D);
+            b.T           = static_cast<int>(T);
+            b.t_ld        = obj->mt_t_ld;
+            b.splits      = obj->mt_splits;
+            b.stages      = obj->mt_bwd_stages;
+            var.backward<<<obj->mt_bwd_grid, kMtThreads, obj->mt_bwd_smem, obj->stream>>>(b);
+            NB200_CUDA_TRY(cudaGetLastError());
+            obj->launches += 1;
+        }
+        status = timing_end(obj);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        const int64_t cols_fb = want_grad ? (1 + T) : 1;
+        reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials, obj->mt_fwd_grid, 1 + T, cols_fb, obj->d_reduced);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        if (want_grad)
+        {
+            reduce_partials_kernel<<<static_cast<unsigned>((T * D + 127) / 128), 128, 0, obj->stream>>>(
+                obj->d_partials_gw, obj->mt_splits, T * D, T * D, obj->d_reduced + 1 + T);
+            NB200_CUDA_TRY(cudaGetLastError());
+            obj->launches += 1;
+        }
+        return finish ? enqueue_finish(obj, x_dev, n_global, gx_out, fx_out) : NB200_OK;
     }
 
     gen_params p{};
@@ -844,7 +976,7 @@ int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj)
     NB200_REQUIRE(obj != nullptr && out_obj != nullptr, "objective: null argument");
     const int status = make_objective(obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
                                       obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
-                                      obj->use_t1 ? obj->t1.variant : -2, out_obj);
+                                      obj->use_t1 ? obj->t1.variant : (obj->use_mt ? -1 : -2), out_obj);
     if (status == NB200_OK)
     {
         (*out_obj)->timing = obj->timing;
@@ -1043,6 +1175,14 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
                " grid=" + std::to_string(obj->t1.grid) + " rows_per_stage=" + std::to_string(obj->t1.rows_per_stage) +
                " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
                " smem=" + std::to_string(obj->t1.smem_bytes);
+    }
+    else if (obj->use_mt)
+    {
+        text = "dmma NT8=" + std::to_string(kMtVariants[obj->mt_variant].NT8) + " fwd_grid=" +
+               std::to_string(obj->mt_fwd_grid) + " fwd_stages=" + std::to_string(obj->mt_fwd_stages) +
+               " fwd_smem=" + std::to_string(obj->mt_fwd_smem) + " bwd_grid=" + std::to_string(obj->mt_bwd_grid) +
+               " splits=" + std::to_string(obj->mt_splits) + " bwd_stages=" + std::to_string(obj->mt_bwd_stages) +
+               " bwd_smem=" + std::to_string(obj->mt_bwd_smem) + " t_ld=" + std::to_string(obj->mt_t_ld);
     }
     else
     {

@@ -1,0 +1,505 @@
+// vgrad_mt.cuh — the many-target path (softmax / multi-label models, BASELINE config 3: 4M x 2048 x 100): the two
+// dense contractions of linear::function_t::do_eval on the FP64 tensor pipe (mma.sync m8n8k4 f64, SASS DMMA.8x8x4).
+//
+//   mt_forward_kernel   O = X W^T + b  (src/linear/util.cpp:19-20), loss value + dL in the epilogue straight from the
+//                       accumulator fragments (include/nano/loss/flatten.h:69-86): O is never written to HBM
+//   mt_backward_kernel  gW = dL^T X    (src/linear/function.cpp:70) as a split-K GEMM over row ranges
+//
+// This case is contraction-bound (50 flop per byte of X at T = 100), so X is read twice (once per GEMM). tcgen05 has no
+// fp64 kind; DMMA through mma.sync is the fp64 tensor path of sm_100a. Both kernels: persistent CTAs, a producer
+// warp feeding a ring of shared-memory stages with 1-D bulk async copies (one per tile row, padded row stride so that
+// the 64-bit fragment loads are bank-conflict free), 8 consumer warps each owning 2 x NT8 (resp. NT8 x 2) m8n8 tiles.
+#pragma once
+
+#include "common.cuh"
+#include "loss.cuh"
+
+namespace nb200
+{
+constexpr int kMtWarps    = 8;   // consumer warps
+constexpr int kMtBM       = 128; // forward: rows per CTA tile (16 per warp)
+constexpr int kMtBK       = 16;  // forward: features per stage
+constexpr int kMtLd       = kMtBK + 4; // forward: shared row stride in doubles (8*row + 2*k mod 32 distinct per half-warp)
+constexpr int kMtBwdCols  = 128; // backward: columns per CTA (2 n8 tiles per warp)
+constexpr int kMtBwdRows  = 16;  // backward: rows per stage
+constexpr int kMtBwdLd    = kMtBwdCols + 4; // backward: shared row stride of the X tile
+constexpr int kMtMaxStages = 8;
+constexpr int kMtProducerWarps = 4;   // a whole warpgroup, so that its registers can be handed to the consumers
+constexpr int kMtThreads       = (kMtWarps + kMtProducerWarps) * 32;
+constexpr int kMtProducerRegs  = 40;  // 384 threads x 168 registers at launch -> 128 x 40 + 256 x 232
+constexpr int kMtConsumerRegs  = 232;
+
+struct mt_forward_params
+{
+    const double* X;  // [N, D]
+    const double* Y;  // [N, T]
+    const double* W;  // [T, D] device
+    const double* b;  // [T] device
+    double*       dL; // [N, T] (GRAD)
+    double*       partials_fb; // [grid, 1 + T]
+    int64_t       N;
+    int           D; // multiple of kMtBK
+    int           T;
+    int           stages;
+    int           loss;
+    double        loss_param;
+};
+
+struct mt_backward_params
+{
+    const double* X;           // [N, D]
+    const double* dL;          // [N, T]
+    double*       partials_gw; // [splits, T, D]
+    int64_t       N;
+    int           D;      // multiple of kMtBwdCols
+    int           T;      // even
+    int           t_ld;   // shared row stride of the dL tile (>= T, = 4 mod 16)
+    int           splits;
+    int           stages;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// sum / max over the 4 lanes that hold one accumulator row (lanes g*4 + {0..3})
+__device__ __forceinline__ double quad_sum(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+__device__ __forceinline__ double quad_max(double v)
+{
+    double o = __shfl_xor_sync(0xffffffffu, v, 1);
+    v        = (v < o) ? o : v;
+    o        = __shfl_xor_sync(0xffffffffu, v, 2);
+    return (v < o) ? o : v;
+}
+
+template <int NT8, bool GRAD>
+__global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forward_params p)
+{
+    constexpr int TP = NT8 * 8; // padded targets
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + kMtMaxStages;
+    double*   fold      = reinterpret_cast<double*>(smem + 256); // [kMtWarps][1 + TP] at the very end of the kernel
+    double*   stage0    = reinterpret_cast<double*>(smem + 256 + sizeof(double) * kMtWarps * (1 + TP) + 256);
+    stage0              = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(stage0) + 127) / 128 * 128);
+    constexpr int kStageDoubles = (kMtBM + TP) * kMtLd;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g    = lane >> 2; // fragment row / column group
+    const int tig  = lane & 3;  // thread in group
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < p.stages; ++s)
+        {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, kMtWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int     D      = p.D;
+    const int     T      = p.T;
+    const int     kchunks = D / kMtBK;
+    const int64_t tiles  = (p.N + kMtBM - 1) / kMtBM;
+
+    if (warp >= kMtWarps)
+    {
+        // ===== producer warpgroup: its first warp issues the row copies (lane 0 arms the barrier) =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMtProducerRegs));
+        if (warp != kMtWarps)
+        {
+            return;
+        }
+        const uint64_t policy_x = l2_policy_evict_first();
+        uint64_t       policy_w;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy_w));
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        {
+            const int64_t row0 = tile * kMtBM;
+            const int     rows = static_cast<int>(min(static_cast<int64_t>(kMtBM), p.N - row0));
+            for (int kc = 0; kc < kchunks; ++kc, ++it)
+            {
+                const int      s     = it % p.stages;
+                const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+                mbar_wait(empty_bar + s, phase ^ 1u);
+                double* xs = stage0 + static_cast<int64_t>(s) * kStageDoubles;
+                double* ws = xs + kMtBM * kMtLd;
+                if (lane == 0)
+                {
+                    mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>((rows + T) * kMtBK * 8));
+                }
+                __syncwarp();
+                for (int r = lane; r < rows; r += 32)
+                {
+                    bulk_copy_g2s(xs + r * kMtLd, p.X + (row0 + r) * D + kc * kMtBK, kMtBK * 8, full_bar + s, policy_x);
+                }
+                for (int t = lane; t < T; t += 32)
+                {
+                    bulk_copy_g2s(ws + t * kMtLd, p.W + static_cast<int64_t>(t) * D + kc * kMtBK, kMtBK * 8,
+                                  full_bar + s, policy_w);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps: rows [warp*16, warp*16 + 16) of the tile, all targets =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMtConsumerRegs));
+    double gbacc[NT8][2]; // column sums of dL owned by this lane (columns nt*8 + 2*tig + {0, 1})
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt)
+    {
+        gbacc[nt][0] = gbacc[nt][1] = 0.0;
+    }
+    double fsum = 0.0;
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        double acc[2][NT8][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+        {
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+                acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            }
+        }
+
+        for (int kc = 0; kc < kchunks; ++kc, ++it)
+        {
+            const int      s     = it % p.stages;
+            const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+            mbar_wait(full_bar + s, phase);
+            const double* xs = stage0 + static_cast<int64_t>(s) * kStageDoubles;
+            const double* ws = xs + kMtBM * kMtLd;
+            const double* xa = xs + (warp * 16 + g) * kMtLd + tig;
+            const double* wb = ws + g * kMtLd + tig;
+#pragma unroll
+            for (int kk = 0; kk < kMtBK / 4; ++kk)
+            {
+                const double a0 = xa[kk * 4];
+                const double a1 = xa[8 * kMtLd + kk * 4];
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+                    const double bv = wb[nt * 8 * kMtLd + kk * 4];
+                    dmma_m8n8k4(acc[0][nt][0], acc[0][nt][1], a0, bv);
+                    dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, bv);
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+            {
+                mbar_arrive(empty_bar + s);
+            }
+        }
+
+        // ----- epilogue on the fragments: + bias (in place), loss value, dL -----
+        const int64_t row_base = tile * kMtBM + warp * 16 + g;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+        {
+            const int64_t row   = row_base + mt * 8;
+            const bool    valid = row < p.N;
+            const double* yrow  = p.Y + (valid ? row : 0) * T; // invalid rows read row 0 and are discarded
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                    const int col = nt * 8 + tig * 2 + e;
+                    acc[mt][nt][e] = (valid && col < T) ? (acc[mt][nt][e] + p.b[col]) : 0.0;
+                }
+            }
+
+            if (p.loss == LOSS_CLASSNLL)
+            {
+                // classnll.h:19-37 on a row spread over 4 lanes
+                double omax = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        if (nt * 8 + tig * 2 + e < T)
+                        {
+                            omax = max_of(omax, acc[mt][nt][e]);
+                        }
+                    }
+                }
+                omax = quad_max(omax);
+                double sumexp = 0.0, dot = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        const int col = nt * 8 + tig * 2 + e;
+                        if (col < T)
+                        {
+                            sumexp += exp(__dsub_rn(acc[mt][nt][e], omax));
+                            dot += __dmul_rn(__dadd_rn(1.0, yrow[col]), acc[mt][nt][e]);
+                        }
+                    }
+                }
+                sumexp = quad_sum(sumexp);
+                dot    = quad_sum(dot);
+                if (valid && tig == 0)
+                {
+                    fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
+                }
+                if (GRAD && valid)
+                {
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt)
+                    {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                        {
+                            const int col = nt * 8 + tig * 2 + e;
+                            if (col < T)
+                            {
+                                const double ex = exp(__dsub_rn(acc[mt][nt][e], omax));
+                                const double gv =
+                                    __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, yrow[col])));
+                                p.dL[row * T + col] = gv;
+                                gbacc[nt][e] += gv;
+                            }
+                        }
+                    }
+                }
+            }
+            else
+            {
+                double sum = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        const int col = nt * 8 + tig * 2 + e;
+                        if (valid && col < T)
+                        {
+                            double term, gv;
+                            loss_term<GRAD>(p.loss, p.loss_param, yrow[col], acc[mt][nt][e], term, gv);
+                            sum += term;
+                            if (GRAD)
+                            {
+                                p.dL[row * T + col] = gv;
+                                gbacc[nt][e] += gv;
+                            }
+                        }
+                    }
+                }
+                sum = quad_sum(sum);
+                if (valid && tig == 0)
+                {
+                    fsum += loss_post(p.loss, sum);
+                }
+            }
+        }
+    }
+
+    // ----- fold: lanes with the same tig hold the same columns -> butterfly over g, then over the warps -----
+    fsum += __shfl_xor_sync(0xffffffffu, fsum, 4);
+    fsum += __shfl_xor_sync(0xffffffffu, fsum, 8);
+    fsum += __shfl_xor_sync(0xffffffffu, fsum, 16);
+    fsum = quad_sum(fsum); // only tig == 0 lanes carried values
+    double* mine = fold + warp * (1 + TP);
+    if (lane == 0)
+    {
+        mine[0] = fsum;
+    }
+    if (GRAD)
+    {
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                double v = gbacc[nt][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (g == 0)
+                {
+                    mine[1 + nt * 8 + tig * 2 + e] = v;
+                }
+            }
+        }
+    }
+    named_bar_sync(1, kMtWarps * 32);
+    double* out = p.partials_fb + static_cast<int64_t>(blockIdx.x) * (1 + T);
+    for (int c = threadIdx.x; c < (GRAD ? 1 + T : 1); c += kMtWarps * 32)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kMtWarps; ++q)
+        {
+            s += fold[q * (1 + TP) + c];
+        }
+        out[c] = s;
+    }
+}
+
+// grid.x = (D / kMtBwdCols) * splits; CTA (ct, split) accumulates gW[:, ct*128 .. +128) over its row range.
+template <int NT8>
+__global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_backward_params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + kMtMaxStages;
+    double*   stage0    = reinterpret_cast<double*>(smem + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g    = lane >> 2;
+    const int tig  = lane & 3;
+
+    const int T      = p.T;
+    const int D      = p.D;
+    const int t_ld   = p.t_ld;
+    const int ctiles = D / kMtBwdCols;
+    const int ct     = blockIdx.x % ctiles;
+    const int split  = blockIdx.x / ctiles;
+
+    // stage layout: dL tile [kMtBwdRows][t_ld] then X tile [kMtBwdRows][kMtBwdLd]; each part rounded to 128 bytes
+    const int dl_doubles    = (kMtBwdRows * t_ld + 15) / 16 * 16;
+    const int stage_doubles = dl_doubles + kMtBwdRows * kMtBwdLd;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < p.stages; ++s)
+        {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, kMtWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // contiguous row range of this split, in whole stages
+    const int64_t chunks_total = (p.N + kMtBwdRows - 1) / kMtBwdRows;
+    const int64_t chunks_each  = (chunks_total + p.splits - 1) / p.splits;
+    const int64_t chunk_begin  = min(chunks_total, split * chunks_each);
+    const int64_t chunk_end    = min(chunks_total, chunk_begin + chunks_each);
+
+    if (warp >= kMtWarps)
+    {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMtProducerRegs));
+        if (warp != kMtWarps)
+        {
+            return;
+        }
+        const uint64_t policy_x = l2_policy_evict_first();
+        uint64_t       policy_g;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy_g));
+        int it = 0;
+        for (int64_t chunk = chunk_begin; chunk < chunk_end; ++chunk, ++it)
+        {
+            const int      s     = it % p.stages;
+            const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+            mbar_wait(empty_bar + s, phase ^ 1u);
+            const int64_t row0 = chunk * kMtBwdRows;
+            const int     rows = static_cast<int>(min(static_cast<int64_t>(kMtBwdRows), p.N - row0));
+            double*       gs   = stage0 + static_cast<int64_t>(s) * stage_doubles;
+            double*       xs   = gs + dl_doubles;
+            if (lane == 0)
+            {
+                mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>(rows * (T + kMtBwdCols) * 8));
+            }
+            __syncwarp();
+            if (lane < rows)
+            {
+                bulk_copy_g2s(gs + lane * t_ld, p.dL + (row0 + lane) * T, T * 8, full_bar + s, policy_g);
+                bulk_copy_g2s(xs + lane * kMtBwdLd, p.X + (row0 + lane) * D + ct * kMtBwdCols, kMtBwdCols * 8,
+                              full_bar + s, policy_x);
+            }
+        }
+        return;
+    }
+
+    // consumer warp: n8 tiles {2*warp, 2*warp + 1} of the 16 column tiles, all NT8 target tiles
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMtConsumerRegs));
+    double acc[NT8][2][2];
+#pragma unroll
+    for (int mt = 0; mt < NT8; ++mt)
+    {
+        acc[mt][0][0] = acc[mt][0][1] = acc[mt][1][0] = acc[mt][1][1] = 0.0;
+    }
+
+    int it = 0;
+    for (int64_t chunk = chunk_begin; chunk < chunk_end; ++chunk, ++it)
+    {
+        const int      s     = it % p.stages;
+        const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+        mbar_wait(full_bar + s, phase);
+        const int     rows = static_cast<int>(min(static_cast<int64_t>(kMtBwdRows), p.N - chunk * kMtBwdRows));
+        const double* gs   = stage0 + static_cast<int64_t>(s) * stage_doubles;
+        const double* xs   = gs + dl_doubles;
+#pragma unroll
+        for (int kk = 0; kk < kMtBwdRows / 4; ++kk)
+        {
+            const int  k  = kk * 4 + tig; // row inside the stage
+            const bool in = k < rows;
+            const double b0 = in ? xs[k * kMtBwdLd + (2 * warp) * 8 + g] : 0.0;
+            const double b1 = in ? xs[k * kMtBwdLd + (2 * warp + 1) * 8 + g] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < NT8; ++mt)
+            {
+                const int    m = mt * 8 + g;
+                const double a = (in && m < T) ? gs[k * t_ld + m] : 0.0;
+                dmma_m8n8k4(acc[mt][0][0], acc[mt][0][1], a, b0);
+                dmma_m8n8k4(acc[mt][1][0], acc[mt][1][1], a, b1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+            mbar_arrive(empty_bar + s);
+        }
+    }
+
+    double* out = p.partials_gw + static_cast<int64_t>(split) * T * D;
+#pragma unroll
+    for (int mt = 0; mt < NT8; ++mt)
+    {
+        const int t = mt * 8 + g;
+        if (t < T)
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                const int col = ct * kMtBwdCols + (2 * warp + j) * 8 + tig * 2;
+                *reinterpret_cast<double2*>(out + static_cast<int64_t>(t) * D + col) =
+                    make_double2(acc[mt][j][0], acc[mt][j][1]);
+            }
+        }
+    }
+}
+
+#endif // __CUDACC__
+} // namespace nb200

@@ -362,3 +362,43 @@ def test_synthetic_config1_sizes(ctx, oracle):
         g2, g3 = np.empty(dims), np.empty(dims)
         assert twin(x, g2) == fx and np.array_equal(g2, gx)
         assert abs(other(x, g3) - fx) > 1e2 * EPSILON0 and np.max(np.abs(g3 - gx)) > 1e-10
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# many-target tensor-pipe path (DMMA kernels, vgrad_mt.cuh): T even in [2, 128], D a multiple of 128
+# ----------------------------------------------------------------------------------------------------------------
+MT_SHAPES = [(1000, 128, 2), (257, 256, 10), (4096, 1024, 100), (129, 2048, 16), (5000, 384, 128), (100, 128, 100),
+             (1, 128, 4), (2049, 512, 26)]
+
+
+@pytest.mark.parametrize("N,D,T", MT_SHAPES)
+@pytest.mark.parametrize("loss_id", ["s-classnll", "mse", "m-logistic", "m-hinge"])
+def test_many_target_tensor_path_parity(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + 3 * D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):
+        Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    assert function.describe().startswith("dmma"), function.describe()
+    fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
+    # same input => same bits; and the shape-generic kernels agree
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)
+    function.set_variant(-3)
+    assert function.describe().startswith("generic")
+    g3 = np.empty_like(x)
+    f3 = function(x, g3)
+    assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+def test_many_target_softmax_sample_of_config3(ctx, oracle):
+    # BASELINE config 3 shape (D = 2048, T = 100, s-classnll) at a row count the oracle finishes in seconds
+    import libnano_b200 as nb
+
+    N, D, T = 8192, 2048, 100
+    data = nb.Dataset.synth(ctx, nb.SYNTH_MULTICLASS, N, D, T=T, seed=42)
+    X, Y = data.read()
+    assert np.all(np.sum(Y > 0, axis=1) == 1)
+    function = nb.LinearFunction(data, nb.Loss("s-classnll"), 0.0, 1e-2)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, function.size()) / np.sqrt(D)
+    check_against_oracle(oracle, function, X, Y, "s-classnll", x, 0.0, 1e-2)
