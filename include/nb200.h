@@ -189,6 +189,23 @@ NB200_API int nb200_objective_set_variant(nb200_obj* obj, int variant);
 /* Human-readable launch plan (kernel variant, grid, stages, shared memory) into buffer[size]. */
 NB200_API int nb200_objective_describe(const nb200_obj* obj, char* buffer, int64_t size);
 
+/* ---- device-resident solver (BASELINE north_star item 3) --------------------------------------------------------- */
+
+/* Sum-all-reduce `length` doubles at `device_buffer` across the ranks of a sample-sharded job, enqueued on
+ * `cuda_stream` (e.g. ncclAllReduce, or torch.distributed.all_reduce on a tensor aliasing the buffer). 0 = success. */
+typedef int (*nb200_allreduce_fn)(void* user, double* device_buffer, int64_t length, void* cuda_stream);
+
+/* nano::solver_lbfgs_t::minimize (src/solver/lbfgs.cpp:25-124; lsearch0 = quadratic, lsearchk = cgdescent, tolerance
+ * (1e-4, 0.9)) with x, g, the (s, y) history, the two-loop recursion and the line-search trial points resident in
+ * HBM: per evaluation only four scalars reach the host. x: in = x0, out = the returned state's x (host, n doubles).
+ * n_global = 0 and allreduce = NULL for a single rank; otherwise every rank calls this with the same x0 and the
+ * callback all-reduces the un-normalised sums between the two phases. stats = {fcalls, gcalls, iterations};
+ * status: 0 max_evals reached, 1 converged (gradient test < epsilon), 4 failed (non-finite state / line search). */
+NB200_API int nb200_lbfgs_minimize(nb200_obj* obj, double* x, int64_t n, double epsilon, int64_t max_evals,
+                                   int64_t history, int64_t n_global, nb200_allreduce_fn allreduce,
+                                   void* allreduce_user, double* fx, double* gradient_test, int64_t* stats,
+                                   int* status);
+
 /* ---- building blocks exposed on their own (reference: linear::predict, loss_t::value / loss_t::vgrad) -------- */
 
 /* outputs[N,T] (host) = X * W^T + b over the pinned dataset; W[T,D], b[T] host. */

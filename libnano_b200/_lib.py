@@ -50,6 +50,9 @@ SIGNATURES = {
     "nb200_objective_pass_stats": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(c_i64), ctypes.c_int]),
     "nb200_objective_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_i64]),
+    "nb200_lbfgs_minimize": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.c_double, c_i64, c_i64, c_i64,
+                                            ctypes.c_void_p, ctypes.c_void_p, c_double_p, c_double_p,
+                                            ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int)]),
     "nb200_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_double_p, c_double_p, c_double_p]),
     "nb200_loss_value": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p, c_i64,
                                         c_i64, c_double_p]),
@@ -58,6 +61,8 @@ SIGNATURES = {
     "nb200_loss_vgrad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p, c_i64,
                                         c_i64, c_double_p]),
 }
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_i64, ctypes.c_void_p)
 
 _lib = None
 

@@ -114,6 +114,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared through the LSU (SASS LDGSTS): the right tool when a tile row is only
+// 128 bytes long, where one bulk-copy request per row would be bound by the request rate of the copy engine
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// the executing thread arrives on `bar` once all of its earlier cp.async copies have landed (the arrival must be
+// part of the barrier's expected count: .noinc)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // named barrier over a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(const uint32_t id, const uint32_t threads)
 {

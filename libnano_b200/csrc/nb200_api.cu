@@ -731,6 +731,8 @@ int collect_result(nb200_obj* obj, double* gx, double* fx)
 }
 } // namespace
 
+#include "lbfgs.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------
@@ -1192,6 +1194,23 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     std::strncpy(buffer, text.c_str(), static_cast<size_t>(size) - 1);
     buffer[size - 1] = '\0';
     return NB200_OK;
+}
+
+int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const double epsilon, const int64_t max_evals,
+                         const int64_t history, const int64_t n_global, nb200_allreduce_fn allreduce,
+                         void* allreduce_user, double* fx, double* gradient_test, int64_t* stats, int* status)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr && gradient_test != nullptr && stats != nullptr &&
+                      status != nullptr,
+                  "lbfgs: null argument");
+    NB200_REQUIRE(n == obj->n, "solver: incompatible initial point (" + std::to_string(n) + " dimensions), expecting " +
+                                   std::to_string(obj->n) + " dimensions!");
+    NB200_REQUIRE(epsilon > 0.0 && max_evals > 0 && history >= 1 && history <= 1000, "lbfgs: invalid parameters");
+    NB200_REQUIRE((allreduce == nullptr) == (n_global == 0 || n_global == obj->data->N),
+                  "lbfgs: a sharded solve needs both the global sample count and the all-reduce callback");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user);
+    return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
 }
 
 int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const double* b, double* outputs)

