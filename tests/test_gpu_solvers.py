@@ -87,3 +87,56 @@ def test_osga_on_nonsmooth_objectives(ctx, oracle, loss_id, l1, l2):
     assert abs(cpu(r_gpu["x"]) - r_gpu["fx"]) <= 1e-12 * (1 + abs(r_gpu["fx"]))
     # one f(x, g) + one f(x') per iteration (src/solver/osga.cpp:101,112)
     assert r_gpu["fcalls"] == 2 * r_gpu["iterations"] + 1 and r_gpu["gcalls"] == r_gpu["iterations"] + 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-resident L-BFGS (nb200_lbfgs_minimize): same algorithm, vectors never leave HBM
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,T,loss_id,l2", [(20000, 64, 1, "s-logistic", 1e-2), (5000, 128, 4, "s-classnll", 1e-2),
+                                              (8000, 100, 1, "mse", 0.0), (3000, 33, 2, "mse", 1e-3)])
+def test_device_resident_lbfgs_matches_the_host_driven_solve(ctx, oracle, N, D, T, loss_id, l2):
+    import libnano_b200 as nb
+    from libnano_b200.solver import lbfgs
+
+    X, Y, _ = make_problem(1, N, D, T, loss_id != "mse")
+    gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss(loss_id), 0.0, l2)
+    x0 = np.zeros(gpu.size())
+    epsilon = 1e-8
+    r_dev = lbfgs(gpu, x0, epsilon=epsilon, max_evals=1000)
+    assert r_dev["status"] == "gradient_test" and r_dev["gradient_test"] < epsilon
+    assert (gpu.fcalls(), gpu.gcalls()) == (r_dev["fcalls"], r_dev["gcalls"]) and r_dev["fcalls"] == r_dev["gcalls"]
+
+    # (a) the restated CPU driver over the CPU oracle objective: same optimum within the solver's epsilon
+    r_cpu = oracle.lbfgs(oracle_objective(oracle, X, Y, loss_id, 0.0, l2), x0, epsilon=epsilon, max_evals=1000)
+    assert r_cpu["status"] == "gradient_test"
+    assert abs(r_dev["fx"] - r_cpu["fx"]) <= epsilon * (1 + abs(r_cpu["fx"]))
+    if l2 > 0:
+        assert np.max(np.abs(r_dev["x"] - r_cpu["x"])) <= 10 * epsilon / (l2 / (D * T))
+    assert abs(r_dev["fcalls"] - r_cpu["fcalls"]) <= max(3, r_cpu["fcalls"] // 4)
+
+    # (b) the returned point is what it claims: f and the gradient test re-evaluated through the host-buffer call
+    g = np.empty_like(x0)
+    f = gpu(r_dev["x"], g)
+    assert abs(f - r_dev["fx"]) <= 1e-12 * (1 + abs(f))
+    assert abs(np.max(np.abs(g)) / max(1.0, abs(f)) - r_dev["gradient_test"]) <= 1e-12
+
+
+def test_device_resident_lbfgs_contract(ctx):
+    import libnano_b200 as nb
+    from libnano_b200.solver import lbfgs
+
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (50, 4))
+    W, b = rng.uniform(-1, 1, (1, 4)), rng.uniform(-1, 1, 1)
+    function = nb.LinearFunction(nb.Dataset.pin(ctx, X, X @ W.T + b), nb.Loss("mse"), 0.0, 0.0)
+    result = lbfgs(function, np.zeros(5), epsilon=1e-10, max_evals=10000)
+    assert result["status"] == "gradient_test" and abs(result["fx"]) < 1e-7
+    assert np.max(np.abs(result["x"] - np.concatenate([W.ravel(), b]))) < 1e-7  # test_linear_function.cpp:152-188
+    # already at the optimum: the early exit of lbfgs.cpp:34-38 costs exactly one evaluation
+    again = lbfgs(function, result["x"], epsilon=1e-6)
+    assert again["fcalls"] <= 3
+    # max_evals is honoured (lbfgs.cpp:45)
+    short = lbfgs(function, np.zeros(5), epsilon=1e-14, max_evals=6)
+    assert short["status"] in ("max_iters", "gradient_test") and short["fcalls"] + short["gcalls"] <= 6 + 8
+    with pytest.raises(RuntimeError, match="incompatible initial point"):
+        lbfgs(function, np.zeros(4))

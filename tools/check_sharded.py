@@ -65,6 +65,26 @@ def main():
             ok = ok and case["rel_f"] <= 1e-13 and case["rel_g"] <= 1e-13 and case["rel_f_value_only"] <= 1e-13
         ok = ok and same
         report["cases"].append(case)
+    # device-resident L-BFGS through the sharded objective (all-reduce callback between the two phases) vs one GPU
+    from libnano_b200.solver import lbfgs
+
+    N, D = 200000, 256
+    row0, rows = shard_rows(N, world, rank)
+    part = nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, rows, D, seed=11, row_offset=row0)
+    sharded = ShardedFunction.from_local(nb.LinearFunction(part, nb.Loss("s-logistic"), 0.0, 1e-2), N)
+    solved = lbfgs(sharded, np.zeros(D + 1), epsilon=1e-8)
+    solve = {"status": solved["status"], "fx": solved["fx"], "fcalls": solved["fcalls"],
+             "gradient_test": solved["gradient_test"]}
+    ok = ok and solved["status"] == "gradient_test"
+    if rank == 0:
+        whole = nb.LinearFunction(nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, N, D, seed=11), nb.Loss("s-logistic"),
+                                  0.0, 1e-2)
+        single = lbfgs(whole, np.zeros(D + 1), epsilon=1e-8)
+        solve["single_gpu_fx"] = single["fx"]
+        solve["single_gpu_fcalls"] = single["fcalls"]
+        solve["max_dx"] = float(np.max(np.abs(single["x"] - solved["x"])))
+        ok = ok and abs(single["fx"] - solved["fx"]) <= 1e-8 * (1 + abs(single["fx"])) and solve["max_dx"] <= 1e-3
+    report["lbfgs"] = solve
     report["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(report), flush=True)
