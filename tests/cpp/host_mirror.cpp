@@ -1,0 +1,104 @@
+// host_mirror.cpp — the Eigen-free C++ host layer (include/nano_b200/function.h) driven like libnano drives a
+// function_t: construct over pinned data, evaluate f(x) and f(x, gx), check counters / errors / clone, and compare
+// with a plain-loop mse objective computed right here (src/linear/function.cpp:44-168 formulas).
+// Built and run by tests/test_cpp_host.py on the GPU box:  g++ -std=c++20 -Iinclude host_mirror.cpp libnb200.so
+#include <nano_b200/function.h>
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+using namespace nano_b200;
+
+#define CHECK(cond)                                                                                                    \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+        {                                                                                                              \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);                                              \
+            return 1;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+int main()
+{
+    const tensor_size_t N = 3000, D = 64, T = 2;
+    std::mt19937_64                        rng(7);
+    std::uniform_real_distribution<double> udist(-1.0, 1.0);
+    std::vector<double>                    X(N * D), Y(N * T), x((D + 1) * T), gx(x.size()), gref(x.size(), 0.0);
+    for (auto& v : X) v = udist(rng);
+    for (auto& v : Y) v = udist(rng);
+    for (auto& v : x) v = udist(rng) / 8.0;
+
+    const double l1 = 0.1, l2 = 0.3;
+    context_t   ctx(0);
+    dataset_t   data(ctx, X.data(), Y.data(), N, D, T);
+    CHECK(data.samples() == N && data.inputs() == D && data.targets() == T);
+    linear::function_t function(data, "mse", l1, l2);
+    CHECK(function.size() == (D + 1) * T && function.convex() && !function.smooth());
+    CHECK(std::fabs(function.strong_convexity() - l2 / (D * T)) < 1e-18);
+    CHECK(function.name() == "linear[130D]");
+
+    // reference: f = mean 0.5 |Wx + b - y|^2 + l1 mean|W| + 0.5 l2 mean(W^2)
+    double fref = 0.0;
+    for (tensor_size_t i = 0; i < N; ++i)
+    {
+        for (tensor_size_t t = 0; t < T; ++t)
+        {
+            double o = x[T * D + t];
+            for (tensor_size_t j = 0; j < D; ++j) o += X[i * D + j] * x[t * D + j];
+            const double d = o - Y[i * T + t];
+            fref += 0.5 * d * d;
+            gref[T * D + t] += d;
+            for (tensor_size_t j = 0; j < D; ++j) gref[t * D + j] += d * X[i * D + j];
+        }
+    }
+    fref /= N;
+    double sabs = 0.0, ssqr = 0.0;
+    for (tensor_size_t k = 0; k < T * D; ++k)
+    {
+        sabs += std::fabs(x[k]);
+        ssqr += x[k] * x[k];
+        gref[k] = gref[k] / N + l1 * ((x[k] > 0) - (x[k] < 0)) / (T * D) + l2 * x[k] / (T * D);
+    }
+    for (tensor_size_t t = 0; t < T; ++t) gref[T * D + t] /= N;
+    fref += l1 * sabs / (T * D) + 0.5 * l2 * ssqr / (T * D);
+
+    const double f1 = function({x.data(), static_cast<tensor_size_t>(x.size())});
+    const double f2 = function({x.data(), static_cast<tensor_size_t>(x.size())},
+                               {gx.data(), static_cast<tensor_size_t>(gx.size())});
+    CHECK(f1 == f2);
+    CHECK(std::fabs(f1 - fref) <= 1e-12 * (1 + std::fabs(fref)));
+    double gmax = 0.0, dmax = 0.0;
+    for (size_t k = 0; k < gx.size(); ++k)
+    {
+        gmax = std::max(gmax, std::fabs(gref[k]));
+        dmax = std::max(dmax, std::fabs(gref[k] - gx[k]));
+    }
+    CHECK(dmax <= 1e-12 * (1 + gmax));
+    CHECK(function.fcalls() == 2 && function.gcalls() == 1); // src/function.cpp:258-260
+
+    // size mismatch throws like nano::critical (src/function.cpp:248-256)
+    bool thrown = false;
+    try
+    {
+        function({x.data(), 3});
+    }
+    catch (const std::runtime_error& e)
+    {
+        thrown = std::string(e.what()).find("invalid input size") != std::string::npos;
+    }
+    CHECK(thrown && function.fcalls() == 2);
+
+    // clone shares the pinned dataset and gives the same bits
+    const auto clone = function.clone();
+    std::vector<double> g2(gx.size());
+    CHECK((*clone)({x.data(), static_cast<tensor_size_t>(x.size())}, {g2.data(), static_cast<tensor_size_t>(g2.size())}) == f2);
+    CHECK(g2 == gx);
+    function.clear_statistics();
+    CHECK(function.fcalls() == 0);
+
+    std::printf("OK f=%.15g |g|_inf=%.6g\n", f1, gmax);
+    return 0;
+}
