@@ -346,7 +346,8 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         const mt_variant& var = kMtVariants[v];
         const int64_t     TP  = var.NT8 * 8;
         // forward: header (barriers + fold area + alignment slack) + stages of (128 + TP) rows x 20 doubles
-        const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + TP);
+        // forward: header (barriers + fold area + the [128][TP + 2] output tile + alignment slack)
+        const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + TP) + 8 * kMtBM * (TP + 2) + 512;
         const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
         const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (data->smem_optin - fwd_header) / fwd_stage);
         // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles

@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMtMaxStages;
+    constexpr int TPs   = TP + 2; // row stride of the output tile: 16-byte fragment stores hit 8 distinct bank groups
     double*   fold      = reinterpret_cast<double*>(smem + 256); // [kMtWarps][1 + TP] at the very end of the kernel
-    double*   stage0    = reinterpret_cast<double*>(smem + 256 + sizeof(double) * kMtWarps * (1 + TP) + 256);
+    double*   otile     = fold + kMtWarps * (1 + TP) + 2;        // [kMtBM][TPs] outputs of the current tile
+    otile               = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(otile) + 127) / 128 * 128);
+    double*   stage0    = otile + kMtBM * TPs;
     stage0              = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(stage0) + 127) / 128 * 128);
     constexpr int kStageDoubles = (kMtBM + TP) * kMtLd;
 
@@ -157,11 +160,12 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
     // ===== consumer warps: rows [warp*16, warp*16 + 16) of the tile, all targets =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMtConsumerRegs));
-    double gbacc[NT8][2]; // column sums of dL owned by this lane (columns nt*8 + 2*tig + {0, 1})
+    constexpr int TL = (TP + 31) / 32; // targets per lane in the row-wise epilogue (target t = lane + 32 * k)
+    double gbacc[TL];                  // column sums of dL owned by this lane
 #pragma unroll
-    for (int nt = 0; nt < NT8; ++nt)
+    for (int k = 0; k < TL; ++k)
     {
-        gbacc[nt][0] = gbacc[nt][1] = 0.0;
+        gbacc[k] = 0.0;
     }
     double fsum = 0.0;
 
@@ -208,80 +212,83 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
             }
         }
 
-        // ----- epilogue on the fragments: + bias (in place), loss value, dL -----
-        const int64_t row_base = tile * kMtBM + warp * 16 + g;
+        // ----- epilogue: accumulator fragments (+ bias) -> this warp's 16 rows of the shared output tile, then a
+        //       compact row-wise loop (lanes stride the targets: coalesced Y reads and dL writes, small code) -----
+        double* orows = otile + (warp * 16) * TPs;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
         {
-            const int64_t row   = row_base + mt * 8;
-            const bool    valid = row < p.N;
-            const double* yrow  = p.Y + (valid ? row : 0) * T; // invalid rows read row 0 and are discarded
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt)
             {
+                const int col = nt * 8 + tig * 2;
+                const double b0 = (col < T) ? p.b[col] : 0.0;
+                const double b1 = (col + 1 < T) ? p.b[col + 1] : 0.0;
+                *reinterpret_cast<double2*>(orows + (mt * 8 + g) * TPs + col) =
+                    make_double2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
+            }
+        }
+        __syncwarp();
+
+        const int64_t row_first = tile * kMtBM + warp * 16;
+        const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(16), p.N - row_first)));
+        for (int r = 0; r < row_count; ++r)
+        {
+            const int64_t row  = row_first + r;
+            double*       orow = orows + r * TPs;
+            const double* yrow = p.Y + row * T;
+            double        y[TL];
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                {
-                    const int col = nt * 8 + tig * 2 + e;
-                    acc[mt][nt][e] = (valid && col < T) ? (acc[mt][nt][e] + p.b[col]) : 0.0;
-                }
+            for (int k = 0; k < TL; ++k)
+            {
+                const int t = lane + 32 * k;
+                y[k]        = (t < T) ? yrow[t] : 0.0;
             }
 
             if (p.loss == LOSS_CLASSNLL)
             {
-                // classnll.h:19-37 on a row spread over 4 lanes
+                // classnll.h:19-37
                 double omax = -INFINITY;
 #pragma unroll
-                for (int nt = 0; nt < NT8; ++nt)
+                for (int k = 0; k < TL; ++k)
                 {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                    const int t = lane + 32 * k;
+                    if (t < T)
                     {
-                        if (nt * 8 + tig * 2 + e < T)
-                        {
-                            omax = max_of(omax, acc[mt][nt][e]);
-                        }
+                        omax = max_of(omax, orow[t]);
                     }
                 }
-                omax = quad_max(omax);
+                omax = warp_allreduce_max(omax);
+                double ex[TL];
                 double sumexp = 0.0, dot = 0.0;
 #pragma unroll
-                for (int nt = 0; nt < NT8; ++nt)
+                for (int k = 0; k < TL; ++k)
                 {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                    const int t = lane + 32 * k;
+                    ex[k]       = 0.0;
+                    if (t < T)
                     {
-                        const int col = nt * 8 + tig * 2 + e;
-                        if (col < T)
-                        {
-                            sumexp += exp(__dsub_rn(acc[mt][nt][e], omax));
-                            dot += __dmul_rn(__dadd_rn(1.0, yrow[col]), acc[mt][nt][e]);
-                        }
+                        const double o = orow[t];
+                        ex[k]          = exp(__dsub_rn(o, omax));
+                        sumexp += ex[k];
+                        dot += __dmul_rn(__dadd_rn(1.0, y[k]), o);
                     }
                 }
-                sumexp = quad_sum(sumexp);
-                dot    = quad_sum(dot);
-                if (valid && tig == 0)
-                {
-                    fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                }
-                if (GRAD && valid)
+                sumexp = warp_allreduce_sum(sumexp);
+                dot    = warp_allreduce_sum(dot);
+                fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
+                if (GRAD)
                 {
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt)
+                    for (int k = 0; k < TL; ++k)
                     {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
+                        const int t = lane + 32 * k;
+                        if (t < T)
                         {
-                            const int col = nt * 8 + tig * 2 + e;
-                            if (col < T)
-                            {
-                                const double ex = exp(__dsub_rn(acc[mt][nt][e], omax));
-                                const double gv =
-                                    __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, yrow[col])));
-                                p.dL[row * T + col] = gv;
-                                gbacc[nt][e] += gv;
-                            }
+                            const double gv =
+                                __dsub_rn(__ddiv_rn(ex[k], sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y[k])));
+                            p.dL[row * T + t] = gv;
+                            gbacc[k] += gv;
                         }
                     }
                 }
@@ -290,60 +297,42 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
             {
                 double sum = 0.0;
 #pragma unroll
-                for (int nt = 0; nt < NT8; ++nt)
+                for (int k = 0; k < TL; ++k)
                 {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                    const int t = lane + 32 * k;
+                    if (t < T)
                     {
-                        const int col = nt * 8 + tig * 2 + e;
-                        if (valid && col < T)
+                        double term, gv;
+                        loss_term<GRAD>(p.loss, p.loss_param, y[k], orow[t], term, gv);
+                        sum += term;
+                        if (GRAD)
                         {
-                            double term, gv;
-                            loss_term<GRAD>(p.loss, p.loss_param, yrow[col], acc[mt][nt][e], term, gv);
-                            sum += term;
-                            if (GRAD)
-                            {
-                                p.dL[row * T + col] = gv;
-                                gbacc[nt][e] += gv;
-                            }
+                            p.dL[row * T + t] = gv;
+                            gbacc[k] += gv;
                         }
                     }
                 }
-                sum = quad_sum(sum);
-                if (valid && tig == 0)
-                {
-                    fsum += loss_post(p.loss, sum);
-                }
+                fsum += loss_post(p.loss, warp_allreduce_sum(sum));
             }
         }
+        __syncwarp(); // the next tile's epilogue overwrites this warp's rows
     }
 
-    // ----- fold: lanes with the same tig hold the same columns -> butterfly over g, then over the warps -----
-    fsum += __shfl_xor_sync(0xffffffffu, fsum, 4);
-    fsum += __shfl_xor_sync(0xffffffffu, fsum, 8);
-    fsum += __shfl_xor_sync(0xffffffffu, fsum, 16);
-    fsum = quad_sum(fsum); // only tig == 0 lanes carried values
+    // ----- fold the 8 consumer warps in warp order -----
     double* mine = fold + warp * (1 + TP);
     if (lane == 0)
     {
-        mine[0] = fsum;
+        mine[0] = fsum; // identical on every lane
     }
     if (GRAD)
     {
 #pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
+        for (int k = 0; k < TL; ++k)
         {
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
+            const int t = lane + 32 * k;
+            if (t < TP)
             {
-                double v = gbacc[nt][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0)
-                {
-                    mine[1 + nt * 8 + tig * 2 + e] = v;
-                }
+                mine[1 + t] = gbacc[k];
             }
         }
     }

@@ -145,3 +145,22 @@ def test_device_resident_lbfgs_contract(ctx):
     assert short["status"] in ("max_iters", "gradient_test") and short["fcalls"] + short["gcalls"] <= 6 + 8
     with pytest.raises(RuntimeError, match="incompatible initial point"):
         lbfgs(function, np.zeros(4))
+
+
+def test_host_driven_osga_matches_the_restated_driver(ctx, oracle):
+    # libnano_b200.solver.osga and oracle/solvers.cpp restate the same algorithm independently: same GPU objective,
+    # same start => the same trajectory up to rounding
+    import libnano_b200 as nb
+    from libnano_b200.solver import osga
+
+    N, D = 3000, 16
+    X, Y, _ = make_problem(5, N, D, 1, True)
+    for l1, l2 in ((1e-2, 0.0), (1e-2, 1e-2)):
+        gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss("s-hinge"), l1, l2)
+        x0 = np.zeros(gpu.size())
+        mine = osga(gpu, x0, epsilon=1e-6, max_evals=2000)
+        ref = oracle.osga(gpu.clone(), x0, epsilon=1e-6, strong_convexity=gpu.strong_convexity(), max_evals=2000)
+        assert mine["status"] == ref["status"]
+        assert abs(mine["iterations"] - ref["iterations"]) <= max(2, ref["iterations"] // 20)
+        assert abs(mine["fx"] - ref["fx"]) <= 1e-6 * (1 + abs(ref["fx"]))
+        assert mine["fcalls"] == 2 * mine["iterations"] + 1 and mine["gcalls"] == mine["iterations"] + 1
