@@ -165,6 +165,18 @@ NB200_API int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, in
 NB200_API int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, int64_t n_global, double* gx_dev,
                                         double* fx_dev);
 
+/* Fused compute + collective for the single-target kernel: instead of all-reducing between two phases, the ONE launch
+ * of every rank writes its locally reduced column slices into the peers' mailboxes over NVLink (peer memory mapped
+ * through CUDA IPC), waits for the matching slices and folds them in rank order — identical bits on every rank, no
+ * NCCL call, no second kernel. Setup once per objective: every rank exports a 64-byte handle (and its grid size,
+ * which must agree across ranks), the handles are all-gathered by the host (world x 64 bytes, rank order), then
+ * connected. Evaluate with nb200_vgrad_sharded(_device); all ranks must call it the same number of times. */
+NB200_API int nb200_objective_peer_export(nb200_obj* obj, int world, void* handle_out, int64_t* grid_out);
+NB200_API int nb200_objective_peer_connect(nb200_obj* obj, int rank, int world, const void* handles);
+NB200_API int nb200_vgrad_sharded(nb200_obj* obj, const double* x, int64_t n, int64_t n_global, double* gx, double* fx);
+NB200_API int nb200_vgrad_sharded_device(nb200_obj* obj, const double* x_dev, int64_t n, int64_t n_global,
+                                         double* gx_dev, double* fx_dev);
+
 /* cudaStream_t of the objective, as an opaque pointer (so that callers can order collectives after phase 1);
  * set_stream re-points the objective at a caller-owned stream (a NULL handle is the legacy default stream), e.g. the
  * stream the caller's NCCL all-reduce is enqueued on, so that phase 1 -> all-reduce -> phase 2 need no host

@@ -42,6 +42,12 @@ SIGNATURES = {
                                                   ctypes.POINTER(c_i64)]),
     "nb200_vgrad_finish_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64, ctypes.c_void_p,
                                                  ctypes.c_void_p]),
+    "nb200_objective_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.POINTER(c_i64)]),
+    "nb200_objective_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "nb200_vgrad_sharded": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, c_i64, c_double_p, c_double_p]),
+    "nb200_vgrad_sharded_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64, c_i64, ctypes.c_void_p,
+                                                  ctypes.c_void_p]),
     "nb200_objective_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nb200_objective_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_launches": (c_i64, [ctypes.c_void_p]),

@@ -237,6 +237,16 @@ struct nb200_obj
     int     mt_fwd_grid{0}, mt_fwd_stages{0}, mt_fwd_smem{0};
     int     mt_splits{0}, mt_bwd_grid{0}, mt_bwd_stages{0}, mt_bwd_smem{0}, mt_t_ld{0};
 
+    // fused cross-rank all-reduce over peer memory (single-target path): mailbox + flags, see vgrad_t1.cuh
+    int                 peer_world{1};
+    int                 peer_rank{0};
+    int                 peer_col_stride{0};
+    unsigned long long  peer_epoch{0};
+    unsigned char*      peer_local{nullptr};               // this rank's mailbox allocation (cudaMalloc, IPC-exported)
+    unsigned char*      peer_base[kT1MaxPeers] = {nullptr}; // every rank's mailbox as seen from this device
+    int*                h_peer_error{nullptr};             // mapped host flag raised by the kernel on a peer timeout
+    int*                d_peer_error{nullptr};
+
     // state of a two-phase evaluation
     bool    partial_has_grad{false};
     const double* partial_x{nullptr};
@@ -268,6 +278,15 @@ void free_obj(nb200_obj* obj)
     cudaFree(obj->d_partials_gw);
     cudaFree(obj->d_dL);
     cudaFree(obj->d_grid_counter);
+    for (int r = 0; r < kT1MaxPeers; ++r)
+    {
+        if (obj->peer_base[r] != nullptr && obj->peer_base[r] != obj->peer_local)
+        {
+            cudaIpcCloseMemHandle(obj->peer_base[r]);
+        }
+    }
+    cudaFree(obj->peer_local);
+    cudaFreeHost(obj->h_peer_error);
     cudaFreeHost(obj->h_x);
     cudaFreeHost(obj->h_out);
     for (cudaEvent_t event : obj->ev0)
@@ -302,6 +321,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     obj->use_t1 = false;
     NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter, 0, sizeof(unsigned long long)));
     obj->grid_epoch = 0;
+    obj->peer_world = 1; // a new plan may change the grid: peers must reconnect
 
     const bool force_generic = forced_variant == -2 || env_int("NB200_FORCE_GENERIC", 0) != 0;
     if (T == 1 && !force_generic && D <= (1 << 20))
@@ -547,7 +567,7 @@ int enqueue_finish(nb200_obj* obj, const double* x_dev, const int64_t n_global, 
 //   finish == true:  also divide by n_global, add the regularisation terms and write gx_out (nullable) / fx_out.
 // The single-target path does all of it in ONE cooperative launch; the generic path takes 3-6 small launches.
 int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, const bool finish, const int64_t n_global,
-                 double* gx_out, double* fx_out)
+                 double* gx_out, double* fx_out, const bool peers = false)
 {
     const nb200_data* data = obj->data;
     const int64_t     N = data->N, D = data->D, T = data->T;
@@ -591,6 +611,22 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.n_global       = n_global;
         p.l1             = obj->l1;
         p.l2             = obj->l2;
+        p.world          = 1;
+        if (peers)
+        {
+            obj->peer_epoch += 1;
+            p.world      = obj->peer_world;
+            p.rank       = obj->peer_rank;
+            p.col_stride = obj->peer_col_stride;
+            p.epoch      = obj->peer_epoch;
+            p.peer_error = obj->d_peer_error;
+            const size_t mail_bytes = static_cast<size_t>(2) * obj->peer_world * obj->peer_col_stride * sizeof(double);
+            for (int r = 0; r < obj->peer_world; ++r)
+            {
+                p.peer_mail[r] = reinterpret_cast<double*>(obj->peer_base[r]);
+                p.peer_flag[r] = reinterpret_cast<unsigned long long*>(obj->peer_base[r] + mail_bytes);
+            }
+        }
 
         // cooperative launch: the grid barrier of the fused tail needs every CTA resident (grid <= #SMs, 1 CTA/SM)
         void*       args[] = {&p};
@@ -1091,6 +1127,99 @@ int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, const int64_t
     NB200_REQUIRE(gx_dev == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     return enqueue_finish(obj, x_dev, n_global, gx_dev, fx_dev);
+}
+
+int nb200_objective_peer_export(nb200_obj* obj, const int world, void* handle_out, int64_t* grid_out)
+{
+    NB200_REQUIRE(obj != nullptr && handle_out != nullptr && grid_out != nullptr, "peers: null argument");
+    NB200_REQUIRE(world >= 2 && world <= kT1MaxPeers, "peers: the world size must be in [2, 8]");
+    NB200_REQUIRE(obj->use_t1, "peers: the fused all-reduce exists for the single-target kernel only");
+    NB200_REQUIRE(obj->peer_local == nullptr, "peers: already exported");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+    obj->peer_col_stride = static_cast<int>(round_up(obj->data->D + 2, 2));
+    const size_t bytes = (static_cast<size_t>(2) * world * obj->peer_col_stride +
+                          static_cast<size_t>(2) * world * obj->t1.grid) * sizeof(double);
+    NB200_CUDA_TRY(cudaMalloc(&obj->peer_local, bytes));
+    NB200_CUDA_TRY(cudaMemset(obj->peer_local, 0, bytes));
+    NB200_CUDA_TRY(cudaHostAlloc(&obj->h_peer_error, sizeof(int), cudaHostAllocMapped));
+    *obj->h_peer_error = 0;
+    NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->d_peer_error, obj->h_peer_error, 0));
+    NB200_CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t handle;
+    NB200_CUDA_TRY(cudaIpcGetMemHandle(&handle, obj->peer_local));
+    std::memcpy(handle_out, &handle, sizeof(handle));
+    *grid_out = obj->t1.grid;
+    return NB200_OK;
+}
+
+int nb200_objective_peer_connect(nb200_obj* obj, const int rank, const int world, const void* handles)
+{
+    NB200_REQUIRE(obj != nullptr && handles != nullptr, "peers: null argument");
+    NB200_REQUIRE(obj->peer_local != nullptr, "peers: export first");
+    NB200_REQUIRE(world >= 2 && world <= kT1MaxPeers && rank >= 0 && rank < world, "peers: invalid rank / world");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    for (int r = 0; r < world; ++r)
+    {
+        if (r == rank)
+        {
+            obj->peer_base[r] = obj->peer_local;
+            continue;
+        }
+        cudaIpcMemHandle_t handle;
+        std::memcpy(&handle, static_cast<const unsigned char*>(handles) + static_cast<size_t>(r) * sizeof(handle),
+                    sizeof(handle));
+        void* mapped = nullptr;
+        NB200_CUDA_TRY(cudaIpcOpenMemHandle(&mapped, handle, cudaIpcMemLazyEnablePeerAccess));
+        obj->peer_base[r] = static_cast<unsigned char*>(mapped);
+    }
+    obj->peer_world = world;
+    obj->peer_rank  = rank;
+    obj->peer_epoch = 0;
+    return NB200_OK;
+}
+
+static int check_peers(nb200_obj* obj)
+{
+    NB200_REQUIRE(obj->peer_world > 1 && obj->use_t1, "peers: nb200_objective_peer_connect has not been called");
+    return NB200_OK;
+}
+
+int nb200_vgrad_sharded(nb200_obj* obj, const double* x, const int64_t n, const int64_t n_global, double* gx, double* fx)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
+    NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    int status = check_peers(obj);
+    if (status == NB200_OK)
+    {
+        status = upload_x(obj, x, n);
+    }
+    if (status == NB200_OK)
+    {
+        status = enqueue_eval(obj, obj->d_x, gx != nullptr, true, n_global, gx != nullptr ? obj->h_out_dev : nullptr,
+                              obj->h_out_dev + obj->n, true);
+    }
+    if (status == NB200_OK)
+    {
+        status = collect_result(obj, gx, fx);
+    }
+    if (status == NB200_OK && *obj->h_peer_error != 0)
+    {
+        *obj->h_peer_error = 0;
+        return fail(NB200_ERR_CUDA, "peers: a rank did not reach the all-reduce within the time limit");
+    }
+    return status;
+}
+
+int nb200_vgrad_sharded_device(nb200_obj* obj, const double* x_dev, const int64_t n, const int64_t n_global,
+                               double* gx_dev, double* fx_dev)
+{
+    NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
+    NB200_REQUIRE(n == obj->n && n_global > 0, "function: invalid sizes");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    const int status = check_peers(obj);
+    return status != NB200_OK ? status : enqueue_eval(obj, x_dev, gx_dev != nullptr, true, n_global, gx_dev, fx_dev, true);
 }
 
 void* nb200_objective_stream(const nb200_obj* obj)

@@ -33,6 +33,7 @@ namespace nb200
 {
 constexpr int kT1MaxStages  = 8;
 constexpr int kT1HeaderSize = 1024; // barriers + dot-exchange slots + tail scratch
+constexpr int kT1MaxPeers   = 8;    // ranks of one NVSwitch domain
 
 struct t1_params
 {
@@ -63,6 +64,17 @@ struct t1_params
     int64_t             n_global;
     double              l1;
     double              l2;
+
+    // fused cross-rank all-reduce over NVLink peer memory (sample-sharded evaluation, world > 1): every rank owns a
+    // mailbox [2 (parity)][world][col_stride] doubles and flags [2][world][grid]; rank r writes its locally reduced
+    // column slices into slot r of EVERY rank's mailbox and raises the matching per-CTA flags.
+    int                 world;       // 1: no cross-rank stage
+    int                 rank;
+    int                 col_stride;  // doubles per mailbox slot (>= D + 2)
+    unsigned long long  epoch;       // evaluation counter, identical on all ranks
+    double*             peer_mail[kT1MaxPeers];
+    unsigned long long* peer_flag[kT1MaxPeers];
+    int*                peer_error;  // mapped host int: set when a peer did not show up in time
 };
 
 #ifdef __CUDACC__
@@ -294,6 +306,71 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
     }
 }
 
+// the final scaling + regularisation of one column of the reduced vector [loss | gb | gW] (one thread)
+template <int NWARPS>
+__device__ __forceinline__ void finish_column(const t1_params& p, const int c, const double sum, const double* w_s,
+                                              const double* scratch)
+{
+    const int    D       = p.D;
+    const double samples = static_cast<double>(p.n_global);
+    const double wsize   = static_cast<double>(D); // T == 1
+    if (c == 0)
+    {
+        double sabs = 0.0, ssqr = 0.0;
+        for (int q = 0; q < NWARPS; ++q)
+        {
+            sabs += scratch[q];
+            ssqr += scratch[NWARPS + q];
+        }
+        double fx = __ddiv_rn(sum, samples);
+        if (p.flavour == 0)
+        {
+            if (p.l1 > 0.0)
+            {
+                fx = __dadd_rn(fx, __dmul_rn(p.l1, __ddiv_rn(sabs, wsize)));
+            }
+            if (p.l2 > 0.0)
+            {
+                fx = __dadd_rn(fx, __dmul_rn(0.5, __ddiv_rn(ssqr, wsize)));
+            }
+        }
+        else
+        {
+            fx = __dadd_rn(fx, __dadd_rn(__dmul_rn(p.l1, sabs), __dmul_rn(0.5, ssqr)));
+        }
+        *p.fx_out = fx;
+    }
+    else if (c == 1)
+    {
+        if (p.flavour == 0 && p.gx_out != nullptr)
+        {
+            p.gx_out[D] = __ddiv_rn(sum, samples); // gb = acc.m_gb / N
+        }
+    }
+    else if (p.gx_out != nullptr)
+    {
+        const int    j  = c - 2;
+        const double wj = w_s[j];
+        double       gj = __ddiv_rn(sum, samples);
+        if (p.flavour == 0)
+        {
+            if (p.l1 > 0.0)
+            {
+                gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l1, sign_of(wj)), wsize));
+            }
+            if (p.l2 > 0.0)
+            {
+                gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l2, wj), wsize));
+            }
+        }
+        else
+        {
+            gj = __dadd_rn(gj, __dadd_rn(__dmul_rn(p.l1, sign_of(wj)), __dmul_rn(p.l2, wj)));
+        }
+        p.gx_out[j] = gj;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tail (all warps): grid barrier, then this CTA folds its slice of columns over every CTA's partial row
 // (sum_reduce, include/nano/core/reduce.h:23-31) and, when fuse_finish, applies the final scaling and the
@@ -339,8 +416,9 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
     const int     c_begin  = blockIdx.x * cpc;
     const int     c_end    = min(cols, c_begin + cpc);
     const int64_t stride   = D + 2;
-    const double  samples  = static_cast<double>(p.n_global);
-    const double  wsize    = static_cast<double>(D); // T == 1
+
+    const int                parity = static_cast<int>(p.epoch & 1ULL);
+    const unsigned long long slot   = static_cast<unsigned long long>(parity) * p.world + p.rank;
 
     for (int c = c_begin + warp; c < c_end; c += NWARPS)
     {
@@ -351,69 +429,69 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
             sum += __ldcg(p.partials + static_cast<int64_t>(r) * stride + c);
         }
         sum = warp_allreduce_sum(sum);
-        if (lane != 0)
+        if (p.world > 1)
         {
-            continue;
+            // all-gather over peer memory: lane q stores this rank's column sum into rank q's mailbox
+            if (lane < p.world)
+            {
+                p.peer_mail[lane][slot * p.col_stride + c] = sum;
+            }
+        }
+        else if (lane == 0)
+        {
+            p.reduced[c] = sum;
+            if (p.fuse_finish != 0)
+            {
+                finish_column<NWARPS>(p, c, sum, w_s, scratch);
+            }
+        }
+    }
+    if (p.world <= 1)
+    {
+        return;
+    }
+
+    // ---- cross-rank stage: publish this CTA's slice, wait for the same slice of every peer, fold in rank order ----
+    __threadfence_system();
+    __syncthreads();
+    if (warp == 0)
+    {
+        if (lane < p.world)
+        {
+            // release: the slice written above is visible to rank `lane` before it sees the flag
+            unsigned long long* flag = p.peer_flag[lane] + slot * G + blockIdx.x;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.epoch) : "memory");
+            // acquire: wait for rank `lane`'s slice in MY mailbox (flags only grow; parity double-buffers the mail)
+            const unsigned long long* mine =
+                p.peer_flag[p.rank] + (static_cast<unsigned long long>(parity) * p.world + lane) * G + blockIdx.x;
+            unsigned long long seen  = 0;
+            const long long    start = clock64();
+            do
+            {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+                if (seen < p.epoch && clock64() - start > 4000000000LL) // ~2 s: a peer never launched
+                {
+                    *p.peer_error = 1;
+                    break;
+                }
+            } while (seen < p.epoch);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    const double* mail = p.peer_mail[p.rank] + static_cast<unsigned long long>(parity) * p.world * p.col_stride;
+    for (int c = c_begin + threadIdx.x; c < c_end; c += NWARPS * 32)
+    {
+        double sum = 0.0;
+        for (int q = 0; q < p.world; ++q) // rank order: identical bits on every rank
+        {
+            sum += __ldcg(mail + static_cast<int64_t>(q) * p.col_stride + c);
         }
         p.reduced[c] = sum;
-        if (p.fuse_finish == 0)
+        if (p.fuse_finish != 0)
         {
-            continue;
-        }
-        if (c == 0)
-        {
-            double sabs = 0.0, ssqr = 0.0;
-            for (int q = 0; q < NWARPS; ++q)
-            {
-                sabs += scratch[q];
-                ssqr += scratch[NWARPS + q];
-            }
-            double fx = __ddiv_rn(sum, samples);
-            if (p.flavour == 0)
-            {
-                if (p.l1 > 0.0)
-                {
-                    fx = __dadd_rn(fx, __dmul_rn(p.l1, __ddiv_rn(sabs, wsize)));
-                }
-                if (p.l2 > 0.0)
-                {
-                    fx = __dadd_rn(fx, __dmul_rn(0.5, __ddiv_rn(ssqr, wsize)));
-                }
-            }
-            else
-            {
-                fx = __dadd_rn(fx, __dadd_rn(__dmul_rn(p.l1, sabs), __dmul_rn(0.5, ssqr)));
-            }
-            *p.fx_out = fx;
-        }
-        else if (c == 1)
-        {
-            if (p.flavour == 0 && p.gx_out != nullptr)
-            {
-                p.gx_out[D] = __ddiv_rn(sum, samples); // gb = acc.m_gb / N
-            }
-        }
-        else if (p.gx_out != nullptr)
-        {
-            const int    j  = c - 2;
-            const double wj = w_s[j];
-            double       gj = __ddiv_rn(sum, samples);
-            if (p.flavour == 0)
-            {
-                if (p.l1 > 0.0)
-                {
-                    gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l1, sign_of(wj)), wsize));
-                }
-                if (p.l2 > 0.0)
-                {
-                    gj = __dadd_rn(gj, __ddiv_rn(__dmul_rn(p.l2, wj), wsize));
-                }
-            }
-            else
-            {
-                gj = __dadd_rn(gj, __dadd_rn(__dmul_rn(p.l1, sign_of(wj)), __dmul_rn(p.l2, wj)));
-            }
-            p.gx_out[j] = gj;
+            finish_column<NWARPS>(p, c, sum, w_s, scratch);
         }
     }
 }
