@@ -51,6 +51,9 @@ def parse_args():
     parser.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of cpu_baseline")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--variant", type=int, default=-1, help="fused-kernel variant (tuning), -1 = heuristic")
+    parser.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                        help="N > 1: 'peer' = all-reduce fused into the kernel over NVLink peer memory, 'nccl' = "
+                             "two phases around torch.distributed.all_reduce, 'auto' = peer if it can be set up")
     return parser.parse_args()
 
 
@@ -242,6 +245,22 @@ def run_b200(args):
         local.set_variant(args.variant)
     function = ShardedFunction.from_local(local, n_global)  # re-points `local` at torch's current stream
     n = function.size()
+    collective = "none"
+    if world > 1:
+        collective = "nccl"
+        if args.collective in ("auto", "peer"):
+            try:
+                if function.connect_peers():
+                    collective = "peer"
+            except Exception as error:  # noqa: BLE001 - fall back to the NCCL path, say so in the JSON line
+                if args.collective == "peer":
+                    raise
+                collective = f"nccl (peer setup failed: {error})"
+        flags = [None] * world
+        dist.all_gather_object(flags, collective == "peer")
+        if not all(flags):  # every rank must take the same path
+            function._shard.fused = False
+            collective = collective if collective != "peer" else "nccl"
 
     rng = np.random.default_rng(0)
     x = rng.uniform(-1.0, 1.0, n) / np.sqrt(features)
@@ -268,6 +287,9 @@ def run_b200(args):
         if world == 1:
             # one cooperative launch: pass over X, cross-CTA reduction, scaling + regularisation
             local.vgrad_device(x_dev.data_ptr(), g_dev.data_ptr(), f_dev.data_ptr())
+        elif collective == "peer":
+            # ONE launch per rank: pass over X + all-reduce over NVLink peer memory + scaling, no NCCL call
+            local.vgrad_sharded_device(x_dev.data_ptr(), n_global, g_dev.data_ptr(), f_dev.data_ptr())
         else:
             ptr, length = local.partial_device(x_dev.data_ptr(), True)
             dist.all_reduce(function._shard._view_for(ptr, length))
@@ -336,12 +358,16 @@ def run_b200(args):
                    "rows_per_gpu": rows, "features": features, "targets": 1, "global_rows": n_global,
                    "parallelism": f"sample-sharded x{world}, one all-reduce of {n + 1} doubles per step"
                    if world > 1 else "single GPU",
+                   "collective": {"peer": "fused into the kernel: peer-memory all-gather over NVLink + rank-ordered sum",
+                                  "none": "none (single GPU)"}.get(collective, collective),
                    "l2_flush": f"inputs larger than L2: {8 * rows * features / 2 ** 30:.1f} GiB of X per GPU is "
                                "streamed every step (L2 is 126 MB)",
                    "kernel": local.describe()},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 1),
-                "api": "libnano_b200.ShardedFunction.__call__(x, gx) -> nb200_vgrad_partial/finish (host buffers)"},
+                "api": "libnano_b200.ShardedFunction.__call__(x, gx) (host buffers) -> " +
+                       {"none": "nb200_vgrad", "peer": "nb200_vgrad_sharded"}.get(collective,
+                                                                                 "nb200_vgrad_partial / finish")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(rows, features),

@@ -254,6 +254,28 @@ class _DeviceFunction(Function):
         _lib.check(_lib.lib().nb200_vgrad_finish_device(self.handle, ctypes.c_void_p(x_ptr), n_global,
                                                         ctypes.c_void_p(gx_ptr or 0), ctypes.c_void_p(fx_ptr)))
 
+    # -- fused compute + collective (single-target kernel; peers' mailboxes mapped through CUDA IPC) -----------------
+    def peer_export(self, world: int):
+        """This rank's 64-byte IPC handle of its mailbox and the grid size (must agree across ranks)."""
+        handle = ctypes.create_string_buffer(64)
+        grid = ctypes.c_int64()
+        _lib.check(_lib.lib().nb200_objective_peer_export(self.handle, world, handle, ctypes.byref(grid)))
+        return handle.raw, grid.value
+
+    def peer_connect(self, rank: int, world: int, handles: bytes) -> None:
+        critical(len(handles) == 64 * world, "peers: expecting ", 64 * world, " bytes of handles")
+        _lib.check(_lib.lib().nb200_objective_peer_connect(self.handle, rank, world, handles))
+
+    def vgrad_sharded(self, x, n_global: int, gx=None) -> float:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        _lib.check(_lib.lib().nb200_vgrad_sharded(self.handle, _ptr(x), x.size, n_global, _ptr(gx),
+                                                  ctypes.byref(self._fx)))
+        return self._fx.value
+
+    def vgrad_sharded_device(self, x_ptr: int, n_global: int, gx_ptr: int | None, fx_ptr: int) -> None:
+        _lib.check(_lib.lib().nb200_vgrad_sharded_device(self.handle, ctypes.c_void_p(x_ptr), self.size(), n_global,
+                                                         ctypes.c_void_p(gx_ptr or 0), ctypes.c_void_p(fx_ptr)))
+
     def sync(self) -> None:
         _lib.check(_lib.lib().nb200_objective_sync(self.handle))
 

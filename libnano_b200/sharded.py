@@ -54,6 +54,7 @@ class DeviceShard:
         self._stream = torch.cuda.current_stream()
         local.set_stream(self._stream.cuda_stream)
         self._view = None
+        self.fused = False  # True once connect_peers() mapped the peers' mailboxes
 
     def size(self) -> int:
         return self.local.size()
@@ -77,6 +78,26 @@ class DeviceShard:
     def eval(self, x, gx):
         """Single-rank shortcut: the fused one-launch evaluation (no all-reduce to wait for)."""
         return self.local.do_eval(x, gx)
+
+    def connect_peers(self, group=None) -> bool:
+        """Set up the fused compute + collective path: every rank maps every other rank's mailbox (CUDA IPC over
+        NVLink), after which ONE kernel launch per rank does the pass over X AND the all-reduce. Returns False (and
+        leaves the NCCL two-phase path in place) when the objective is not on the single-target kernel."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > 8 or not self.local.describe().startswith("t1"):
+            return False
+        handle, grid = self.local.peer_export(world)
+        mine = self._torch.tensor(list(handle) + [grid % 256, grid // 256], dtype=self._torch.uint8, device="cuda")
+        gathered = [self._torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blobs = [bytes(t.cpu().tolist()) for t in gathered]
+        critical(all(b[64:] == blobs[0][64:] for b in blobs), "peers: the ranks run different grids")
+        self.local.peer_connect(rank, world, b"".join(b[:64] for b in blobs))
+        dist.barrier(group=group)
+        self.fused = True
+        return True
 
 
 class ShardedFunction(Function):
@@ -105,9 +126,15 @@ class ShardedFunction(Function):
     def world_size(self) -> int:
         return self._dist.get_world_size(self._group) if self._dist.is_initialized() else 1
 
+    def connect_peers(self) -> bool:
+        """Switch to the fused compute + collective kernel (peer memory over NVLink) when the shard supports it."""
+        return bool(getattr(self._shard, "connect_peers", lambda group=None: False)(self._group))
+
     def do_eval(self, x, gx) -> float:
         if self.world_size() == 1 and hasattr(self._shard, "eval"):
             return self._shard.eval(x, gx)
+        if getattr(self._shard, "fused", False):
+            return self._shard.local.vgrad_sharded(x, self._n_global, gx)
         buffer = self._shard.partial(x, gx is not None)
         if self.world_size() > 1:
             self._dist.all_reduce(buffer, op=self._dist.ReduceOp.SUM, group=self._group)

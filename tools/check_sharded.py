@@ -24,6 +24,7 @@ def main():
     import libnano_b200 as nb
     from libnano_b200.sharded import ShardedFunction, broadcast_x, shard_rows
 
+    args_fused = "--fused" in sys.argv
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -40,6 +41,7 @@ def main():
         part = nb.Dataset.synth(ctx, kind, rows, D, T=T, seed=7, row_offset=row0)
         local = nb.LinearFunction(part, nb.Loss(loss_id), 0.01 if loss_id == "s-hinge" else 0.0, 1e-2)
         sharded = ShardedFunction.from_local(local, N)
+        fused = bool(args_fused and world > 1 and sharded.connect_peers())
         rng = np.random.default_rng(1)
         x = broadcast_x(rng.uniform(-1, 1, sharded.size()) / np.sqrt(D))
         gx = np.empty_like(x)
@@ -53,7 +55,10 @@ def main():
             same = all(torch.equal(gathered[0], t) for t in gathered)
         else:
             same = True
-        case = {"N": N, "D": D, "T": T, "loss": loss_id, "identical_across_ranks": bool(same)}
+        case = {"N": N, "D": D, "T": T, "loss": loss_id, "identical_across_ranks": bool(same), "fused_peers": fused}
+        for _ in range(5):  # repeated evaluations exercise the mailbox parity / epoch logic
+            g2 = np.empty_like(x)
+            same = same and sharded(x, g2) == fx and np.array_equal(g2, gx) and sharded(x) == fv
         if rank == 0:
             whole = nb.LinearFunction(nb.Dataset.synth(ctx, kind, N, D, T=T, seed=7), nb.Loss(loss_id),
                                       0.01 if loss_id == "s-hinge" else 0.0, 1e-2)
