@@ -137,7 +137,7 @@ def cpu_sample(rows, features, X=None, Y=None):
     return np.ascontiguousarray(X), np.ascontiguousarray(Y)
 
 
-def time_cpu(X, Y, budget_seconds, min_calls=3, max_calls=16):
+def time_cpu(X, Y, budget_seconds, min_calls=3, max_calls=100000):
     """Mirror of nano::measure (include/nano/core/chrono.h:81-114): repeated calls, minimum time; x = 0 as in
     app/bench_function.cpp:16. Returns (samples*features/s from the min, per-call seconds list, threads)."""
     import oracle
