@@ -121,6 +121,19 @@ NB200_API int64_t nb200_dataset_samples(const nb200_data* data);
 NB200_API int64_t nb200_dataset_inputs(const nb200_data* data);
 NB200_API int64_t nb200_dataset_targets(const nb200_data* data);
 
+/* flatten_iterator_t::scaling on the device (src/dataset/stats.cpp:81-137,357-401): column statistics over the finite
+ * values of the pinned inputs and targets, then in-place scaling (0 none, 1 mean, 2 minmax, 3 standard — the values of
+ * nano::scaling_type, include/nano/dataset/scaling.h:10-16) with non-finite values (missing data) set to 0.
+ * enable_*: optional byte masks, 0 = leave that column unscaled (categorical columns / class targets). Call once, before
+ * creating objectives. nb200_dataset_stats returns the scalar_stats_t arrays (any pointer may be NULL; which: 0 inputs,
+ * 1 targets); nb200_upscale is nano::upscale (stats.cpp:211-230): it maps (W [T, D], b [T]) fitted on the scaled data
+ * back to the original units, in place. */
+NB200_API int nb200_dataset_scale(nb200_data* data, int inputs_scaling, int targets_scaling,
+                                  const unsigned char* enable_inputs, const unsigned char* enable_targets);
+NB200_API int nb200_dataset_stats(const nb200_data* data, int which, double* samples, double* min, double* max,
+                                  double* mean, double* stdev, double* div_range, double* div_stdev);
+NB200_API int nb200_upscale(const nb200_data* data, double* W, double* b);
+
 /* Datasets are reference counted: objectives retain the dataset they were created on. */
 NB200_API void nb200_dataset_retain(nb200_data* data);
 NB200_API void nb200_dataset_release(nb200_data* data);

@@ -22,6 +22,10 @@ SIGNATURES = {
     "nb200_dataset_synth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
                                            ctypes.c_double, c_void_pp]),
     "nb200_dataset_read": (ctypes.c_int, [ctypes.c_void_p, c_i64, c_i64, c_double_p, c_double_p]),
+    "nb200_dataset_scale": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                           ctypes.c_char_p]),
+    "nb200_dataset_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [c_double_p] * 7),
+    "nb200_upscale": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
     "nb200_dataset_samples": (c_i64, [ctypes.c_void_p]),
     "nb200_dataset_inputs": (c_i64, [ctypes.c_void_p]),
     "nb200_dataset_targets": (c_i64, [ctypes.c_void_p]),

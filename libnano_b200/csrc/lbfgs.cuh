@@ -400,7 +400,8 @@ private:
         int status;
         if (m_allreduce == nullptr)
         {
-            status = enqueue_eval(m_obj, m_x, true, true, m_n_global, m_g, m_f);
+            // one launch; with connected peers the cross-rank all-reduce happens inside it (vgrad_t1.cuh)
+            status = enqueue_eval(m_obj, m_x, true, true, m_n_global, m_g, m_f, m_obj->peer_world > 1);
         }
         else
         {

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "loss.cuh"
 #include "reduce.cuh"
+#include "scale.cuh"
 #include "synth.cuh"
 #include "vgrad_gen.cuh"
 #include "vgrad_mt.cuh"
@@ -42,6 +43,8 @@ struct nb200_data
     double*          X{nullptr}; // [N, D] + 256 bytes of zeroed slack (bulk copies round tails up to 16 bytes)
     double*          Y{nullptr}; // [N, T] + slack
     int64_t          N{0}, D{0}, T{0};
+    nb200::column_stats_t inputs_stats;  // filled by nb200_dataset_scale
+    nb200::column_stats_t targets_stats;
 };
 
 namespace
@@ -1004,6 +1007,139 @@ void nb200_dataset_release(nb200_data* data)
     }
 }
 
+static int device_column_stats(nb200_data* data, const double* values, const int64_t C, const unsigned char* enable,
+                               column_stats_t& stats)
+{
+    const int64_t N      = data->N;
+    const int     chunks = static_cast<int>((N + kStatsRowsPerBlock - 1) / kStatsRowsPerBlock);
+    double *      partial = nullptr, *folded = nullptr;
+    const auto    run     = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&partial, static_cast<size_t>(chunks) * 5 * C * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&folded, static_cast<size_t>(5) * C * sizeof(double)));
+        const dim3 grid(static_cast<unsigned>((C + 255) / 256), static_cast<unsigned>(chunks));
+        column_stats_kernel<<<grid, 256>>>(values, N, C, partial);
+        NB200_CUDA_TRY(cudaGetLastError());
+        column_stats_fold_kernel<<<static_cast<unsigned>((C + 255) / 256), 256>>>(partial, chunks, C, folded);
+        NB200_CUDA_TRY(cudaGetLastError());
+        std::vector<double> raw(static_cast<size_t>(5 * C));
+        NB200_CUDA_TRY(cudaMemcpy(raw.data(), folded, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        finish_column_stats(raw, C, enable, stats);
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(partial);
+    cudaFree(folded);
+    return status;
+}
+
+static int device_column_scale(double* values, const int64_t N, const int64_t C, const column_stats_t& stats,
+                               const int scaling, const int sm_count)
+{
+    std::vector<double> shift(static_cast<size_t>(C), 0.0), mul(static_cast<size_t>(C), 1.0);
+    for (int64_t i = 0; i < C; ++i)
+    {
+        switch (scaling) // scalar_stats_t::scale (stats.cpp:357-401)
+        {
+        case 1: shift[i] = stats.mean[i]; mul[i] = stats.div_range[i]; break;
+        case 2: shift[i] = stats.min[i]; mul[i] = stats.div_range[i]; break;
+        case 3: shift[i] = stats.mean[i]; mul[i] = stats.div_stdev[i]; break;
+        default: break; // none: only non-finite -> 0
+        }
+    }
+    double*    d   = nullptr;
+    const auto run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&d, static_cast<size_t>(2 * C) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMemcpy(d, shift.data(), static_cast<size_t>(C) * sizeof(double), cudaMemcpyHostToDevice));
+        NB200_CUDA_TRY(cudaMemcpy(d + C, mul.data(), static_cast<size_t>(C) * sizeof(double), cudaMemcpyHostToDevice));
+        column_scale_kernel<<<sm_count * 8, 256>>>(values, N, C, d, d + C);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaDeviceSynchronize());
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(d);
+    return status;
+}
+
+int nb200_dataset_scale(nb200_data* data, const int inputs_scaling, const int targets_scaling,
+                        const unsigned char* enable_inputs, const unsigned char* enable_targets)
+{
+    NB200_REQUIRE(data != nullptr, "dataset: null argument");
+    NB200_REQUIRE(inputs_scaling >= 0 && inputs_scaling <= 3 && targets_scaling >= 0 && targets_scaling <= 3,
+                  "dataset: unhandled scaling type");
+    NB200_REQUIRE(data->inputs_stats.empty(), "dataset: already scaled");
+    NB200_CUDA_TRY(cudaSetDevice(data->device));
+    int status = device_column_stats(data, data->X, data->D, enable_inputs, data->inputs_stats);
+    if (status == NB200_OK)
+    {
+        status = device_column_stats(data, data->Y, data->T, enable_targets, data->targets_stats);
+    }
+    if (status == NB200_OK)
+    {
+        status = device_column_scale(data->X, data->N, data->D, data->inputs_stats, inputs_scaling, data->sm_count);
+    }
+    if (status == NB200_OK)
+    {
+        status = device_column_scale(data->Y, data->N, data->T, data->targets_stats, targets_scaling, data->sm_count);
+    }
+    if (status == NB200_OK)
+    {
+        data->inputs_stats.scaling  = inputs_scaling;
+        data->targets_stats.scaling = targets_scaling;
+    }
+    return status;
+}
+
+int nb200_dataset_stats(const nb200_data* data, const int which, double* samples, double* min, double* max,
+                        double* mean, double* stdev, double* div_range, double* div_stdev)
+{
+    NB200_REQUIRE(data != nullptr && (which == 0 || which == 1), "dataset: invalid argument");
+    const column_stats_t& stats = (which == 0) ? data->inputs_stats : data->targets_stats;
+    NB200_REQUIRE(!stats.empty(), "dataset: statistics are available after nb200_dataset_scale");
+    const auto copy = [](const std::vector<double>& from, double* to)
+    {
+        if (to != nullptr)
+        {
+            std::memcpy(to, from.data(), from.size() * sizeof(double));
+        }
+    };
+    copy(stats.samples, samples);
+    copy(stats.min, min);
+    copy(stats.max, max);
+    copy(stats.mean, mean);
+    copy(stats.stdev, stdev);
+    copy(stats.div_range, div_range);
+    copy(stats.div_stdev, div_stdev);
+    return NB200_OK;
+}
+
+int nb200_upscale(const nb200_data* data, double* W, double* b)
+{
+    // nano::upscale (src/dataset/stats.cpp:211-230)
+    NB200_REQUIRE(data != nullptr && W != nullptr && b != nullptr, "upscale: null argument");
+    NB200_REQUIRE(!data->inputs_stats.empty(), "upscale: the dataset has not been scaled");
+    std::vector<double> fw, fb, tw, tb;
+    scaling_affine(data->inputs_stats, data->inputs_stats.scaling, fw, fb);
+    scaling_affine(data->targets_stats, data->targets_stats.scaling, tw, tb);
+    const int64_t D = data->D, T = data->T;
+    for (int64_t t = 0; t < T; ++t)
+    {
+        double dot = 0.0;
+        for (int64_t j = 0; j < D; ++j)
+        {
+            dot += W[t * D + j] * fb[static_cast<size_t>(j)];
+        }
+        b[t] = (dot + b[t] - tb[static_cast<size_t>(t)]) / tw[static_cast<size_t>(t)];
+        for (int64_t j = 0; j < D; ++j)
+        {
+            W[t * D + j] = W[t * D + j] / tw[static_cast<size_t>(t)] * fw[static_cast<size_t>(j)];
+        }
+    }
+    return NB200_OK;
+}
+
 int nb200_objective_create(nb200_data* data, const int loss, const double loss_param, const int flavour,
                            const double l1, const double l2, const double* fixed_bias, nb200_obj** out_obj)
 {
@@ -1336,8 +1472,9 @@ int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const doubl
     NB200_REQUIRE(n == obj->n, "solver: incompatible initial point (" + std::to_string(n) + " dimensions), expecting " +
                                    std::to_string(obj->n) + " dimensions!");
     NB200_REQUIRE(epsilon > 0.0 && max_evals > 0 && history >= 1 && history <= 1000, "lbfgs: invalid parameters");
-    NB200_REQUIRE((allreduce == nullptr) == (n_global == 0 || n_global == obj->data->N),
-                  "lbfgs: a sharded solve needs both the global sample count and the all-reduce callback");
+    NB200_REQUIRE(allreduce == nullptr || n_global > 0, "lbfgs: a sharded solve needs the global sample count");
+    NB200_REQUIRE(allreduce != nullptr || n_global == 0 || n_global == obj->data->N || obj->peer_world > 1,
+                  "lbfgs: a sharded solve needs the all-reduce callback or connected peers");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user);
     return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);

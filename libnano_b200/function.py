@@ -105,6 +105,40 @@ class Dataset:
         _lib.check(_lib.lib().nb200_dataset_read(self.handle, row0, rows, _ptr(X), _ptr(Y)))
         return X, Y
 
+    SCALINGS = {"none": 0, "mean": 1, "minmax": 2, "standard": 3}  # nano::scaling_type (dataset/scaling.h:10-16)
+
+    def scale(self, inputs: str = "standard", targets: str = "none", enable_inputs=None, enable_targets=None):
+        """flatten_iterator_t::scaling (src/dataset/stats.cpp:81-137,357-401) on the device, once: column statistics
+        over the finite values, in-place scaling, non-finite -> 0. `enable_*`: per-column masks (False = categorical
+        column / class target, left unscaled). Returns self."""
+        critical(inputs in self.SCALINGS and targets in self.SCALINGS, "dataset: unhandled scaling type")
+
+        def mask(values, size):
+            if values is None:
+                return None
+            values = np.ascontiguousarray(values, dtype=np.uint8)
+            critical(values.size == size, "dataset: scaling mask of the wrong size")
+            return values.tobytes()
+
+        _lib.check(_lib.lib().nb200_dataset_scale(self.handle, self.SCALINGS[inputs], self.SCALINGS[targets],
+                                                  mask(enable_inputs, self.inputs), mask(enable_targets, self.targets)))
+        return self
+
+    def stats(self, which: str = "inputs"):
+        """scalar_stats_t of the inputs or the targets (after scale()): dict of arrays."""
+        size = self.inputs if which == "inputs" else self.targets
+        names = ("samples", "min", "max", "mean", "stdev", "div_range", "div_stdev")
+        arrays = [np.empty(size, dtype=np.float64) for _ in names]
+        _lib.check(_lib.lib().nb200_dataset_stats(self.handle, 0 if which == "inputs" else 1, *[_ptr(a) for a in arrays]))
+        return dict(zip(names, arrays))
+
+    def upscale(self, W, b):
+        """nano::upscale (src/dataset/stats.cpp:211-230): (W, b) fitted on the scaled data -> original units."""
+        W = np.array(W, dtype=np.float64).reshape(self.targets, self.inputs)
+        b = np.array(b, dtype=np.float64).reshape(self.targets)
+        _lib.check(_lib.lib().nb200_upscale(self.handle, _ptr(W), _ptr(b)))
+        return W, b
+
     def predict(self, W, b):
         """linear::predict (src/linear/util.cpp:6-21): outputs[N, T] = X W^T + b."""
         W = np.ascontiguousarray(W, dtype=np.float64).reshape(self.targets, self.inputs)

@@ -30,7 +30,9 @@ def lbfgs(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, history: i
     if isinstance(function, ShardedFunction):
         shard = function._shard
         local = shard.local
-        if function.world_size() > 1:
+        if function.world_size() > 1 and getattr(shard, "fused", False):
+            n_global = function._n_global  # the all-reduce happens inside the kernel (peer memory): no callback
+        elif function.world_size() > 1:
             import torch.distributed as dist
 
             n_global = function._n_global

@@ -91,6 +91,9 @@ def lib():
                                             _i64, ctypes.c_int, _dp]
         L.oracle_linear_finish.restype = ctypes.c_double
         L.oracle_linear_finish.argtypes = [_dp, _i64, _i64, _i64, ctypes.c_double, ctypes.c_double, _dp, _dp]
+        L.oracle_scalar_stats.argtypes = [_dp, _i64, _i64, ctypes.c_char_p, _dp]
+        L.oracle_scale.argtypes = [_dp, _i64, _i64, _dp, ctypes.c_int]
+        L.oracle_upscale.argtypes = [_dp, ctypes.c_int, _dp, ctypes.c_int, _i64, _i64, _dp, _dp]
         L.oracle_synth_samples.restype = _i64
         L.oracle_synth_samples.argtypes = [_i64, ctypes.c_double]
         L.oracle_synth_model.argtypes = [_i64, _i64, ctypes.c_uint64, _i64, ctypes.c_int, _dp, _dp, _dp, _dp]
@@ -224,6 +227,36 @@ def synth_vgrad(X, Y, bopt, loss, x, alpha1=0.0, alpha2=0.0, want_grad=True):
     gx = np.empty_like(x) if want_grad else None
     fx = lib().oracle_synth_vgrad(_ptr(X), _ptr(Y), bopt, N, D, SYNTH_LOSSES[loss], alpha1, alpha2, _ptr(x), _ptr(gx))
     return fx, gx
+
+
+SCALINGS = {"none": 0, "mean": 1, "minmax": 2, "standard": 3}
+STAT_NAMES = ("samples", "min", "max", "mean", "stdev", "div_range", "div_stdev")
+
+
+def scalar_stats(values, enable=None):
+    """scalar_stats_t over the columns of values[N, C] -> [7, C] array (rows: STAT_NAMES)."""
+    values = _f64(values)
+    N, C = values.shape
+    stats = np.empty((7, C), dtype=np.float64)
+    mask = None if enable is None else np.ascontiguousarray(enable, dtype=np.uint8).tobytes()
+    lib().oracle_scalar_stats(_ptr(values), N, C, mask, _ptr(stats))
+    return stats
+
+
+def scale(values, stats, scaling: str):
+    out = _f64(values).copy()
+    N, C = out.shape
+    lib().oracle_scale(_ptr(out), N, C, _ptr(_f64(stats, (7, C))), SCALINGS[scaling])
+    return out
+
+
+def upscale(istats, iscaling: str, tstats, tscaling: str, W, b):
+    W = _f64(W).copy()
+    b = _f64(b).copy()
+    T, D = W.shape
+    lib().oracle_upscale(_ptr(_f64(istats, (7, D))), SCALINGS[iscaling], _ptr(_f64(tstats, (7, T))), SCALINGS[tscaling],
+                         D, T, _ptr(W), _ptr(b))
+    return W, b
 
 
 def hardware_threads() -> int:

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <random>
 #include <thread>
 #include <vector>
@@ -667,6 +668,130 @@ double oracle_linear_finish(const double* reduced, const int64_t n_global, const
         v /= static_cast<double>(n_global);
     }
     return finish_linear(scaled.data(), D, T, l1, l2, x, gx);
+}
+
+void oracle_scalar_stats(const double* values, const int64_t N, const int64_t C, const unsigned char* enable,
+                         double* stats /* [7][C]: samples, min, max, mean, stdev, div_range, div_stdev */)
+{
+    // update + done of src/dataset/stats.cpp:81-137 (sequential over samples, finite values only)
+    const double epsilon = 1e-8; // epsilon2
+    double* samples = stats;
+    double* vmin    = stats + C;
+    double* vmax    = stats + 2 * C;
+    double* mean    = stats + 3 * C;
+    double* stdev   = stats + 4 * C;
+    double* drange  = stats + 5 * C;
+    double* dstdev  = stats + 6 * C;
+    for (int64_t c = 0; c < C; ++c)
+    {
+        samples[c] = 0.0;
+        vmin[c]    = std::numeric_limits<double>::max();
+        vmax[c]    = std::numeric_limits<double>::lowest();
+        mean[c]    = 0.0;
+        stdev[c]   = 0.0;
+    }
+    for (int64_t i = 0; i < N; ++i)
+    {
+        for (int64_t c = 0; c < C; ++c)
+        {
+            const double value = values[i * C + c];
+            if (std::isfinite(value))
+            {
+                samples[c] += 1.0;
+                mean[c] += value;
+                stdev[c] += value * value;
+                vmin[c] = std::min(vmin[c], value);
+                vmax[c] = std::max(vmax[c], value);
+            }
+        }
+    }
+    for (int64_t c = 0; c < C; ++c)
+    {
+        if (const double n = samples[c]; n > 1.0)
+        {
+            stdev[c]  = std::sqrt((stdev[c] - mean[c] * mean[c] / n) / (n - 1.0));
+            mean[c]   = mean[c] / n;
+            drange[c] = 1.0 / std::max(vmax[c] - vmin[c], epsilon);
+            dstdev[c] = 1.0 / std::max(stdev[c], epsilon);
+        }
+        else
+        {
+            if (n == 0.0)
+            {
+                vmin[c] = vmax[c] = mean[c] = 0.0;
+            }
+            stdev[c]  = 0.0;
+            drange[c] = 1.0;
+            dstdev[c] = 1.0;
+        }
+        if (enable != nullptr && enable[c] == 0)
+        {
+            vmin[c] = vmax[c] = mean[c] = stdev[c] = 0.0;
+            drange[c] = dstdev[c] = 1.0;
+        }
+    }
+}
+
+void oracle_scale(double* values, const int64_t N, const int64_t C, const double* stats, const int scaling)
+{
+    // scalar_stats_t::scale (src/dataset/stats.cpp:357-401) + nan2zero (:8-22)
+    const double* vmin   = stats + C;
+    const double* mean   = stats + 3 * C;
+    const double* drange = stats + 5 * C;
+    const double* dstdev = stats + 6 * C;
+    for (int64_t i = 0; i < N; ++i)
+    {
+        for (int64_t c = 0; c < C; ++c)
+        {
+            double& value = values[i * C + c];
+            switch (scaling)
+            {
+            case 1: value = (value - mean[c]) * drange[c]; break;
+            case 2: value = (value - vmin[c]) * drange[c]; break;
+            case 3: value = (value - mean[c]) * dstdev[c]; break;
+            default: break;
+            }
+            if (!std::isfinite(value))
+            {
+                value = 0.0;
+            }
+        }
+    }
+}
+
+void oracle_upscale(const double* istats, const int iscaling, const double* tstats, const int tscaling, const int64_t D,
+                    const int64_t T, double* W, double* b)
+{
+    // nano::upscale (src/dataset/stats.cpp:211-230) with make_scaling (:46-78)
+    const auto affine = [](const double* stats, const int64_t C, const int scaling, std::vector<double>& w,
+                           std::vector<double>& off)
+    {
+        w.assign(static_cast<size_t>(C), 1.0);
+        off.assign(static_cast<size_t>(C), 0.0);
+        for (int64_t c = 0; c < C; ++c)
+        {
+            const double vmin = stats[C + c], mean = stats[3 * C + c], drange = stats[5 * C + c],
+                         dstdev = stats[6 * C + c];
+            switch (scaling)
+            {
+            case 1: w[c] = drange; off[c] = -mean * drange; break;
+            case 2: w[c] = drange; off[c] = -vmin * drange; break;
+            case 3: w[c] = dstdev; off[c] = -mean * dstdev; break;
+            default: break;
+            }
+        }
+    };
+    std::vector<double> fw, fb, tw, tb;
+    affine(istats, D, iscaling, fw, fb);
+    affine(tstats, T, tscaling, tw, tb);
+    for (int64_t t = 0; t < T; ++t)
+    {
+        b[t] = (dot_plain(W + t * D, fb.data(), D) + b[t] - tb[t]) / tw[t];
+        for (int64_t j = 0; j < D; ++j)
+        {
+            W[t * D + j] = W[t * D + j] / tw[t] * fw[j];
+        }
+    }
 }
 
 int64_t oracle_synth_samples(const int64_t dims, const double sratio)

@@ -101,6 +101,14 @@ void oracle_synth_model(int64_t samples, int64_t inputs, uint64_t seed, int64_t 
 double oracle_synth_vgrad(const double* X, const double* Y, double bopt, int64_t N, int64_t D, int synth_loss,
                           double alpha1, double alpha2, const double* x, double* gx);
 
+/* flatten_iterator_t's view of the data: scalar_stats_t update/done (src/dataset/stats.cpp:81-137),
+ * scalar_stats_t::scale + nan2zero (:357-401, :8-22) and nano::upscale (:211-230).
+ * stats: [7][C] = samples, min, max, mean, stdev, div_range, div_stdev; scaling: 0 none, 1 mean, 2 minmax, 3 standard */
+void oracle_scalar_stats(const double* values, int64_t N, int64_t C, const unsigned char* enable, double* stats);
+void oracle_scale(double* values, int64_t N, int64_t C, const double* stats, int scaling);
+void oracle_upscale(const double* istats, int iscaling, const double* tstats, int tscaling, int64_t D, int64_t T,
+                    double* W, double* b);
+
 /* make_samples (src/function/mlearn/ridge.cpp:23-26) */
 int64_t oracle_synth_samples(int64_t dims, double sratio);
 

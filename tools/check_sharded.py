@@ -77,9 +77,10 @@ def main():
     row0, rows = shard_rows(N, world, rank)
     part = nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, rows, D, seed=11, row_offset=row0)
     sharded = ShardedFunction.from_local(nb.LinearFunction(part, nb.Loss("s-logistic"), 0.0, 1e-2), N)
+    lbfgs_fused = bool(args_fused and world > 1 and sharded.connect_peers())
     solved = lbfgs(sharded, np.zeros(D + 1), epsilon=1e-8)
     solve = {"status": solved["status"], "fx": solved["fx"], "fcalls": solved["fcalls"],
-             "gradient_test": solved["gradient_test"]}
+             "gradient_test": solved["gradient_test"], "fused_peers": lbfgs_fused}
     ok = ok and solved["status"] == "gradient_test"
     if rank == 0:
         whole = nb.LinearFunction(nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, N, D, seed=11), nb.Loss("s-logistic"),

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 -o timeout_method=thread -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/pytest_gpu.log | cut -c1-300
