@@ -53,44 +53,49 @@ using t1_kernel_t = void (*)(const t1_params);
 
 struct t1_variant
 {
-    int         V, KC, WS, NCW;
+    int         V, KC, WS, NCW, RW;
     t1_kernel_t grad;
     t1_kernel_t value;
 };
 
-#define NB200_T1_VARIANT(V, KC, WS, NCW)                                                                               \
+#define NB200_T1_VARIANT(V, KC, WS, NCW, RW)                                                                           \
     t1_variant                                                                                                         \
     {                                                                                                                  \
-        V, KC, WS, NCW, vgrad_t1_kernel<V, KC, WS, NCW, true>, vgrad_t1_kernel<V, KC, WS, NCW, false>                  \
+        V, KC, WS, NCW, RW, vgrad_t1_kernel<V, KC, WS, NCW, RW, true>, vgrad_t1_kernel<V, KC, WS, NCW, RW, false>      \
     }
 
 // Ordered so that the first variant whose column capacity 32*V*KC*WS covers D is the heuristic choice; the extra
 // entries at the end are alternative decompositions selectable with nb200_objective_set_variant.
+// Short rows are processed RW at a time (64 KiB stages hold 8 * RW rows of <= 8 KiB / RW).
 const t1_variant kT1Variants[] = {
-    /* 0*/ NB200_T1_VARIANT(2, 1, 1, 8),
-    /* 1*/ NB200_T1_VARIANT(2, 2, 1, 8),
-    /* 2*/ NB200_T1_VARIANT(2, 4, 1, 8),
-    /* 3*/ NB200_T1_VARIANT(2, 8, 1, 8),
-    /* 4*/ NB200_T1_VARIANT(2, 16, 1, 8),
-    /* 5*/ NB200_T1_VARIANT(2, 16, 2, 8),
-    /* 6*/ NB200_T1_VARIANT(2, 16, 4, 8),
-    /* 7*/ NB200_T1_VARIANT(2, 16, 8, 8),
-    /* 8*/ NB200_T1_VARIANT(1, 1, 1, 8),
-    /* 9*/ NB200_T1_VARIANT(1, 2, 1, 8),
-    /*10*/ NB200_T1_VARIANT(1, 4, 1, 8),
-    /*11*/ NB200_T1_VARIANT(1, 8, 1, 8),
-    /*12*/ NB200_T1_VARIANT(1, 16, 1, 8),
-    /*13*/ NB200_T1_VARIANT(1, 32, 1, 8),
-    /*14*/ NB200_T1_VARIANT(1, 32, 2, 8),
-    /*15*/ NB200_T1_VARIANT(1, 32, 4, 8),
-    /*16*/ NB200_T1_VARIANT(1, 32, 8, 8),
-    // alternatives (same coverage, different warp decomposition)
-    /*17*/ NB200_T1_VARIANT(2, 8, 2, 8),
-    /*18*/ NB200_T1_VARIANT(2, 8, 2, 16),
-    /*19*/ NB200_T1_VARIANT(2, 4, 4, 16),
-    /*20*/ NB200_T1_VARIANT(2, 16, 1, 12),
-    /*21*/ NB200_T1_VARIANT(2, 4, 2, 16),
-    /*22*/ NB200_T1_VARIANT(2, 2, 4, 16),
+    /* 0*/ NB200_T1_VARIANT(2, 1, 1, 8, 8),
+    /* 1*/ NB200_T1_VARIANT(2, 2, 1, 8, 8),
+    /* 2*/ NB200_T1_VARIANT(2, 4, 1, 8, 4),
+    /* 3*/ NB200_T1_VARIANT(2, 8, 1, 8, 2),
+    /* 4*/ NB200_T1_VARIANT(2, 16, 1, 8, 1),
+    /* 5*/ NB200_T1_VARIANT(2, 16, 2, 8, 1),
+    /* 6*/ NB200_T1_VARIANT(2, 16, 4, 8, 1),
+    /* 7*/ NB200_T1_VARIANT(2, 16, 8, 8, 1),
+    /* 8*/ NB200_T1_VARIANT(1, 1, 1, 8, 8),
+    /* 9*/ NB200_T1_VARIANT(1, 2, 1, 8, 8),
+    /*10*/ NB200_T1_VARIANT(1, 4, 1, 8, 8),
+    /*11*/ NB200_T1_VARIANT(1, 8, 1, 8, 4),
+    /*12*/ NB200_T1_VARIANT(1, 16, 1, 8, 2),
+    /*13*/ NB200_T1_VARIANT(1, 32, 1, 8, 1),
+    /*14*/ NB200_T1_VARIANT(1, 32, 2, 8, 1),
+    /*15*/ NB200_T1_VARIANT(1, 32, 4, 8, 1),
+    /*16*/ NB200_T1_VARIANT(1, 32, 8, 8, 1),
+    // alternatives (same coverage, different decomposition)
+    /*17*/ NB200_T1_VARIANT(2, 8, 2, 8, 1),
+    /*18*/ NB200_T1_VARIANT(2, 8, 2, 16, 1),
+    /*19*/ NB200_T1_VARIANT(2, 4, 4, 16, 1),
+    /*20*/ NB200_T1_VARIANT(2, 16, 1, 12, 1),
+    /*21*/ NB200_T1_VARIANT(2, 16, 1, 8, 2),
+    /*22*/ NB200_T1_VARIANT(2, 8, 1, 8, 1),
+    /*23*/ NB200_T1_VARIANT(2, 8, 1, 8, 4),
+    /*24*/ NB200_T1_VARIANT(2, 4, 1, 8, 1),
+    /*25*/ NB200_T1_VARIANT(2, 4, 1, 8, 8),
+    /*26*/ NB200_T1_VARIANT(2, 2, 1, 8, 1),
 };
 constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
 constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
@@ -1440,6 +1445,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
         const t1_variant& var = kT1Variants[obj->t1.variant];
         text = "t1 variant=" + std::to_string(obj->t1.variant) + " V=" + std::to_string(var.V) +
                " KC=" + std::to_string(var.KC) + " WS=" + std::to_string(var.WS) + " NCW=" + std::to_string(var.NCW) +
+               " RW=" + std::to_string(var.RW) +
                " grid=" + std::to_string(obj->t1.grid) + " rows_per_stage=" + std::to_string(obj->t1.rows_per_stage) +
                " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
                " smem=" + std::to_string(obj->t1.smem_bytes);

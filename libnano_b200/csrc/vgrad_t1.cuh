@@ -23,7 +23,8 @@
 //
 // Template knobs: V = doubles per lane per 32-lane chunk (2 => 128-bit loads, needs even D; 1 => any D),
 // KC = chunks per warp (a warp covers 32*V*KC columns), WS = warps cooperating on one row (row split in WS
-// column slices), NCW = consumer warps, GRAD = accumulate the gradient (false: value-only call).
+// column slices), NCW = consumer warps, RW = rows a warp handles per iteration (several short rows amortise the
+// shuffle / loss chain: lane r evaluates the loss of row r), GRAD = accumulate the gradient (false: value-only call).
 #pragma once
 
 #include "common.cuh"
@@ -101,11 +102,12 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const 
 // ---------------------------------------------------------------------------------------------------------------
 // consumer role: rows -> registers -> dot -> loss -> gradient slices; leaves this CTA's partial row in HBM
 // ---------------------------------------------------------------------------------------------------------------
-template <int V, int KC, int WS, int NCW, bool GRAD>
+template <int V, int KC, int WS, int NCW, int RW, bool GRAD>
 __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_bar, uint64_t* empty_bar,
                                              double* exchange, const double* w_s, unsigned char* stage_base,
                                              const int warp, const int lane)
 {
+    static_assert(RW >= 1 && RW <= 32 && (RW == 1 || WS == 1), "several rows per iteration need whole rows per warp");
     constexpr int NG  = NCW / WS;    // row groups
     constexpr int CPW = 32 * V * KC; // columns per warp
     const int     D   = p.D;
@@ -121,6 +123,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
     {
         g[k] = 0.0;
     }
+    // RW == 1: every lane carries the same sums; RW > 1: lane r carries the sums of the r-th row of each iteration
     double fsum = 0.0, gbsum = 0.0;
 
     const double bias = *p.bias;
@@ -151,61 +154,58 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             continue;
         }
 
-        for (int i = 0; i < count; ++i)
+        for (int i = 0; i < count; i += RW)
         {
-            const int     r   = first + i;
-            const double* row = xs + static_cast<int64_t>(r) * D;
+            const int nrows = min(RW, count - i); // rows of this iteration (RW of them except at the tail)
 
-            // row slice -> registers; partial dot with w
-            double x[V * KC];
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            // RW row slices -> registers; partial dots with w (w is read once per iteration)
+            double x[RW][V * KC];
+            double acc[RW][2];
+#pragma unroll
+            for (int r = 0; r < RW; ++r)
+            {
+                acc[r][0] = acc[r][1] = 0.0;
+            }
 #pragma unroll
             for (int k = 0; k < KC; ++k)
             {
-                const int col = cbase + (k * 32 + lane) * V;
+                const int  col = cbase + (k * 32 + lane) * V;
+                const bool in  = col < D;
                 if constexpr (V == 2)
                 {
-                    double2 xv = make_double2(0.0, 0.0), wv = make_double2(0.0, 0.0);
-                    if (col < D)
+                    const double2 wv = in ? *reinterpret_cast<const double2*>(w_s + col) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int r = 0; r < RW; ++r)
                     {
-                        xv = *reinterpret_cast<const double2*>(row + col);
-                        wv = *reinterpret_cast<const double2*>(w_s + col);
-                    }
-                    x[2 * k]     = xv.x;
-                    x[2 * k + 1] = xv.y;
-                    if (k & 1)
-                    {
-                        acc2 = fma(xv.x, wv.x, acc2);
-                        acc3 = fma(xv.y, wv.y, acc3);
-                    }
-                    else
-                    {
-                        acc0 = fma(xv.x, wv.x, acc0);
-                        acc1 = fma(xv.y, wv.y, acc1);
+                        double2 xv = make_double2(0.0, 0.0);
+                        if (in && r < nrows)
+                        {
+                            xv = *reinterpret_cast<const double2*>(xs + static_cast<int64_t>(first + i + r) * D + col);
+                        }
+                        x[r][2 * k]     = xv.x;
+                        x[r][2 * k + 1] = xv.y;
+                        acc[r][0]       = fma(xv.x, wv.x, acc[r][0]);
+                        acc[r][1]       = fma(xv.y, wv.y, acc[r][1]);
                     }
                 }
                 else
                 {
-                    double xv = 0.0, wv = 0.0;
-                    if (col < D)
+                    const double wv = in ? w_s[col] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < RW; ++r)
                     {
-                        xv = row[col];
-                        wv = w_s[col];
-                    }
-                    x[k] = xv;
-                    switch (k & 3)
-                    {
-                    case 0: acc0 = fma(xv, wv, acc0); break;
-                    case 1: acc1 = fma(xv, wv, acc1); break;
-                    case 2: acc2 = fma(xv, wv, acc2); break;
-                    default: acc3 = fma(xv, wv, acc3); break;
+                        const double xv = (in && r < nrows) ? xs[static_cast<int64_t>(first + i + r) * D + col] : 0.0;
+                        x[r][k]         = xv;
+                        acc[r][k & 1]   = fma(xv, wv, acc[r][k & 1]);
                     }
                 }
             }
-            const double y = ys[r];
+            // target of "my" row: lane r serves row r of this iteration when RW > 1, every lane row 0 otherwise
+            const int    my_row = (RW > 1) ? min(lane, nrows - 1) : 0;
+            const double y      = ys[first + i + my_row];
 
-            // the stage can be refilled as soon as the last row this warp owns is in registers
-            if (i == count - 1)
+            // the stage can be refilled as soon as the last rows this warp owns are in registers
+            if (i + RW >= count)
             {
                 __syncwarp();
                 if (lane == 0)
@@ -214,41 +214,69 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                 }
             }
 
-            double dot = warp_allreduce_sum((acc0 + acc1) + (acc2 + acc3));
+            double dot[RW];
+#pragma unroll
+            for (int r = 0; r < RW; ++r)
+            {
+                dot[r] = warp_allreduce_sum(acc[r][0] + acc[r][1]);
+            }
             if constexpr (WS > 1)
             {
                 // combine the column slices of the WS warps sharing this row, in slice order
                 double* slot = exchange + (group * 2 + exparity) * WS;
                 if (lane == 0)
                 {
-                    slot[slice] = dot;
+                    slot[slice] = dot[0];
                 }
                 named_bar_sync(1 + group, WS * 32);
-                dot = 0.0;
+                dot[0] = 0.0;
 #pragma unroll
                 for (int q = 0; q < WS; ++q)
                 {
-                    dot += slot[q];
+                    dot[0] += slot[q];
                 }
                 exparity ^= 1;
             }
 
-            // predict + loss + dL, identical on every lane (src/linear/util.cpp:19-20: product first, then + bias)
-            const double o = dot + bias;
+            // predict + loss + dL (src/linear/util.cpp:19-20: product first, then + bias). With several rows per
+            // iteration lane r evaluates row r, so the transcendental chain is paid once per RW rows.
+            double mine = dot[0];
+#pragma unroll
+            for (int r = 1; r < RW; ++r)
+            {
+                mine = (lane == r) ? dot[r] : mine;
+            }
+            const double o = mine + bias;
             double       term, dl;
             loss_term<GRAD>(p.loss, p.loss_param, y, o, term, dl);
-            fsum += loss_post(p.loss, term);
+            if (RW > 1 && lane >= nrows)
+            {
+                term = 0.0;
+                dl   = 0.0;
+            }
+            fsum += (RW > 1 && lane >= nrows) ? 0.0 : loss_post(p.loss, term);
 
             if constexpr (GRAD)
             {
                 gbsum += dl;
 #pragma unroll
-                for (int k = 0; k < V * KC; ++k)
+                for (int r = 0; r < RW; ++r)
                 {
-                    g[k] = fma(dl, x[k], g[k]);
+                    const double dlr = (RW > 1) ? __shfl_sync(0xffffffffu, dl, r) : dl;
+#pragma unroll
+                    for (int k = 0; k < V * KC; ++k)
+                    {
+                        g[k] = fma(dlr, x[r][k], g[k]);
+                    }
                 }
             }
         }
+    }
+    if constexpr (RW > 1)
+    {
+        // lanes 0..RW-1 carried the per-row sums: fold them (lane order) so that every lane holds the totals
+        fsum  = warp_allreduce_sum(fsum);
+        gbsum = warp_allreduce_sum(gbsum);
     }
 
     // fixed-order reduction of the row groups inside the CTA, through the (now idle) stages
@@ -516,7 +544,7 @@ struct t1_consumer_regs
     static_assert(kLaunchRegs <= 255 && value >= kLaunchRegs, "register hand-over must not shrink the consumers");
 };
 
-template <int V, int KC, int WS, int NCW, bool GRAD>
+template <int V, int KC, int WS, int NCW, int RW, bool GRAD>
 __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_kernel(const t1_params p)
 {
     static_assert(V == 1 || V == 2, "V is 1 (64-bit loads) or 2 (128-bit loads)");
@@ -583,7 +611,7 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
     {
         // ===== consumer warpgroups =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(t1_consumer_regs<NCW>::value));
-        consume_rows<V, KC, WS, NCW, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
+        consume_rows<V, KC, WS, NCW, RW, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
     }
 
     fold_partials<NCW + kT1ProducerWarps, GRAD>(p, w_s, scratch, warp, lane);

@@ -58,7 +58,7 @@ def test_register_hand_over_matches_the_allocation(library):
     # the fused kernel re-distributes registers between its producer and consumer warpgroups (setmaxnreg); asking
     # for more than the CTA's pool would dead-lock, so pin the per-thread launch allocation ptxas chose
     out = subprocess.run(["cuobjdump", "-res-usage", library._name], capture_output=True, text=True).stdout
-    found = re.findall(r"vgrad_t1_kernelILi\d+ELi\d+ELi\d+ELi(\d+)ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
+    found = re.findall(r"vgrad_t1_kernelILi\d+ELi\d+ELi\d+ELi(\d+)ELi\d+ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
     assert len(found) >= 40
     for ncw, regs in found:
         threads = (int(ncw) + 4) * 32
