@@ -348,6 +348,18 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
             {
                 ok = plan_t1(v, N, D, data->sm_count, data->smem_optin, plan);
             }
+            // measured (profiles/r01_sweep_rw.txt): for 256 < D <= 512 two rows per iteration pay off only when the
+            // loss has a transcendental chain to amortise; the cheap losses run 5-8 % faster one row at a time
+            const bool cheap_loss = obj->loss == LOSS_MSE || obj->loss == LOSS_MAE || obj->loss == LOSS_HINGE ||
+                                    obj->loss == LOSS_SQUARED_HINGE || obj->loss == LOSS_PINBALL;
+            if (ok && plan.variant == 3 && cheap_loss)
+            {
+                t1_plan alternative;
+                if (plan_t1(22, N, D, data->sm_count, data->smem_optin, alternative))
+                {
+                    plan = alternative;
+                }
+            }
         }
         if (ok)
         {

@@ -27,6 +27,8 @@
 // shuffle / loss chain: lane r evaluates the loss of row r), GRAD = accumulate the gradient (false: value-only call).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "loss.cuh"
 
@@ -154,9 +156,10 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             continue;
         }
 
-        for (int i = 0; i < count; i += RW)
+        // one iteration = RW rows of this warp; FULL: all RW rows exist (no per-row predicates in the hot path)
+        const auto iteration = [&](const int i, const int nrows, auto full_tag)
         {
-            const int nrows = min(RW, count - i); // rows of this iteration (RW of them except at the tail)
+            constexpr bool FULL = decltype(full_tag)::value;
 
             // RW row slices -> registers; partial dots with w (w is read once per iteration)
             double x[RW][V * KC];
@@ -166,6 +169,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             {
                 acc[r][0] = acc[r][1] = 0.0;
             }
+            const double* rows0 = xs + static_cast<int64_t>(first + i) * D;
 #pragma unroll
             for (int k = 0; k < KC; ++k)
             {
@@ -178,9 +182,9 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                     for (int r = 0; r < RW; ++r)
                     {
                         double2 xv = make_double2(0.0, 0.0);
-                        if (in && r < nrows)
+                        if (in && (FULL || r < nrows))
                         {
-                            xv = *reinterpret_cast<const double2*>(xs + static_cast<int64_t>(first + i + r) * D + col);
+                            xv = *reinterpret_cast<const double2*>(rows0 + static_cast<int64_t>(r) * D + col);
                         }
                         x[r][2 * k]     = xv.x;
                         x[r][2 * k + 1] = xv.y;
@@ -194,7 +198,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
 #pragma unroll
                     for (int r = 0; r < RW; ++r)
                     {
-                        const double xv = (in && r < nrows) ? xs[static_cast<int64_t>(first + i + r) * D + col] : 0.0;
+                        const double xv = (in && (FULL || r < nrows)) ? rows0[static_cast<int64_t>(r) * D + col] : 0.0;
                         x[r][k]         = xv;
                         acc[r][k & 1]   = fma(xv, wv, acc[r][k & 1]);
                     }
@@ -249,15 +253,12 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             const double o = mine + bias;
             double       term, dl;
             loss_term<GRAD>(p.loss, p.loss_param, y, o, term, dl);
-            if (RW > 1 && lane >= nrows)
-            {
-                term = 0.0;
-                dl   = 0.0;
-            }
-            fsum += (RW > 1 && lane >= nrows) ? 0.0 : loss_post(p.loss, term);
+            const bool counted = (RW == 1) || lane < nrows;
+            fsum += counted ? loss_post(p.loss, term) : 0.0;
 
             if constexpr (GRAD)
             {
+                dl = counted ? dl : 0.0;
                 gbsum += dl;
 #pragma unroll
                 for (int r = 0; r < RW; ++r)
@@ -270,6 +271,16 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                     }
                 }
             }
+        };
+
+        int i = 0;
+        for (; i + RW <= count; i += RW)
+        {
+            iteration(i, RW, std::true_type{});
+        }
+        if (i < count)
+        {
+            iteration(i, count - i, std::false_type{});
         }
     }
     if constexpr (RW > 1)
