@@ -19,6 +19,7 @@
 #include "synth.cuh"
 #include "vgrad_gen.cuh"
 #include "vgrad_mt.cuh"
+#include "batch.cuh"
 #include "vgrad_t1.cuh"
 
 using namespace nb200;
@@ -121,6 +122,85 @@ const mt_variant kMtVariants[] = {NB200_MT_VARIANT(1), NB200_MT_VARIANT(2),  NB2
                                   NB200_MT_VARIANT(4), NB200_MT_VARIANT(6),  NB200_MT_VARIANT(8),
                                   NB200_MT_VARIANT(10), NB200_MT_VARIANT(13), NB200_MT_VARIANT(16)};
 constexpr int    kNumMtVariants = static_cast<int>(sizeof(kMtVariants) / sizeof(kMtVariants[0]));
+
+// launch geometry of the tensor-pipe kernels for an (N, D, T) problem
+struct mt_geometry
+{
+    int variant{0};
+    int fwd_grid{0}, fwd_stages{0}, fwd_smem{0};
+    int splits{0}, bwd_grid{0}, bwd_stages{0}, bwd_smem{0}, t_ld{0};
+};
+
+// T in [2, 128] even (16-byte row copies of dL), D a multiple of 128; false when the shape is not covered
+bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin,
+             mt_geometry& geo)
+{
+    if (!(T >= 2 && T <= 128 && T % 2 == 0 && D % kMtBwdCols == 0 && D > 0 && N > 0))
+    {
+        return false;
+    }
+    int v = 0;
+    while (v < kNumMtVariants && kMtVariants[v].NT8 * 8 < T)
+    {
+        ++v;
+    }
+    const int64_t TP = kMtVariants[v].NT8 * 8;
+    // forward: header (barriers + fold area [8][1 + 2 TP] + the [128][TP + 2] output tile + alignment slack)
+    const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + 2 * TP) + 8 * kMtBM * (TP + 2) + 512;
+    const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
+    const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - fwd_header) / fwd_stage);
+    // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
+    int64_t t_ld = T;
+    while (t_ld % 16 != 4)
+    {
+        t_ld += 2;
+    }
+    const int64_t bwd_stage  = (round_up(kMtBwdRows * t_ld, 16) + kMtBwdRows * kMtBwdLd) * 8;
+    const int64_t bwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - 256) / bwd_stage);
+    const int64_t ctiles     = D / kMtBwdCols;
+    const int64_t chunks     = (N + kMtBwdRows - 1) / kMtBwdRows;
+    const int64_t splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, sm_count / std::max<int64_t>(ctiles, 1)));
+    if (fwd_stages < 2 || bwd_stages < 2 || ctiles > sm_count)
+    {
+        return false;
+    }
+    geo.variant    = v;
+    geo.fwd_grid   = static_cast<int>(std::min<int64_t>((N + kMtBM - 1) / kMtBM, sm_count));
+    geo.fwd_stages = static_cast<int>(fwd_stages);
+    geo.fwd_smem   = static_cast<int>(fwd_header + fwd_stages * fwd_stage);
+    geo.splits     = static_cast<int>(splits);
+    geo.bwd_grid   = static_cast<int>(ctiles * splits);
+    geo.bwd_stages = static_cast<int>(bwd_stages);
+    geo.bwd_smem   = static_cast<int>(256 + bwd_stages * bwd_stage);
+    geo.t_ld       = static_cast<int>(t_ld);
+    return true;
+}
+
+// scratch of nb200_vgrad_batch (K single-target models in one pass), sized for the largest K seen so far
+struct batch_state
+{
+    int64_t     Kp{0}; // padded (even) model count the buffers are sized for
+    mt_geometry geo{};
+    double *    d_x{nullptr}, *d_W{nullptr}, *d_b{nullptr}, *d_l{nullptr}, *d_dL{nullptr};
+    double *    d_partials_fb{nullptr}, *d_partials_gw{nullptr}, *d_red_fb{nullptr}, *d_red_gw{nullptr};
+    double *    h_in{nullptr}, *h_out{nullptr}, *h_out_dev{nullptr};
+
+    void release()
+    {
+        cudaFree(d_x);
+        cudaFree(d_W);
+        cudaFree(d_b);
+        cudaFree(d_l);
+        cudaFree(d_dL);
+        cudaFree(d_partials_fb);
+        cudaFree(d_partials_gw);
+        cudaFree(d_red_fb);
+        cudaFree(d_red_gw);
+        cudaFreeHost(h_in);
+        cudaFreeHost(h_out);
+        *this = batch_state{};
+    }
+};
 
 constexpr int kTimingRing = 64; // event pairs kept in flight when pass timing is enabled
 
@@ -255,6 +335,8 @@ struct nb200_obj
     int*                h_peer_error{nullptr};             // mapped host flag raised by the kernel on a peer timeout
     int*                d_peer_error{nullptr};
 
+    batch_state batch; // nb200_vgrad_batch
+
     // state of a two-phase evaluation
     bool    partial_has_grad{false};
     const double* partial_x{nullptr};
@@ -295,6 +377,7 @@ void free_obj(nb200_obj* obj)
     }
     cudaFree(obj->peer_local);
     cudaFreeHost(obj->h_peer_error);
+    obj->batch.release();
     cudaFreeHost(obj->h_x);
     cudaFreeHost(obj->h_out);
     for (cudaEvent_t event : obj->ev0)
@@ -374,54 +457,30 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         }
     }
 
-    // many-target tensor-pipe path: T in [2, 128] even (16-byte row copies of dL), D a multiple of 128
+    // many-target tensor-pipe path
     obj->use_mt = false;
-    if (T >= 2 && T <= 128 && T % 2 == 0 && D % kMtBwdCols == 0 && !force_generic && forced_variant != -3)
+    mt_geometry geo;
+    if (!force_generic && forced_variant != -3 && plan_mt(N, D, T, data->sm_count, data->smem_optin, geo))
     {
-        int v = 0;
-        while (v < kNumMtVariants && kMtVariants[v].NT8 * 8 < T)
-        {
-            ++v;
-        }
-        const mt_variant& var = kMtVariants[v];
-        const int64_t     TP  = var.NT8 * 8;
-        // forward: header (barriers + fold area + alignment slack) + stages of (128 + TP) rows x 20 doubles
-        // forward: header (barriers + fold area + the [128][TP + 2] output tile + alignment slack)
-        const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + TP) + 8 * kMtBM * (TP + 2) + 512;
-        const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
-        const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (data->smem_optin - fwd_header) / fwd_stage);
-        // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
-        int64_t t_ld = T;
-        while (t_ld % 16 != 4)
-        {
-            t_ld += 2;
-        }
-        const int64_t bwd_stage  = (round_up(kMtBwdRows * t_ld, 16) + kMtBwdRows * kMtBwdLd) * 8;
-        const int64_t bwd_stages = std::min<int64_t>(kMtMaxStages, (data->smem_optin - 256) / bwd_stage);
-        const int64_t ctiles     = D / kMtBwdCols;
-        const int64_t chunks     = (N + kMtBwdRows - 1) / kMtBwdRows;
-        const int64_t splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, data->sm_count / ctiles));
-        if (fwd_stages >= 2 && bwd_stages >= 2 && ctiles <= data->sm_count)
-        {
-            obj->mt_variant    = v;
-            obj->mt_fwd_grid   = static_cast<int>(std::min<int64_t>((N + kMtBM - 1) / kMtBM, data->sm_count));
-            obj->mt_fwd_stages = static_cast<int>(fwd_stages);
-            obj->mt_fwd_smem   = static_cast<int>(fwd_header + fwd_stages * fwd_stage);
-            obj->mt_splits     = static_cast<int>(splits);
-            obj->mt_bwd_grid   = static_cast<int>(ctiles * splits);
-            obj->mt_bwd_stages = static_cast<int>(bwd_stages);
-            obj->mt_bwd_smem   = static_cast<int>(256 + bwd_stages * bwd_stage);
-            obj->mt_t_ld       = static_cast<int>(t_ld);
-            NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_fwd_smem));
-            NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_fwd_smem));
-            NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->mt_bwd_smem));
-            NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(obj->mt_fwd_grid) * (1 + T) * sizeof(double)));
-            NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(splits) * T * D * sizeof(double)));
-            NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
-            NB200_CUDA_TRY(cudaDeviceSynchronize());
-            obj->use_mt = true;
-            return NB200_OK;
-        }
+        const mt_variant& var = kMtVariants[geo.variant];
+        obj->mt_variant    = geo.variant;
+        obj->mt_fwd_grid   = geo.fwd_grid;
+        obj->mt_fwd_stages = geo.fwd_stages;
+        obj->mt_fwd_smem   = geo.fwd_smem;
+        obj->mt_splits     = geo.splits;
+        obj->mt_bwd_grid   = geo.bwd_grid;
+        obj->mt_bwd_stages = geo.bwd_stages;
+        obj->mt_bwd_smem   = geo.bwd_smem;
+        obj->mt_t_ld       = geo.t_ld;
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(geo.fwd_grid) * (1 + T) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(geo.splits) * T * D * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
+        NB200_CUDA_TRY(cudaDeviceSynchronize());
+        obj->use_mt = true;
+        return NB200_OK;
     }
 
     // generic path
@@ -673,6 +732,9 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         f.stages      = obj->mt_fwd_stages;
         f.loss        = obj->loss;
         f.loss_param  = obj->loss_param;
+        f.y_broadcast     = 0;
+        f.per_target_loss = 0;
+        f.fb_stride       = static_cast<int>(1 + T);
         (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;
@@ -1496,6 +1558,177 @@ int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const doubl
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user);
     return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
+}
+
+static int ensure_batch(nb200_obj* obj, const int64_t Kp)
+{
+    batch_state&      bs   = obj->batch;
+    const nb200_data* data = obj->data;
+    const int64_t     N = data->N, D = data->D, n = obj->n;
+    if (bs.Kp == Kp)
+    {
+        return NB200_OK;
+    }
+    bs.release();
+    mt_geometry geo;
+    if (!plan_mt(N, D, Kp, data->sm_count, data->smem_optin, geo))
+    {
+        return fail(NB200_ERR_UNSUPPORTED, "batch: this (D, K) is not covered by the tensor-pipe kernels");
+    }
+    const mt_variant& var = kMtVariants[geo.variant];
+    NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+    NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+    NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
+    const size_t K = static_cast<size_t>(Kp);
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_x, K * (n + 2) * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_W, K * D * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_b, K * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_l, 2 * K * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_dL, static_cast<size_t>(N) * K * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_partials_fb, static_cast<size_t>(geo.fwd_grid) * (1 + 2 * K) * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_partials_gw, static_cast<size_t>(geo.splits) * K * D * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_red_fb, (1 + 2 * K) * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_red_gw, K * D * sizeof(double)));
+    NB200_CUDA_TRY(cudaMallocHost(&bs.h_in, (K * (n + 2) + 2 * K) * sizeof(double)));
+    NB200_CUDA_TRY(cudaHostAlloc(&bs.h_out, K * (n + 1) * sizeof(double), cudaHostAllocMapped));
+    NB200_CUDA_TRY(cudaHostGetDevicePointer(&bs.h_out_dev, bs.h_out, 0));
+    NB200_CUDA_TRY(cudaDeviceSynchronize());
+    bs.Kp  = Kp;
+    bs.geo = geo;
+    return NB200_OK;
+}
+
+int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const int64_t n, const double* l1,
+                      const double* l2, double* gx, double* fx)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && l1 != nullptr && l2 != nullptr && fx != nullptr,
+                  "batch: null argument");
+    NB200_REQUIRE(K >= 1 && K <= 128, "batch: the number of models must be in [1, 128]");
+    NB200_REQUIRE(n == obj->n, "function: invalid input size, expecting (" + std::to_string(obj->n) + ",), got (" +
+                                   std::to_string(n) + ",) instead!");
+    NB200_REQUIRE(obj->data->T == 1, "batch: the models must be single-target");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    const nb200_data* data = obj->data;
+    const int64_t     N = data->N, D = data->D;
+    const int64_t     Kp = (K % 2 == 0) ? K : K + 1;
+
+    mt_geometry probe;
+    if (!plan_mt(N, D, Kp, data->sm_count, data->smem_optin, probe))
+    {
+        // shapes outside the tensor-pipe kernels: K passes of the single-model path (still the GPU, just not fused)
+        const double keep1 = obj->l1, keep2 = obj->l2;
+        int          status = NB200_OK;
+        for (int64_t k = 0; k < K && status == NB200_OK; ++k)
+        {
+            obj->l1 = l1[k];
+            obj->l2 = l2[k];
+            status  = nb200_vgrad(obj, x + k * n, n, gx != nullptr ? gx + k * n : nullptr, fx + k);
+        }
+        obj->l1 = keep1;
+        obj->l2 = keep2;
+        return status;
+    }
+
+    int status = ensure_batch(obj, Kp);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    batch_state&      bs   = obj->batch;
+    const mt_geometry geo  = bs.geo;
+    const mt_variant& var  = kMtVariants[geo.variant];
+    const bool        grad = gx != nullptr;
+    cudaStream_t      st   = obj->stream;
+
+    // upload the K parameter vectors and their regularisation factors
+    std::memcpy(bs.h_in, x, static_cast<size_t>(K * n) * sizeof(double));
+    double* h_l = bs.h_in + K * n;
+    for (int64_t k = 0; k < Kp; ++k)
+    {
+        h_l[k]      = l1[std::min(k, K - 1)];
+        h_l[Kp + k] = l2[std::min(k, K - 1)];
+    }
+    NB200_CUDA_TRY(cudaMemcpyAsync(bs.d_x, bs.h_in, static_cast<size_t>(K * n) * sizeof(double), cudaMemcpyHostToDevice, st));
+    NB200_CUDA_TRY(cudaMemcpyAsync(bs.d_l, h_l, static_cast<size_t>(2 * Kp) * sizeof(double), cudaMemcpyHostToDevice, st));
+    batch_pack_kernel<<<dim3(static_cast<unsigned>(std::min<int64_t>((D + 255) / 256, 64)), static_cast<unsigned>(Kp)),
+                        256, 0, st>>>(static_cast<int>(K), static_cast<int>(Kp), D, n, obj->flavour, bs.d_x,
+                                      obj->d_fixed_bias, bs.d_W, bs.d_b);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+
+    status = timing_begin(obj);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    mt_forward_params f{};
+    f.X               = data->X;
+    f.Y               = data->Y;
+    f.W               = bs.d_W;
+    f.b               = bs.d_b;
+    f.dL              = grad ? bs.d_dL : nullptr;
+    f.partials_fb     = bs.d_partials_fb;
+    f.N               = N;
+    f.D               = static_cast<int>(D);
+    f.T               = static_cast<int>(Kp);
+    f.stages          = geo.fwd_stages;
+    f.loss            = obj->loss;
+    f.loss_param      = obj->loss_param;
+    f.y_broadcast     = 1;
+    f.per_target_loss = 1;
+    f.fb_stride       = static_cast<int>(1 + 2 * Kp);
+    (grad ? var.grad : var.value)<<<geo.fwd_grid, kMtThreads, geo.fwd_smem, st>>>(f);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    if (grad)
+    {
+        mt_backward_params b{};
+        b.X           = data->X;
+        b.dL          = bs.d_dL;
+        b.partials_gw = bs.d_partials_gw;
+        b.N           = N;
+        b.D           = static_cast<int>(D);
+        b.T           = static_cast<int>(Kp);
+        b.t_ld        = geo.t_ld;
+        b.splits      = geo.splits;
+        b.stages      = geo.bwd_stages;
+        var.backward<<<geo.bwd_grid, kMtThreads, geo.bwd_smem, st>>>(b);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+    }
+    status = timing_end(obj);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    const int64_t cols_fb = 1 + 2 * Kp;
+    reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, st>>>(
+        bs.d_partials_fb, geo.fwd_grid, cols_fb, cols_fb, bs.d_red_fb);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    if (grad)
+    {
+        reduce_partials_kernel<<<static_cast<unsigned>((Kp * D + 127) / 128), 128, 0, st>>>(
+            bs.d_partials_gw, geo.splits, Kp * D, Kp * D, bs.d_red_gw);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+    }
+    batch_finish_kernel<<<static_cast<unsigned>(K), 256, 0, st>>>(static_cast<int>(Kp), D, n, N, obj->flavour, bs.d_red_fb,
+                                                                   bs.d_red_gw, bs.d_x, bs.d_l, bs.d_l + Kp, grad ? 1 : 0,
+                                                                   bs.h_out_dev);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+    NB200_CUDA_TRY(cudaStreamSynchronize(st));
+    collect_timing(obj);
+    for (int64_t k = 0; k < K; ++k)
+    {
+        if (grad)
+        {
+            std::memcpy(gx + k * n, bs.h_out + k * (n + 1), static_cast<size_t>(n) * sizeof(double));
+        }
+        fx[k] = bs.h_out[k * (n + 1) + n];
+    }
+    return NB200_OK;
 }
 
 int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const double* b, double* outputs)

@@ -45,6 +45,11 @@ struct mt_forward_params
     int           stages;
     int           loss;
     double        loss_param;
+    // batched evaluation of K single-target models that share X and Y: the K weight vectors play
+    // the role of the targets, every "target" is compared with the same y_i, the losses are kept apart per model
+    int           y_broadcast;     // 1: Y is [N, 1] and is used for every column
+    int           per_target_loss; // 1: partial row = [total | dL sums (T) | loss sums (T)]
+    int           fb_stride;       // doubles per row of partials_fb: 1 + T, or 1 + 2 T with per_target_loss
 };
 
 struct mt_backward_params
@@ -94,8 +99,9 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMtMaxStages;
     constexpr int TPs   = TP + 2; // row stride of the output tile: 16-byte fragment stores hit 8 distinct bank groups
-    double*   fold      = reinterpret_cast<double*>(smem + 256); // [kMtWarps][1 + TP] at the very end of the kernel
-    double*   otile     = fold + kMtWarps * (1 + TP) + 2;        // [kMtBM][TPs] outputs of the current tile
+    constexpr int kFold = 1 + 2 * TP; // per warp: [loss | dL sums (TP) | per-target loss sums (TP)]
+    double*   fold      = reinterpret_cast<double*>(smem + 256); // [kMtWarps][kFold] at the very end of the kernel
+    double*   otile     = fold + kMtWarps * kFold + 2;           // [kMtBM][TPs] outputs of the current tile
     otile               = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(otile) + 127) / 128 * 128);
     double*   stage0    = otile + kMtBM * TPs;
     stage0              = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(stage0) + 127) / 128 * 128);
@@ -162,10 +168,12 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMtConsumerRegs));
     constexpr int TL = (TP + 31) / 32; // targets per lane in the row-wise epilogue (target t = lane + 32 * k)
     double gbacc[TL];                  // column sums of dL owned by this lane
+    double lossacc[TL];                // per-target loss sums (batched single-target models)
 #pragma unroll
     for (int k = 0; k < TL; ++k)
     {
-        gbacc[k] = 0.0;
+        gbacc[k]   = 0.0;
+        lossacc[k] = 0.0;
     }
     double fsum = 0.0;
 
@@ -236,13 +244,13 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
         {
             const int64_t row  = row_first + r;
             double*       orow = orows + r * TPs;
-            const double* yrow = p.Y + row * T;
+            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
             double        y[TL];
 #pragma unroll
             for (int k = 0; k < TL; ++k)
             {
                 const int t = lane + 32 * k;
-                y[k]        = (t < T) ? yrow[t] : 0.0;
+                y[k]        = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
             }
 
             if (p.loss == LOSS_CLASSNLL)
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                         double term, gv;
                         loss_term<GRAD>(p.loss, p.loss_param, y[k], orow[t], term, gv);
                         sum += term;
+                        lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
                         if (GRAD)
                         {
                             p.dL[row * T + t] = gv;
@@ -319,34 +328,34 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     }
 
     // ----- fold the 8 consumer warps in warp order -----
-    double* mine = fold + warp * (1 + TP);
+    double* mine = fold + warp * kFold;
     if (lane == 0)
     {
         mine[0] = fsum; // identical on every lane
     }
-    if (GRAD)
-    {
 #pragma unroll
-        for (int k = 0; k < TL; ++k)
+    for (int k = 0; k < TL; ++k)
+    {
+        const int t = lane + 32 * k;
+        if (t < TP)
         {
-            const int t = lane + 32 * k;
-            if (t < TP)
-            {
-                mine[1 + t] = gbacc[k];
-            }
+            mine[1 + t]      = GRAD ? gbacc[k] : 0.0;
+            mine[1 + TP + t] = lossacc[k];
         }
     }
     named_bar_sync(1, kMtWarps * 32);
-    double* out = p.partials_fb + static_cast<int64_t>(blockIdx.x) * (1 + T);
-    for (int c = threadIdx.x; c < (GRAD ? 1 + T : 1); c += kMtWarps * 32)
+    double*   out   = p.partials_fb + static_cast<int64_t>(blockIdx.x) * p.fb_stride;
+    const int ncols = p.per_target_loss ? (1 + 2 * T) : (GRAD ? 1 + T : 1);
+    for (int c = threadIdx.x; c < ncols; c += kMtWarps * 32)
     {
-        double s = 0.0;
+        const int src = (c <= T) ? c : (1 + TP + (c - 1 - T)); // [loss | dL sums | per-target loss sums]
+        double    sum = 0.0;
 #pragma unroll
         for (int q = 0; q < kMtWarps; ++q)
         {
-            s += fold[q * (1 + TP) + c];
+            sum += fold[q * kFold + src];
         }
-        out[c] = s;
+        out[c] = sum;
     }
 }
 

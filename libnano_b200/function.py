@@ -258,6 +258,25 @@ class _DeviceFunction(Function):
         _lib.check(_lib.lib().nb200_vgrad(self.handle, _ptr(x), x.size, _ptr(gx), ctypes.byref(self._fx)))
         return self._fx.value
 
+    # -- many models in one pass over X ---------------------------------------------------------------
+    def vgrad_batch(self, xs, l1s, l2s, want_grad: bool = True):
+        """K single-target models sharing this objective's data and loss, differing in (x_k, l1_k, l2_k): returns
+        (fs[K], gs[K, n] or None). What the tuner's grid of regularisation values costs the reference K passes over X
+        (src/machine/tune.cpp:25-42) costs two here (one many-"target" problem on the FP64 tensor pipe)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        critical(xs.ndim == 2 and xs.shape[1] == self.size(), "function: invalid input size, expecting (K, ",
+                 self.size(), ")")
+        K = xs.shape[0]
+        l1s = np.ascontiguousarray(np.broadcast_to(np.asarray(l1s, dtype=np.float64), (K,)))
+        l2s = np.ascontiguousarray(np.broadcast_to(np.asarray(l2s, dtype=np.float64), (K,)))
+        gs = np.empty_like(xs) if want_grad else None
+        fs = np.empty(K, dtype=np.float64)
+        _lib.check(_lib.lib().nb200_vgrad_batch(self.handle, K, _ptr(xs), xs.shape[1], _ptr(l1s), _ptr(l2s), _ptr(gs),
+                                                _ptr(fs)))
+        self._fcalls += K
+        self._gcalls += K if want_grad else 0
+        return fs, gs
+
     # -- sample-sharded evaluation (one rank per GPU; see sharded.py) ------------------------------------------------
     def partial(self, x, want_grad: bool = True):
         """Phase 1: returns (device pointer, length) of the un-normalised [loss | gb | gW] sums."""
