@@ -145,8 +145,8 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         ++v;
     }
     const int64_t TP = kMtVariants[v].NT8 * 8;
-    // forward: header (barriers + fold area [8][1 + 2 TP] + the [128][TP + 2] output tile + alignment slack)
-    const int64_t fwd_header = 1024 + 8 * kMtWarps * (1 + 2 * TP) + 8 * kMtBM * (TP + 2) + 512;
+    // forward: header (barriers + the [128][TP + 2] output tile, which also hosts the final fold + alignment slack)
+    const int64_t fwd_header = 1024 + 8 * kMtBM * (TP + 2) + 512;
     const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
     const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - fwd_header) / fwd_stage);
     // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
@@ -1612,8 +1612,9 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     const int64_t     N = data->N, D = data->D;
     const int64_t     Kp = (K % 2 == 0) ? K : K + 1;
 
+    // fewer than 6 models: K single passes at ~6.4 TB/s beat the two tensor-pipe passes (measured cross-over K ~ 5)
     mt_geometry probe;
-    if (!plan_mt(N, D, Kp, data->sm_count, data->smem_optin, probe))
+    if (Kp < 6 || !plan_mt(N, D, Kp, data->sm_count, data->smem_optin, probe))
     {
         // shapes outside the tensor-pipe kernels: K passes of the single-model path (still the GPU, just not fused)
         const double keep1 = obj->l1, keep2 = obj->l2;

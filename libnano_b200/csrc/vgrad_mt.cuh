@@ -99,10 +99,11 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMtMaxStages;
     constexpr int TPs   = TP + 2; // row stride of the output tile: 16-byte fragment stores hit 8 distinct bank groups
-    constexpr int kFold = 1 + 2 * TP; // per warp: [loss | dL sums (TP) | per-target loss sums (TP)]
-    double*   fold      = reinterpret_cast<double*>(smem + 256); // [kMtWarps][kFold] at the very end of the kernel
-    double*   otile     = fold + kMtWarps * kFold + 2;           // [kMtBM][TPs] outputs of the current tile
+    constexpr int kFold = 16 * TPs; // distance between the warps' fold rows (each inside that warp's 16 tile rows)
+    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit 16 tile rows");
+    double*   otile     = reinterpret_cast<double*>(smem + 256); // [kMtBM][TPs] outputs of the current tile
     otile               = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(otile) + 127) / 128 * 128);
+    double*   fold      = otile; // after the last tile the output tile is dead: it hosts the per-warp fold rows
     double*   stage0    = otile + kMtBM * TPs;
     stage0              = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(stage0) + 127) / 128 * 128);
     constexpr int kStageDoubles = (kMtBM + TP) * kMtLd;
