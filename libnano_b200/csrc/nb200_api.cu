@@ -181,7 +181,7 @@ struct batch_state
 {
     int64_t     Kp{0}; // padded (even) model count the buffers are sized for
     mt_geometry geo{};
-    double *    d_x{nullptr}, *d_W{nullptr}, *d_b{nullptr}, *d_l{nullptr}, *d_dL{nullptr};
+    double *    d_x{nullptr}, *d_W{nullptr}, *d_Wp{nullptr}, *d_b{nullptr}, *d_l{nullptr}, *d_dL{nullptr};
     double *    d_partials_fb{nullptr}, *d_partials_gw{nullptr}, *d_red_fb{nullptr}, *d_red_gw{nullptr};
     double *    h_in{nullptr}, *h_out{nullptr}, *h_out_dev{nullptr};
 
@@ -189,6 +189,7 @@ struct batch_state
     {
         cudaFree(d_x);
         cudaFree(d_W);
+        cudaFree(d_Wp);
         cudaFree(d_b);
         cudaFree(d_l);
         cudaFree(d_dL);
@@ -305,6 +306,7 @@ struct nb200_obj
     double* d_partials{nullptr};   // T1: [grid, D + 2]; generic: forward [blocks, 1 + T]
     double* d_partials_gw{nullptr}; // generic: [splits, T*D]
     double* d_dL{nullptr};         // generic: [N, T]
+    double* d_Wp{nullptr};         // tensor-pipe forward: W packed per k-chunk [D / 16][T][20]
     unsigned long long* d_grid_counter{nullptr}; // arrival counter of the fused kernel's grid barrier
     unsigned long long  grid_epoch{0};           // launches issued on that counter under the current plan
     // pinned host staging; h_out is MAPPED: kernels write (g, f) straight into it through h_out_dev
@@ -367,6 +369,7 @@ void free_obj(nb200_obj* obj)
     cudaFree(obj->d_partials);
     cudaFree(obj->d_partials_gw);
     cudaFree(obj->d_dL);
+    cudaFree(obj->d_Wp);
     cudaFree(obj->d_grid_counter);
     for (int r = 0; r < kT1MaxPeers; ++r)
     {
@@ -408,7 +411,8 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     cudaFree(obj->d_partials);
     cudaFree(obj->d_partials_gw);
     cudaFree(obj->d_dL);
-    obj->d_partials = obj->d_partials_gw = obj->d_dL = nullptr;
+    cudaFree(obj->d_Wp);
+    obj->d_partials = obj->d_partials_gw = obj->d_dL = obj->d_Wp = nullptr;
     obj->use_t1 = false;
     NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter, 0, sizeof(unsigned long long)));
     obj->grid_epoch = 0;
@@ -478,6 +482,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(geo.fwd_grid) * (1 + T) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(geo.splits) * T * D * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_Wp, static_cast<size_t>(D / kMtBK) * T * kMtLd * sizeof(double)));
         NB200_CUDA_TRY(cudaDeviceSynchronize());
         obj->use_mt = true;
         return NB200_OK;
@@ -719,10 +724,14 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
     if (obj->use_mt)
     {
         const mt_variant& var = kMtVariants[obj->mt_variant];
+        mt_pack_weights_kernel<<<static_cast<unsigned>(std::min<int64_t>((T * D + 255) / 256, 2048)), 256, 0,
+                                 obj->stream>>>(W, static_cast<int>(T), static_cast<int>(D), obj->d_Wp);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
         mt_forward_params f{};
         f.X           = data->X;
         f.Y           = data->Y;
-        f.W           = W;
+        f.W           = obj->d_Wp;
         f.b           = bias;
         f.dL          = want_grad ? obj->d_dL : nullptr;
         f.partials_fb = obj->d_partials;
@@ -1582,6 +1591,7 @@ static int ensure_batch(nb200_obj* obj, const int64_t Kp)
     const size_t K = static_cast<size_t>(Kp);
     NB200_CUDA_TRY(cudaMalloc(&bs.d_x, K * (n + 2) * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_W, K * D * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_Wp, static_cast<size_t>(D / kMtBK) * K * kMtLd * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_b, K * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_l, 2 * K * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_dL, static_cast<size_t>(N) * K * sizeof(double)));
@@ -1657,6 +1667,11 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     NB200_CUDA_TRY(cudaGetLastError());
     obj->launches += 1;
 
+    mt_pack_weights_kernel<<<static_cast<unsigned>(std::min<int64_t>((Kp * D + 255) / 256, 2048)), 256, 0, st>>>(
+        bs.d_W, static_cast<int>(Kp), static_cast<int>(D), bs.d_Wp);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 1;
+
     status = timing_begin(obj);
     if (status != NB200_OK)
     {
@@ -1665,7 +1680,7 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     mt_forward_params f{};
     f.X               = data->X;
     f.Y               = data->Y;
-    f.W               = bs.d_W;
+    f.W               = bs.d_Wp;
     f.b               = bs.d_b;
     f.dL              = grad ? bs.d_dL : nullptr;
     f.partials_fb     = bs.d_partials_fb;

@@ -35,7 +35,7 @@ struct mt_forward_params
 {
     const double* X;  // [N, D]
     const double* Y;  // [N, T]
-    const double* W;  // [T, D] device
+    const double* W;  // packed by mt_pack_weights_kernel: [D / 16][T][20] (k-chunk major, padded rows)
     const double* b;  // [T] device
     double*       dL; // [N, T] (GRAD)
     double*       partials_fb; // [grid, 1 + T]
@@ -66,6 +66,23 @@ struct mt_backward_params
 };
 
 #ifdef __CUDACC__
+
+// W [T, D] -> Wp [D / kMtBK][T][kMtLd]: the W tile of one k-chunk becomes ONE contiguous block that already has the
+// padded shared-memory row stride, so the forward producer moves it with a single bulk copy per stage
+__global__ void __launch_bounds__(256) mt_pack_weights_kernel(const double* __restrict__ W, const int T, const int D,
+                                                              double* __restrict__ Wp)
+{
+    const int64_t total = static_cast<int64_t>(D / kMtBK) * T * kMtLd;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    {
+        const int     j  = static_cast<int>(i % kMtLd);
+        const int64_t r  = i / kMtLd;
+        const int     t  = static_cast<int>(r % T);
+        const int64_t kc = r / T;
+        Wp[i]            = (j < kMtBK) ? W[static_cast<int64_t>(t) * D + kc * kMtBK + j] : 0.0;
+    }
+}
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, const double a, const double b)
 {
@@ -117,7 +134,8 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     {
         for (int s = 0; s < p.stages; ++s)
         {
-            mbar_init(full_bar + s, kMtProducerWarps * 32); // every producer thread arrives when its chunks landed
+            // every producer thread arrives when its X chunks landed; one more arrival carries the W tile's bytes
+            mbar_init(full_bar + s, kMtProducerWarps * 32 + 1);
             mbar_init(empty_bar + s, kMtWarps);
         }
         mbar_fence_init();
@@ -135,6 +153,8 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMtProducerRegs));
         const int pt = threadIdx.x - kMtWarps * 32;
         constexpr int kChunks = kMtBK / 2; // 16-byte chunks per tile row
+        uint64_t      policy_w;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy_w));
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
         {
@@ -148,16 +168,17 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                 double*       xs   = stage0 + static_cast<int64_t>(s) * kStageDoubles;
                 double*       ws   = xs + kMtBM * kMtLd;
                 const double* xsrc = p.X + row0 * D + kc * kMtBK;
-                const double* wsrc = p.W + kc * kMtBK;
+                if (pt == 0)
+                {
+                    // the packed W tile of this k-chunk: one contiguous bulk copy (re-read by every CTA: keep in L2)
+                    const uint32_t bytes = static_cast<uint32_t>(T * kMtLd * 8);
+                    mbar_arrive_expect_tx(full_bar + s, bytes);
+                    bulk_copy_g2s(ws, p.W + static_cast<int64_t>(kc) * T * kMtLd, bytes, full_bar + s, policy_w);
+                }
                 for (int c = pt; c < rows * kChunks; c += kMtProducerWarps * 32)
                 {
                     const int r = c / kChunks, j = c % kChunks;
                     cp_async_16(xs + r * kMtLd + j * 2, xsrc + static_cast<int64_t>(r) * D + j * 2);
-                }
-                for (int c = pt; c < T * kChunks; c += kMtProducerWarps * 32)
-                {
-                    const int t = c / kChunks, j = c % kChunks;
-                    cp_async_16(ws + t * kMtLd + j * 2, wsrc + static_cast<int64_t>(t) * D + j * 2);
                 }
                 cp_async_arrive(full_bar + s);
             }

@@ -71,6 +71,7 @@ class Dataset:
         X = np.ascontiguousarray(X, dtype=np.float64)
         critical(X.ndim == 2, "dataset: inputs must be a (samples, features) matrix")
         N, D = X.shape
+        critical(N > 0 and D > 0, "dataset: sizes must be positive")
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         critical(Y.shape[0] == N if Y.ndim else False, "dataset: inputs and targets disagree on the sample count")
         Y = Y.reshape(N, -1)

@@ -402,3 +402,54 @@ def test_many_target_softmax_sample_of_config3(ctx, oracle):
     rng = np.random.default_rng(0)
     x = rng.uniform(-1, 1, function.size()) / np.sqrt(D)
     check_against_oracle(oracle, function, X, Y, "s-classnll", x, 0.0, 1e-2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# edge cases the reference tests: output scales up to e^20 (test/test_loss.cpp:102-148), degenerate / maximum shapes
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loss_id", ALL_LOSSES)
+def test_loss_at_large_output_scales(ctx, oracle, loss_id):
+    import libnano_b200 as nb
+
+    rng = np.random.default_rng(12)
+    loss = nb.Loss(loss_id)
+    T = 3
+    if is_classification(loss_id):
+        targets = -np.ones((30, T))
+        targets[np.arange(30), rng.integers(0, T, 30)] = 1.0
+    else:
+        targets = rng.uniform(-1, 1, (30, T))
+    for power in (6, 10, 20):
+        if power > 6 and loss_id in ("s-exponential", "m-exponential", "s-savage"):
+            continue  # the reference stops these at e^6 too (they overflow by design)
+        outputs = rng.uniform(-1, 1, (30, T)) * np.e ** power
+        v, v_ref = loss.value(ctx, targets, outputs), oracle.loss_value(loss_id, targets, outputs)
+        g, g_ref = loss.vgrad(ctx, targets, outputs), oracle.loss_vgrad(loss_id, targets, outputs)
+        assert np.array_equal(np.isfinite(v), np.isfinite(v_ref)) and np.array_equal(np.isfinite(g), np.isfinite(g_ref))
+        ok_v, ok_g = np.isfinite(v_ref), np.isfinite(g_ref)
+        assert np.all(np.abs(v[ok_v] - v_ref[ok_v]) <= PARITY * (1 + np.abs(v_ref[ok_v])))
+        assert np.all(np.abs(g[ok_g] - g_ref[ok_g]) <= PARITY * (1 + np.abs(g_ref[ok_g])))
+
+
+@pytest.mark.parametrize("N,D,T,loss_id", [(7, 8192, 1, "mse"), (3, 9000, 1, "s-logistic"), (40, 256, 128, "s-classnll"),
+                                           (40, 256, 130, "s-classnll"), (5, 3, 200, "mse"), (2, 1, 1, "mae")])
+def test_extreme_shapes(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + D + T, N, D, T, is_classification(loss_id))
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.1)
+    check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.1)
+
+
+def test_invalid_requests_fail_like_critical(ctx):
+    import libnano_b200 as nb
+
+    with pytest.raises(RuntimeError):
+        nb.Dataset.pin(ctx, np.zeros((0, 4)), np.zeros((0, 1)))  # empty dataset
+    with pytest.raises(RuntimeError):
+        nb.Dataset.pin(ctx, np.zeros((4, 3)), np.zeros((5, 1)))  # sample counts disagree
+    data = nb.Dataset.pin(ctx, np.ones((4, 3)), np.ones((4, 2)))
+    with pytest.raises(RuntimeError):
+        nb.SyntheticFunction(ctx, "mse", "ridge", 4, seed=20000)  # function::seed range (ridge.cpp:35)
+    with pytest.raises(RuntimeError):
+        nb.LinearFunction(data, nb.Loss("mse")).vgrad_batch(np.zeros((2, 8)), 0.0, 0.0)  # batch needs one target
+    with pytest.raises(RuntimeError):
+        nb.Loss("s-hinge").value(ctx, np.zeros((2, 2)), np.zeros((2, 3)))
