@@ -145,10 +145,14 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         ++v;
     }
     const int64_t TP = kMtVariants[v].NT8 * 8;
-    // forward: header (barriers + the [128][TP + 2] output tile, which also hosts the final fold + alignment slack)
-    const int64_t fwd_header = 1024 + 8 * kMtBM * (TP + 2) + 512;
+    // forward: header (barriers + the [64][TP + 2] output tile, which also hosts the final fold + alignment slack)
+    const int64_t fwd_header = 1024 + 8 * (kMtBM / 2) * (TP + 2) + 512;
     const int64_t fwd_stage  = (kMtBM + TP) * kMtLd * 8;
-    const int64_t fwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - fwd_header) / fwd_stage);
+    int64_t       fwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - fwd_header) / fwd_stage);
+    if (const int forced = env_int("NB200_MT_STAGES", 0); forced >= 2)
+    {
+        fwd_stages = std::min<int64_t>(fwd_stages, forced); // tuning knob
+    }
     // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
     int64_t t_ld = T;
     while (t_ld % 16 != 4)

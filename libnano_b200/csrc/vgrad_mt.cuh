@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMtMaxStages;
     constexpr int TPs   = TP + 2; // row stride of the output tile: 16-byte fragment stores hit 8 distinct bank groups
-    constexpr int kFold = 16 * TPs; // distance between the warps' fold rows (each inside that warp's 16 tile rows)
-    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit 16 tile rows");
+    constexpr int kFold = 8 * TPs; // distance between the warps' fold rows (each inside that warp's 8 tile rows)
+    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit 8 tile rows");
     double*   otile     = reinterpret_cast<double*>(smem + 256); // [kMtBM][TPs] outputs of the current tile
     otile               = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(otile) + 127) / 128 * 128);
     double*   fold      = otile; // after the last tile the output tile is dead: it hosts the per-warp fold rows
-    double*   stage0    = otile + kMtBM * TPs;
+    double*   stage0    = otile + (kMtBM / 2) * TPs; // 8 rows per warp at a time: the two m8 tiles take turns
     stage0              = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(stage0) + 127) / 128 * 128);
     constexpr int kStageDoubles = (kMtBM + TP) * kMtLd;
 
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
         // ----- epilogue: accumulator fragments (+ bias) -> this warp's 16 rows of the shared output tile, then a
         //       compact row-wise loop (lanes stride the targets: coalesced Y reads and dL writes, small code) -----
-        double* orows = otile + (warp * 16) * TPs;
+        double* orows = otile + (warp * 8) * TPs;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
         {
@@ -254,14 +254,13 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                 const int col = nt * 8 + tig * 2;
                 const double b0 = (col < T) ? p.b[col] : 0.0;
                 const double b1 = (col + 1 < T) ? p.b[col + 1] : 0.0;
-                *reinterpret_cast<double2*>(orows + (mt * 8 + g) * TPs + col) =
+                *reinterpret_cast<double2*>(orows + g * TPs + col) =
                     make_double2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
             }
-        }
         __syncwarp();
 
-        const int64_t row_first = tile * kMtBM + warp * 16;
-        const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(16), p.N - row_first)));
+        const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
+        const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
         for (int r = 0; r < row_count; ++r)
         {
             const int64_t row  = row_first + r;
@@ -346,7 +345,8 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                 fsum += loss_post(p.loss, warp_allreduce_sum(sum));
             }
         }
-        __syncwarp(); // the next tile's epilogue overwrites this warp's rows
+        __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
+        }
     }
 
     // ----- fold the 8 consumer warps in warp order -----
