@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libnb200.so")
+STAMP_PATH = LIB_PATH + ".sha256"  # travels with the .so (git-ignored, not gpurun-ignored)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,11 +40,23 @@ def sources():
     return files
 
 
+def _fingerprint() -> str:
+    """Content hash of every source plus the flags: file times do not survive the snapshot to the GPU box."""
+    import hashlib
+
+    digest = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in sources():
+        digest.update(os.path.basename(path).encode())
+        with open(path, "rb") as handle:
+            digest.update(handle.read())
+    return digest.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > built for s in sources())
+    with open(STAMP_PATH) as handle:
+        return handle.read().strip() != _fingerprint()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -58,6 +71,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(result.stderr)
     if result.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + result.stdout + result.stderr)
+    with open(STAMP_PATH, "w") as handle:
+        handle.write(_fingerprint() + "\n")
     return LIB_PATH
 
 

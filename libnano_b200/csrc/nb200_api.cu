@@ -131,6 +131,12 @@ struct mt_geometry
     int splits{0}, bwd_grid{0}, bwd_stages{0}, bwd_smem{0}, t_ld{0};
 };
 
+int env_int(const char* name, const int fallback)
+{
+    const char* value = std::getenv(name);
+    return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
+}
+
 // T in [2, 128] even (16-byte row copies of dL), D a multiple of 128; false when the shape is not covered
 bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin,
              mt_geometry& geo)
@@ -221,12 +227,6 @@ struct t1_plan
     int     smem_bytes{0};
     int64_t num_tiles{0};
 };
-
-int env_int(const char* name, const int fallback)
-{
-    const char* value = std::getenv(name);
-    return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
-}
 
 // Shared-memory geometry of variant `v` for a (N, D) problem; false if it cannot cover D or does not fit.
 bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, const int smem_optin, t1_plan& plan)

@@ -86,18 +86,39 @@ class DeviceShard:
         import torch.distributed as dist
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        if world < 2 or world > 8 or not self.local.describe().startswith("t1"):
+        if world < 2 or world > 8:
             return False
-        handle, grid = self.local.peer_export(world)
-        mine = self._torch.tensor(list(handle) + [grid % 256, grid // 256], dtype=self._torch.uint8, device="cuda")
+
+        def everyone(flag: bool) -> bool:
+            """Every rank takes part in every collective, whatever happened locally: no rank is left waiting."""
+            mine = self._torch.tensor([1 if flag else 0], dtype=self._torch.uint8, device="cuda")
+            votes = [self._torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(votes, mine, group=group)
+            return all(int(v.item()) == 1 for v in votes)
+
+        # (1) export this rank's mailbox (fails, e.g., when the objective is not on the single-target kernel)
+        handle, grid, ok = bytes(64), 0, True
+        try:
+            if not self.local.describe().startswith("t1"):
+                raise RuntimeError("not the single-target kernel")
+            handle, grid = self.local.peer_export(world)
+        except Exception:  # noqa: BLE001 - reported through the vote below
+            ok = False
+        mine = self._torch.tensor(list(handle) + [grid % 256, grid // 256, int(ok)], dtype=self._torch.uint8,
+                                  device="cuda")
         gathered = [self._torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine, group=group)
         blobs = [bytes(t.cpu().tolist()) for t in gathered]
-        critical(all(b[64:] == blobs[0][64:] for b in blobs), "peers: the ranks run different grids")
-        self.local.peer_connect(rank, world, b"".join(b[:64] for b in blobs))
-        dist.barrier(group=group)
-        self.fused = True
-        return True
+        if not all(b[66] == 1 for b in blobs) or not all(b[64:66] == blobs[0][64:66] for b in blobs):
+            return False  # some rank could not export, or the ranks run different grids: keep the NCCL path
+
+        # (2) map the peers' mailboxes (CUDA IPC); only if every rank succeeded is the fused path switched on
+        try:
+            self.local.peer_connect(rank, world, b"".join(b[:64] for b in blobs))
+        except Exception:  # noqa: BLE001
+            ok = False
+        self.fused = everyone(ok)
+        return self.fused
 
 
 class ShardedFunction(Function):
