@@ -50,6 +50,13 @@ def parse_args():
     parser.add_argument("--cpu-rows", type=int, default=1 << 17, help="rows of the bounded CPU sample")
     parser.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of cpu_baseline")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--settle-seconds", type=float, default=1.5,
+                        help="idle time before the warm-up of each timed region: both regions start from the same "
+                             "board state (streaming fp64 from HBM holds the board at its 1000 W power cap, so the "
+                             "second region would otherwise inherit the first one's throttled clocks)")
+    parser.add_argument("--sustained-seconds", type=float, default=0.0,
+                        help="also run the device-resident loop back to back for this long and report the steady "
+                             "state (second half) in a 'sustained' object")
     parser.add_argument("--variant", type=int, default=-1, help="fused-kernel variant (tuning), -1 = heuristic")
     parser.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                         help="N > 1: 'peer' = all-reduce fused into the kernel over NVLink peer memory, 'nccl' = "
@@ -295,6 +302,8 @@ def run_b200(args):
             dist.all_reduce(function._shard._view_for(ptr, length))
             local.finish_device(x_dev.data_ptr(), n_global, g_dev.data_ptr(), f_dev.data_ptr())
 
+    barrier()
+    time.sleep(args.settle_seconds)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -322,6 +331,8 @@ def run_b200(args):
     f_device = float(f_dev.item())
 
     # ---- (2) end-to-end loop: the public call with HOST buffers ---------------------------------------------------
+    barrier()
+    time.sleep(args.settle_seconds)
     for _ in range(max(args.warmup, 3)):
         function(x, gx)
     barrier()
@@ -333,6 +344,25 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(start2.elapsed_time(stop2))
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+
+    sustained = None
+    if args.sustained_seconds > 0:
+        # back-to-back evaluations for a fixed wall time; the second half is the steady state under the power cap
+        local.enable_timing(True)
+        local.pass_stats(reset=True)
+        batches = []
+        t_sustained = time.perf_counter()
+        while time.perf_counter() - t_sustained < args.sustained_seconds:
+            for _ in range(25):
+                step_device()
+            barrier()
+            local.sync()
+            total_ms, count = local.pass_stats(reset=True)
+            batches.append(total_ms / max(count, 1))
+        local.enable_timing(False)
+        steady_ms = max_over_ranks(float(np.mean(batches[len(batches) // 2:])))
+        sustained = {"seconds": args.sustained_seconds, "launches": 25 * len(batches), "kernel_ms_first": batches[0],
+                     "kernel_ms_steady": steady_ms}
 
     if not np.isfinite(f_host) or abs(f_host - f_device) > 1e-12 * (1 + abs(f_host)):
         raise SystemExit(f"bench.py: device-resident and host-buffer evaluations disagree: {f_device} vs {f_host}")
@@ -376,6 +406,13 @@ def run_b200(args):
         "clocks": clocks,
         "f": f_host,
     }
+    line["config"]["settle"] = (f"{args.settle_seconds} s idle before the warm-up of each timed region (device-resident "
+                                "and end-to-end), so both start from the same board state")
+    if sustained is not None:
+        sustained["achieved_gbs"] = bytes_alg / (sustained["kernel_ms_steady"] * 1e-3) / 1e9
+        sustained["frac"] = sustained["achieved_gbs"] / peak
+        sustained["value"] = float(n_global) * features / (sustained["kernel_ms_steady"] * 1e-3)
+        line["sustained"] = sustained
 
     if world == 1 and not args.no_cpu_baseline:
         cpu_rows = min(args.cpu_rows, rows)

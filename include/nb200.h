@@ -207,6 +207,11 @@ NB200_API int    nb200_objective_enable_timing(nb200_obj* obj, int enabled);
 NB200_API double nb200_objective_last_pass_ms(nb200_obj* obj);
 NB200_API int    nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count, int reset);
 
+/* Host-side wall clock of nb200_vgrad since the last reset, microseconds summed over `calls` calls: staging x
+ * (+ enqueueing its H2D copy), enqueueing the evaluation, waiting for the stream and handing (g, f) over. */
+NB200_API int nb200_objective_host_profile(nb200_obj* obj, double* stage_us, double* enqueue_us, double* wait_us,
+                                           int64_t* calls, int reset);
+
 /* Tuning knob for the fused T == 1 kernel: variant id (see DESIGN.md "kernel variants"), -1 = heuristic,
  * -2 = force the shape-generic two-kernel path. */
 NB200_API int nb200_objective_set_variant(nb200_obj* obj, int variant);

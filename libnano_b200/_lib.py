@@ -58,6 +58,8 @@ SIGNATURES = {
     "nb200_objective_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_last_pass_ms": (ctypes.c_double, [ctypes.c_void_p]),
     "nb200_objective_pass_stats": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(c_i64), ctypes.c_int]),
+    "nb200_objective_host_profile": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p,
+                                                    ctypes.POINTER(c_i64), ctypes.c_int]),
     "nb200_objective_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_describe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_i64]),
     "nb200_vgrad_batch": (ctypes.c_int, [ctypes.c_void_p, c_i64, c_double_p, c_i64, c_double_p, c_double_p, c_double_p,

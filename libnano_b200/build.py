@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "-cudart", "static",
+    "-split-compile", "0",  # the 50-odd kernel instantiations are optimised in parallel
 ]
 
 

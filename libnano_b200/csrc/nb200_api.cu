@@ -6,6 +6,7 @@
 #include "../../include/nb200.h"
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -347,6 +348,12 @@ struct nb200_obj
     bool    partial_has_grad{false};
     const double* partial_x{nullptr};
 
+    // how (g, f) reach the host: 0 = the kernel writes into the mapped pinned buffer, 1 = device buffer + one D2H copy
+    int     result_copy{0};
+    // host-side wall clock of the public call, microseconds: [stage x + H2D | enqueue | wait + hand-over]
+    double  host_us[3] = {0.0, 0.0, 0.0};
+    int64_t host_calls{0};
+
     // statistics
     int64_t     launches{0};
     bool        timing{false};
@@ -573,6 +580,7 @@ int make_objective(nb200_data* data, const int loss, const double loss_param, co
         NB200_CUDA_TRY(cudaMallocHost(&obj->h_x, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaHostAlloc(&obj->h_out, (n + 2) * sizeof(double), cudaHostAllocMapped));
         NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->h_out_dev, obj->h_out, 0));
+        obj->result_copy = env_int("NB200_RESULT_COPY", 0);
         if (flavour == NB200_FLAVOUR_SYNTH)
         {
             obj->fixed_bias.assign(fixed_bias, fixed_bias + data->T);
@@ -719,8 +727,18 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         // cooperative launch: the grid barrier of the fused tail needs every CTA resident (grid <= #SMs, 1 CTA/SM)
         void*       args[] = {&p};
         const void* kernel = reinterpret_cast<const void*>(want_grad ? var.grad : var.value);
-        NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32), args,
-                                                   static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
+        static const int plain_launch = env_int("NB200_PLAIN_LAUNCH", 0); // probe: grid <= #SMs is co-resident anyway
+        if (plain_launch != 0)
+        {
+            NB200_CUDA_TRY(cudaLaunchKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32), args,
+                                            static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
+        }
+        else
+        {
+            NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid),
+                                                       dim3((var.NCW + kT1ProducerWarps) * 32), args,
+                                                       static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
+        }
         obj->launches += 1;
         return timing_end(obj);
     }
@@ -848,10 +866,21 @@ int upload_x(nb200_obj* obj, const double* x, const int64_t n)
     return NB200_OK;
 }
 
-// the kernels wrote (g, f) into the mapped pinned buffer: wait for the stream, hand the values to the caller
+// where the kernels of a host-buffer call write (g, f): the mapped pinned buffer, or the device buffer + one copy
+double* result_base(nb200_obj* obj)
+{
+    return obj->result_copy != 0 ? obj->d_out : obj->h_out_dev;
+}
+
+// the kernels wrote (g, f): wait for the stream, hand the values to the caller
 int collect_result(nb200_obj* obj, double* gx, double* fx)
 {
     const size_t n = static_cast<size_t>(obj->n);
+    if (obj->result_copy != 0)
+    {
+        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out, obj->d_out, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost,
+                                       obj->stream));
+    }
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
     collect_timing(obj);
     if (gx != nullptr)
@@ -1265,17 +1294,44 @@ int nb200_vgrad(nb200_obj* obj, const double* x, const int64_t n, double* gx, do
 {
     NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    int status = upload_x(obj, x, n);
+    const auto t0     = std::chrono::steady_clock::now();
+    int        status = upload_x(obj, x, n);
+    const auto t1     = std::chrono::steady_clock::now();
     if (status == NB200_OK)
     {
-        status = enqueue_eval(obj, obj->d_x, gx != nullptr, true, obj->data->N,
-                              gx != nullptr ? obj->h_out_dev : nullptr, obj->h_out_dev + obj->n);
+        double* out = result_base(obj);
+        status      = enqueue_eval(obj, obj->d_x, gx != nullptr, true, obj->data->N, gx != nullptr ? out : nullptr,
+                                   out + obj->n);
     }
+    const auto t2 = std::chrono::steady_clock::now();
     if (status == NB200_OK)
     {
         status = collect_result(obj, gx, fx);
     }
+    const auto t3 = std::chrono::steady_clock::now();
+    obj->host_us[0] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+    obj->host_us[1] += std::chrono::duration<double, std::micro>(t2 - t1).count();
+    obj->host_us[2] += std::chrono::duration<double, std::micro>(t3 - t2).count();
+    obj->host_calls += 1;
     return status;
+}
+
+int nb200_objective_host_profile(nb200_obj* obj, double* stage_us, double* enqueue_us, double* wait_us,
+                                 int64_t* calls, const int reset)
+{
+    NB200_REQUIRE(obj != nullptr && stage_us != nullptr && enqueue_us != nullptr && wait_us != nullptr &&
+                      calls != nullptr,
+                  "objective: null argument");
+    *stage_us   = obj->host_us[0];
+    *enqueue_us = obj->host_us[1];
+    *wait_us    = obj->host_us[2];
+    *calls      = obj->host_calls;
+    if (reset != 0)
+    {
+        obj->host_us[0] = obj->host_us[1] = obj->host_us[2] = 0.0;
+        obj->host_calls = 0;
+    }
+    return NB200_OK;
 }
 
 int nb200_vgrad_device(nb200_obj* obj, const double* x_dev, const int64_t n, double* gx_dev, double* fx_dev)
@@ -1321,8 +1377,8 @@ int nb200_vgrad_finish(nb200_obj* obj, const int64_t n_global, double* gx, doubl
     NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
     NB200_REQUIRE(gx == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    int status = enqueue_finish(obj, obj->d_x, n_global, gx != nullptr ? obj->h_out_dev : nullptr,
-                                obj->h_out_dev + obj->n);
+    double* out    = result_base(obj);
+    int     status = enqueue_finish(obj, obj->d_x, n_global, gx != nullptr ? out : nullptr, out + obj->n);
     if (status == NB200_OK)
     {
         status = collect_result(obj, gx, fx);
@@ -1425,8 +1481,9 @@ int nb200_vgrad_sharded(nb200_obj* obj, const double* x, const int64_t n, const 
     }
     if (status == NB200_OK)
     {
-        status = enqueue_eval(obj, obj->d_x, gx != nullptr, true, n_global, gx != nullptr ? obj->h_out_dev : nullptr,
-                              obj->h_out_dev + obj->n, true);
+        double* out = result_base(obj);
+        status      = enqueue_eval(obj, obj->d_x, gx != nullptr, true, n_global, gx != nullptr ? out : nullptr,
+                                   out + obj->n, true);
     }
     if (status == NB200_OK)
     {

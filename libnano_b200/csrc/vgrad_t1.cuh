@@ -125,27 +125,37 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
     {
         g[k] = 0.0;
     }
-    // RW == 1: every lane carries the same sums; RW > 1: lane r carries the sums of the r-th row of each iteration
+    // lane r carries the loss / dL sums of the r-th row of each iteration (the other lanes stay at zero)
     double fsum = 0.0, gbsum = 0.0;
 
     const double bias = *p.bias;
     const int    rpg  = p.rows_per_group;
 
-    int it       = 0;
-    int exparity = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
+    int      stage_index = 0;
+    uint32_t phase       = 0;
+    int      exparity    = 0;
+    // EXACT: the warps' column slices tile the row exactly (D == WS * CPW), so no column predicate is needed
+    const bool    exact      = D == WS * CPW;
+    const int64_t full_tiles = p.N / rps; // tiles [0, full_tiles) hold rps rows; at most one partial tile follows
+    const int     first      = group * rpg;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
     {
-        const int      s     = it % p.stages;
-        const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
+        const int s = stage_index;
         mbar_wait(full_bar + s, phase);
 
         const unsigned char* stage = stage_base + static_cast<int64_t>(s) * p.stage_stride;
         const double*        xs    = reinterpret_cast<const double*>(stage);
         const double*        ys    = reinterpret_cast<const double*>(stage + p.y_offset);
 
-        const int rows  = static_cast<int>(min(rps, p.N - tile * rps));
-        const int first = group * rpg;
-        const int count = max(0, min(rpg, rows - first)); // rows of this stage owned by this warp group
+        int count = rpg; // rows of this stage owned by this warp group
+        if (tile >= full_tiles)
+        {
+            const int rows = static_cast<int>(p.N - tile * rps);
+            count          = max(0, min(rpg, rows - first));
+        }
+        const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
+        stage_index            = wrapped ? 0 : stage_index + 1;
+        phase ^= wrapped;
 
         if (count == 0)
         {
@@ -157,9 +167,10 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
         }
 
         // one iteration = RW rows of this warp; FULL: all RW rows exist (no per-row predicates in the hot path)
-        const auto iteration = [&](const int i, const int nrows, auto full_tag)
+        const auto iteration = [&](const int i, const int nrows, auto full_tag, auto exact_tag)
         {
-            constexpr bool FULL = decltype(full_tag)::value;
+            constexpr bool FULL  = decltype(full_tag)::value;
+            constexpr bool EXACT = decltype(exact_tag)::value;
 
             // RW row slices -> registers; partial dots with w (w is read once per iteration)
             double x[RW][V * KC];
@@ -174,7 +185,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             for (int k = 0; k < KC; ++k)
             {
                 const int  col = cbase + (k * 32 + lane) * V;
-                const bool in  = col < D;
+                const bool in  = EXACT || col < D;
                 if constexpr (V == 2)
                 {
                     const double2 wv = in ? *reinterpret_cast<const double2*>(w_s + col) : make_double2(0.0, 0.0);
@@ -204,7 +215,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                     }
                 }
             }
-            // target of "my" row: lane r serves row r of this iteration when RW > 1, every lane row 0 otherwise
+            // target of "my" row: lane r serves row r of this iteration
             const int    my_row = (RW > 1) ? min(lane, nrows - 1) : 0;
             const double y      = ys[first + i + my_row];
 
@@ -242,28 +253,31 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                 exparity ^= 1;
             }
 
-            // predict + loss + dL (src/linear/util.cpp:19-20: product first, then + bias). With several rows per
-            // iteration lane r evaluates row r, so the transcendental chain is paid once per RW rows.
+            // predict + loss + dL (src/linear/util.cpp:19-20: product first, then + bias). Lane r evaluates row r of
+            // the iteration and the other lanes sit the transcendental chain out (32 redundant fp64 evaluations per
+            // row were most of the kernel's arithmetic energy; the board runs at its power cap); dL is broadcast.
             double mine = dot[0];
 #pragma unroll
             for (int r = 1; r < RW; ++r)
             {
                 mine = (lane == r) ? dot[r] : mine;
             }
-            const double o = mine + bias;
-            double       term, dl;
-            loss_term<GRAD>(p.loss, p.loss_param, y, o, term, dl);
-            const bool counted = (RW == 1) || lane < nrows;
-            fsum += counted ? loss_post(p.loss, term) : 0.0;
+            double dl = 0.0;
+            if (lane < RW && (FULL || lane < nrows))
+            {
+                const double o = mine + bias;
+                double       term;
+                loss_term<GRAD>(p.loss, p.loss_param, y, o, term, dl);
+                fsum += loss_post(p.loss, term);
+                gbsum += dl;
+            }
 
             if constexpr (GRAD)
             {
-                dl = counted ? dl : 0.0;
-                gbsum += dl;
 #pragma unroll
                 for (int r = 0; r < RW; ++r)
                 {
-                    const double dlr = (RW > 1) ? __shfl_sync(0xffffffffu, dl, r) : dl;
+                    const double dlr = __shfl_sync(0xffffffffu, dl, r);
 #pragma unroll
                     for (int k = 0; k < V * KC; ++k)
                     {
@@ -274,13 +288,23 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
         };
 
         int i = 0;
-        for (; i + RW <= count; i += RW)
+        if (exact)
         {
-            iteration(i, RW, std::true_type{});
+            for (; i + RW <= count; i += RW)
+            {
+                iteration(i, RW, std::true_type{}, std::true_type{});
+            }
+        }
+        else
+        {
+            for (; i + RW <= count; i += RW)
+            {
+                iteration(i, RW, std::true_type{}, std::false_type{});
+            }
         }
         if (i < count)
         {
-            iteration(i, count - i, std::false_type{});
+            iteration(i, count - i, std::false_type{}, std::false_type{});
         }
     }
     if constexpr (RW > 1)
@@ -584,10 +608,6 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
         }
         mbar_fence_init();
     }
-    for (int j = threadIdx.x; j < D; j += blockDim.x)
-    {
-        w_s[j] = p.w[j];
-    }
     __syncthreads();
 
     if (warp >= NCW)
@@ -598,12 +618,11 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
         {
             const int64_t  rps    = p.rows_per_stage;
             const uint64_t policy = l2_policy_evict_first();
-            int            it     = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it)
+            int            s      = 0;
+            uint32_t       phase  = 1; // the first lap passes at once: no consumer has arrived yet
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
             {
-                const int      s     = it % p.stages;
-                const uint32_t phase = static_cast<uint32_t>((it / p.stages) & 1);
-                mbar_wait(empty_bar + s, phase ^ 1u); // passes at once on the first lap
+                mbar_wait(empty_bar + s, phase);
 
                 const int64_t  row0    = tile * rps;
                 const int64_t  rows    = min(rps, p.N - row0);
@@ -614,6 +633,11 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
                 mbar_arrive_expect_tx(full_bar + s, bytes_x + bytes_y);
                 bulk_copy_g2s(stage, p.X + row0 * D, bytes_x, full_bar + s, policy);
                 bulk_copy_g2s(stage + p.y_offset, p.Y + row0, bytes_y, full_bar + s, policy);
+                if (++s == p.stages)
+                {
+                    s = 0;
+                    phase ^= 1u;
+                }
             }
         }
         __syncwarp();
@@ -621,6 +645,12 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
     else
     {
         // ===== consumer warpgroups =====
+        // the producer is already streaming: the parameters reach shared memory while the first tiles are in flight
+        for (int j = threadIdx.x; j < D; j += NCW * 32)
+        {
+            w_s[j] = p.w[j];
+        }
+        named_bar_sync(15, NCW * 32);
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(t1_consumer_regs<NCW>::value));
         consume_rows<V, KC, WS, NCW, RW, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
     }

@@ -359,6 +359,13 @@ class _DeviceFunction(Function):
                                                          int(reset)))
         return total.value, count.value
 
+    def host_profile(self, reset: bool = False):
+        """Host-side wall clock of the host-buffer call since the last reset: (stage_us, enqueue_us, wait_us, calls)."""
+        a, b, c, calls = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _lib.check(_lib.lib().nb200_objective_host_profile(self.handle, ctypes.byref(a), ctypes.byref(b),
+                                                           ctypes.byref(c), ctypes.byref(calls), int(reset)))
+        return a.value, b.value, c.value, calls.value
+
     def set_variant(self, variant: int) -> None:
         _lib.check(_lib.lib().nb200_objective_set_variant(self.handle, variant))
 
