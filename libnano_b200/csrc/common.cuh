@@ -146,6 +146,42 @@ __device__ __forceinline__ double warp_allreduce_sum(double value)
     return value;
 }
 
+__host__ __device__ constexpr int log2_of(const int value)
+{
+    return value <= 1 ? 0 : 1 + log2_of(value / 2);
+}
+
+// Sum R per-lane values ACROSS the warp at once (R a power of two <= 32): recursive halving — at every step a lane
+// keeps one half of its values and ships the other half to its partner — takes R - 1 exchanges plus a plain
+// butterfly over the remaining log2(32 / R) offsets, against 5 * R exchanges for R separate butterflies. Returns
+// the total of row (lane >> (5 - log2 R)); every lane of that group holds the same bits (both partners of an
+// exchange add the same two numbers). values[] is clobbered.
+template <int R>
+__device__ __forceinline__ double warp_reduce_rows(double (&values)[R], const int lane)
+{
+    int offset = 16;
+#pragma unroll
+    for (int n = R; n > 1; n /= 2)
+    {
+        const bool upper = (lane & offset) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j)
+        {
+            const double keep = upper ? values[j + n / 2] : values[j];
+            const double send = upper ? values[j] : values[j + n / 2];
+            values[j]         = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+        }
+        offset >>= 1;
+    }
+    double total = values[0];
+#pragma unroll
+    for (; offset > 0; offset >>= 1)
+    {
+        total += __shfl_xor_sync(0xffffffffu, total, offset);
+    }
+    return total;
+}
+
 __device__ __forceinline__ double warp_allreduce_max(double value)
 {
 #pragma unroll

@@ -55,16 +55,18 @@ using t1_kernel_t = void (*)(const t1_params);
 
 struct t1_variant
 {
-    int         V, KC, WS, NCW, RW;
+    int         V, KC, WS, NCW, RW, ALT;
     t1_kernel_t grad;
     t1_kernel_t value;
 };
 
-#define NB200_T1_VARIANT(V, KC, WS, NCW, RW)                                                                           \
+#define NB200_T1_VARIANT_ALT(V, KC, WS, NCW, RW, ALT)                                                                  \
     t1_variant                                                                                                         \
     {                                                                                                                  \
-        V, KC, WS, NCW, RW, vgrad_t1_kernel<V, KC, WS, NCW, RW, true>, vgrad_t1_kernel<V, KC, WS, NCW, RW, false>      \
+        V, KC, WS, NCW, RW, ALT, vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, true>,                                       \
+            vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, false>                                                            \
     }
+#define NB200_T1_VARIANT(V, KC, WS, NCW, RW) NB200_T1_VARIANT_ALT(V, KC, WS, NCW, RW, 1)
 
 // Ordered so that the first variant whose column capacity 32*V*KC*WS covers D is the heuristic choice; the extra
 // entries at the end are alternative decompositions selectable with nb200_objective_set_variant.
@@ -98,6 +100,20 @@ const t1_variant kT1Variants[] = {
     /*24*/ NB200_T1_VARIANT(2, 4, 1, 8, 1),
     /*25*/ NB200_T1_VARIANT(2, 4, 1, 8, 8),
     /*26*/ NB200_T1_VARIANT(2, 2, 1, 8, 1),
+    // four consumer warps, twice the rows per warp and stage: 64 doubles of X per lane for every width, the loss
+    // chain and the reduction are paid once per RW rows
+    /*27*/ NB200_T1_VARIANT(2, 16, 1, 4, 2),
+    /*28*/ NB200_T1_VARIANT(2, 8, 1, 4, 4),
+    /*29*/ NB200_T1_VARIANT(2, 4, 1, 4, 8),
+    /*30*/ NB200_T1_VARIANT(2, 2, 1, 4, 16),
+    /*31*/ NB200_T1_VARIANT(2, 1, 1, 4, 32),
+    // eight consumer warps in two sets that alternate over the CTA's tiles: the rows per warp and stage of the
+    // four-warp family with two warps per scheduler to hide the loss / reduction chain
+    /*32*/ NB200_T1_VARIANT_ALT(2, 16, 1, 8, 2, 2),
+    /*33*/ NB200_T1_VARIANT_ALT(2, 8, 1, 8, 4, 2),
+    /*34*/ NB200_T1_VARIANT_ALT(2, 4, 1, 8, 8, 2),
+    /*35*/ NB200_T1_VARIANT_ALT(2, 2, 1, 8, 16, 2),
+    /*36*/ NB200_T1_VARIANT_ALT(2, 1, 1, 8, 32, 2),
 };
 constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
 constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
@@ -242,7 +258,8 @@ bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, 
     {
         return false;
     }
-    const int     NG       = var.NCW / var.WS;
+    const int     NG       = var.NCW / var.WS / var.ALT; // row groups that share one stage
+    const int     NG_fold  = var.NCW / var.WS;           // partial gradient rows folded through the stage area
     const int64_t w_bytes  = round_up(D * 8, 128);
     const int64_t avail    = static_cast<int64_t>(smem_optin) - kT1HeaderSize - w_bytes;
     const int64_t row_b    = D * 8;
@@ -250,12 +267,16 @@ bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, 
     const int     stages_x = env_int("NB200_STAGES", kT1MaxStages);
 
     int64_t rpg = std::max<int64_t>(1, target / (NG * row_b));
+    if (rpg > var.RW)
+    {
+        rpg = rpg / var.RW * var.RW; // whole iterations of RW rows
+    }
     if ((NG * rpg) % 2 != 0)
     {
         rpg += 1; // tiles must start on 16-byte boundaries for any D
     }
     // the epilogue folds [NG][WS*CPW] partial gradients through the stage area
-    const int64_t epilogue = (static_cast<int64_t>(NG) * capacity + 2 * NG) * 8;
+    const int64_t epilogue = (static_cast<int64_t>(NG_fold) * capacity + 2 * NG_fold) * 8;
     for (;;)
     {
         const int64_t rps      = NG * rpg;
@@ -442,21 +463,21 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         }
         else
         {
+            // measured on B200 (profiles/r01_sustained_*.jsonl): the board sits at its 1000 W power cap while it
+            // streams fp64 from HBM, so the variant with the fewest instructions per row wins the steady state —
+            // several rows per warp iteration (one reduction and one loss chain per RW rows), two alternating sets of
+            // four consumer warps for rows up to 4 KiB, four consumer warps for 8 KiB rows
+            static const int preferred[] = {36, 35, 34, 33, 27};
+            for (const int v : preferred)
+            {
+                if (!ok)
+                {
+                    ok = plan_t1(v, N, D, data->sm_count, data->smem_optin, plan);
+                }
+            }
             for (int v = 0; v < kNumT1Heuristic && !ok; ++v)
             {
                 ok = plan_t1(v, N, D, data->sm_count, data->smem_optin, plan);
-            }
-            // measured (profiles/r01_sweep_rw.txt): for 256 < D <= 512 two rows per iteration pay off only when the
-            // loss has a transcendental chain to amortise; the cheap losses run 5-8 % faster one row at a time
-            const bool cheap_loss = obj->loss == LOSS_MSE || obj->loss == LOSS_MAE || obj->loss == LOSS_HINGE ||
-                                    obj->loss == LOSS_SQUARED_HINGE || obj->loss == LOSS_PINBALL;
-            if (ok && plan.variant == 3 && cheap_loss)
-            {
-                t1_plan alternative;
-                if (plan_t1(22, N, D, data->sm_count, data->smem_optin, alternative))
-                {
-                    plan = alternative;
-                }
             }
         }
         if (ok)
@@ -1589,7 +1610,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
         const t1_variant& var = kT1Variants[obj->t1.variant];
         text = "t1 variant=" + std::to_string(obj->t1.variant) + " V=" + std::to_string(var.V) +
                " KC=" + std::to_string(var.KC) + " WS=" + std::to_string(var.WS) + " NCW=" + std::to_string(var.NCW) +
-               " RW=" + std::to_string(var.RW) +
+               " RW=" + std::to_string(var.RW) + " ALT=" + std::to_string(var.ALT) +
                " grid=" + std::to_string(obj->t1.grid) + " rows_per_stage=" + std::to_string(obj->t1.rows_per_stage) +
                " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
                " smem=" + std::to_string(obj->t1.smem_bytes);

@@ -104,19 +104,29 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, const 
 // ---------------------------------------------------------------------------------------------------------------
 // consumer role: rows -> registers -> dot -> loss -> gradient slices; leaves this CTA's partial row in HBM
 // ---------------------------------------------------------------------------------------------------------------
-template <int V, int KC, int WS, int NCW, int RW, bool GRAD>
+template <int V, int KC, int WS, int NCW, int RW, int ALT, bool GRAD>
 __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_bar, uint64_t* empty_bar,
                                              double* exchange, const double* w_s, unsigned char* stage_base,
                                              const int warp, const int lane)
 {
     static_assert(RW >= 1 && RW <= 32 && (RW == 1 || WS == 1), "several rows per iteration need whole rows per warp");
-    constexpr int NG  = NCW / WS;    // row groups
+    static_assert((RW & (RW - 1)) == 0, "rows per iteration must be a power of two");
+    static_assert(ALT >= 1 && NCW % (ALT * WS) == 0, "the alternating warp sets must hold whole row groups");
+    constexpr int NG  = NCW / WS;    // row groups of the CTA (all sets): one partial gradient row each in the fold
+    constexpr int SW  = NCW / ALT;   // consumer warps per set; set a serves the CTA's tiles a, a + ALT, a + 2 ALT, ...
     constexpr int CPW = 32 * V * KC; // columns per warp
+    // after warp_reduce_rows the total of row r sits in lanes [r << OWNER_SHIFT, (r + 1) << OWNER_SHIFT); the first
+    // lane of each group evaluates the loss of its row
+    constexpr int OWNER_SHIFT = 5 - log2_of(RW);
+    const int     my_row      = lane >> OWNER_SHIFT;
+    const bool    owner       = (lane & ((1 << OWNER_SHIFT) - 1)) == 0;
     const int     D   = p.D;
     const int64_t rps = p.rows_per_stage;
 
-    const int group = warp / WS;   // which rows of a stage
-    const int slice = warp % WS;   // which columns of a row
+    const int set   = warp / SW;        // which of the CTA's tiles
+    const int group = warp / WS;        // row group within the CTA (fold slot, named barrier)
+    const int sgrp  = (warp % SW) / WS; // row group within the set: which rows of a stage
+    const int slice = warp % WS;        // which columns of a row
     const int cbase = slice * CPW; // first column of this warp's slice
 
     double g[V * KC]; // per-lane slice of sum dL_i * x_i
@@ -131,17 +141,36 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
     const double bias = *p.bias;
     const int    rpg  = p.rows_per_group;
 
-    int      stage_index = 0;
+    int      stage_index = 0; // the CTA's it-th tile lands in stage it % stages
     uint32_t phase       = 0;
+    int      turn        = 0; // it % ALT: the set whose tile this is
     int      exparity    = 0;
     // EXACT: the warps' column slices tile the row exactly (D == WS * CPW), so no column predicate is needed
     const bool    exact      = D == WS * CPW;
     const int64_t full_tiles = p.N / rps; // tiles [0, full_tiles) hold rps rows; at most one partial tile follows
-    const int     first      = group * rpg;
+    const int     first      = sgrp * rpg;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
     {
+        // every warp observes EVERY fill of the ring in order and releases it, also the tiles of the other sets: a
+        // parity wait can tell only adjacent phases apart, so no warp may fall a whole lap behind the producer
         const int s = stage_index;
         mbar_wait(full_bar + s, phase);
+        const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
+        stage_index            = wrapped ? 0 : stage_index + 1;
+        phase ^= wrapped;
+        if constexpr (ALT > 1)
+        {
+            const bool mine = turn == set;
+            turn            = (turn + 1 == ALT) ? 0 : turn + 1;
+            if (!mine)
+            {
+                if (lane == 0)
+                {
+                    mbar_arrive(empty_bar + s);
+                }
+                continue;
+            }
+        }
 
         const unsigned char* stage = stage_base + static_cast<int64_t>(s) * p.stage_stride;
         const double*        xs    = reinterpret_cast<const double*>(stage);
@@ -153,10 +182,6 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             const int rows = static_cast<int>(p.N - tile * rps);
             count          = max(0, min(rpg, rows - first));
         }
-        const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
-        stage_index            = wrapped ? 0 : stage_index + 1;
-        phase ^= wrapped;
-
         if (count == 0)
         {
             if (lane == 0)
@@ -215,9 +240,8 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                     }
                 }
             }
-            // target of "my" row: lane r serves row r of this iteration
-            const int    my_row = (RW > 1) ? min(lane, nrows - 1) : 0;
-            const double y      = ys[first + i + my_row];
+            // target of "my" row: the lanes of group (lane >> OWNER_SHIFT) serve row (lane >> OWNER_SHIFT)
+            const double y = ys[first + i + min(my_row, nrows - 1)];
 
             // the stage can be refilled as soon as the last rows this warp owns are in registers
             if (i + RW >= count)
@@ -229,41 +253,38 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                 }
             }
 
-            double dot[RW];
+            // the RW partial dots are reduced together (recursive halving: RW - 1 exchanges instead of 5 * RW); the
+            // lanes of group (lane >> OWNER_SHIFT) end up with the total of that row
+            double part[RW];
 #pragma unroll
             for (int r = 0; r < RW; ++r)
             {
-                dot[r] = warp_allreduce_sum(acc[r][0] + acc[r][1]);
+                part[r] = acc[r][0] + acc[r][1];
             }
+            double mine = warp_reduce_rows<RW>(part, lane);
             if constexpr (WS > 1)
             {
                 // combine the column slices of the WS warps sharing this row, in slice order
                 double* slot = exchange + (group * 2 + exparity) * WS;
                 if (lane == 0)
                 {
-                    slot[slice] = dot[0];
+                    slot[slice] = mine;
                 }
                 named_bar_sync(1 + group, WS * 32);
-                dot[0] = 0.0;
+                mine = 0.0;
 #pragma unroll
                 for (int q = 0; q < WS; ++q)
                 {
-                    dot[0] += slot[q];
+                    mine += slot[q];
                 }
                 exparity ^= 1;
             }
 
-            // predict + loss + dL (src/linear/util.cpp:19-20: product first, then + bias). Lane r evaluates row r of
-            // the iteration and the other lanes sit the transcendental chain out (32 redundant fp64 evaluations per
-            // row were most of the kernel's arithmetic energy; the board runs at its power cap); dL is broadcast.
-            double mine = dot[0];
-#pragma unroll
-            for (int r = 1; r < RW; ++r)
-            {
-                mine = (lane == r) ? dot[r] : mine;
-            }
+            // predict + loss + dL (src/linear/util.cpp:19-20: product first, then + bias). ONE lane per row evaluates
+            // the loss and the other lanes sit the transcendental chain out (32 redundant fp64 evaluations per row
+            // were most of the kernel's arithmetic energy, and the board runs at its power cap); dL is broadcast.
             double dl = 0.0;
-            if (lane < RW && (FULL || lane < nrows))
+            if (owner && (FULL || my_row < nrows))
             {
                 const double o = mine + bias;
                 double       term;
@@ -277,7 +298,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
 #pragma unroll
                 for (int r = 0; r < RW; ++r)
                 {
-                    const double dlr = __shfl_sync(0xffffffffu, dl, r);
+                    const double dlr = __shfl_sync(0xffffffffu, dl, r << OWNER_SHIFT);
 #pragma unroll
                     for (int k = 0; k < V * KC; ++k)
                     {
@@ -309,7 +330,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
     }
     if constexpr (RW > 1)
     {
-        // lanes 0..RW-1 carried the per-row sums: fold them (lane order) so that every lane holds the totals
+        // the owner lanes carried the per-row sums: fold them (fixed order) so that every lane holds the totals
         fsum  = warp_allreduce_sum(fsum);
         gbsum = warp_allreduce_sum(gbsum);
     }
@@ -563,6 +584,8 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
 // other three idle until the tail). The producer warpgroup hands its registers to the consumers (setmaxnreg): the
 // 128-register row + gradient slices of the widest variant then fit without spilling.
 constexpr int kT1ProducerWarps = 4;
+// 40 / 232 is the split that works: 24 / 240 would need the producer warps to grow back for the tail fold, and a
+// setmaxnreg.inc of the producer warpgroup after a consumer .dec was observed to hang on B200 (round-1 notes)
 constexpr int kT1ProducerRegs  = 40;
 
 template <int NCW>
@@ -572,14 +595,18 @@ struct t1_consumer_regs
     // 168 / 128 / 96 registers for 8 / 12 / 16 consumer warps); the CTA's pool is that times the thread count, and
     // asking for more than the pool holds would block setmaxnreg.inc forever.
     static constexpr int kThreads    = (NCW + kT1ProducerWarps) * 32;
-    static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+    static constexpr int kRawRegs    = (65536 / kThreads) / 8 * 8;
+    static constexpr int kLaunchRegs = kRawRegs > 248 ? 248 : kRawRegs;
     static constexpr int kPool       = kThreads * kLaunchRegs;
     static constexpr int kBudget     = ((kPool - kT1ProducerWarps * 32 * kT1ProducerRegs) / (NCW * 32)) / 8 * 8;
     static constexpr int value       = kBudget > 232 ? 232 : kBudget;
-    static_assert(kLaunchRegs <= 255 && value >= kLaunchRegs, "register hand-over must not shrink the consumers");
+    // with few consumer warps every thread already owns more registers than setmaxnreg could hand over
+    static constexpr bool kHandOver  = kLaunchRegs < value;
+
+    static_assert(kLaunchRegs <= 255, "register budget out of range");
 };
 
-template <int V, int KC, int WS, int NCW, int RW, bool GRAD>
+template <int V, int KC, int WS, int NCW, int RW, int ALT, bool GRAD>
 __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_kernel(const t1_params p)
 {
     static_assert(V == 1 || V == 2, "V is 1 (64-bit loads) or 2 (128-bit loads)");
@@ -604,7 +631,7 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
         for (int s = 0; s < p.stages; ++s)
         {
             mbar_init(full_bar + s, 1);
-            mbar_init(empty_bar + s, NCW);
+            mbar_init(empty_bar + s, NCW); // every consumer warp releases every stage (its own tiles after loading)
         }
         mbar_fence_init();
     }
@@ -613,7 +640,10 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
     if (warp >= NCW)
     {
         // ===== producer warpgroup: one lane of its first warp feeds the ring =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT1ProducerRegs));
+        if constexpr (t1_consumer_regs<NCW>::kHandOver)
+        {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT1ProducerRegs));
+        }
         if (warp == NCW && lane == 0)
         {
             const int64_t  rps    = p.rows_per_stage;
@@ -651,8 +681,11 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
             w_s[j] = p.w[j];
         }
         named_bar_sync(15, NCW * 32);
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(t1_consumer_regs<NCW>::value));
-        consume_rows<V, KC, WS, NCW, RW, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
+        if constexpr (t1_consumer_regs<NCW>::kHandOver)
+        {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(t1_consumer_regs<NCW>::value));
+        }
+        consume_rows<V, KC, WS, NCW, RW, ALT, GRAD>(p, full_bar, empty_bar, exchange, w_s, stage_base, warp, lane);
     }
 
     fold_partials<NCW + kT1ProducerWarps, GRAD>(p, w_s, scratch, warp, lane);
