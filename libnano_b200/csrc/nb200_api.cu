@@ -34,6 +34,7 @@ struct nb200_ctx
     cudaStream_t stream{nullptr};
     int          sm_count{0};
     int          smem_optin{0};
+    int          l2_bytes{0};
 };
 
 struct nb200_data
@@ -42,6 +43,7 @@ struct nb200_data
     int              device{0};
     int              sm_count{0};
     int              smem_optin{0};
+    int              l2_bytes{0};
     double*          X{nullptr}; // [N, D] + 256 bytes of zeroed slack (bulk copies round tails up to 16 bytes)
     double*          Y{nullptr}; // [N, T] + slack
     int64_t          N{0}, D{0}, T{0};
@@ -718,6 +720,7 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.y_offset       = obj->t1.y_offset;
         p.loss           = obj->loss;
         p.loss_param     = obj->loss_param;
+        p.l2_resident    = (static_cast<int64_t>(N) * (D + 1) * 8 <= (static_cast<int64_t>(data->l2_bytes) * 3) / 4) ? 1 : 0;
         p.grid_counter   = obj->d_grid_counter;
         p.grid_target    = obj->grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
         p.reduced        = obj->d_reduced;
@@ -965,6 +968,7 @@ int nb200_init(const int device, nb200_ctx** out_ctx)
     ctx->device     = device;
     ctx->sm_count   = prop.multiProcessorCount;
     ctx->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    ctx->l2_bytes   = prop.l2CacheSize;
     const cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess)
     {
@@ -997,6 +1001,7 @@ static int alloc_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const
     data->device     = ctx->device;
     data->sm_count   = ctx->sm_count;
     data->smem_optin = ctx->smem_optin;
+    data->l2_bytes   = ctx->l2_bytes;
     data->N          = N;
     data->D          = D;
     data->T          = T;

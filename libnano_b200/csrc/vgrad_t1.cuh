@@ -55,6 +55,7 @@ struct t1_params
     int           y_offset;     // byte offset of the Y tile inside a stage (multiple of 128)
     int           loss;
     double        loss_param;
+    int           l2_resident; // 1: X + Y fit in L2 and are re-read by the next evaluation
 
     // fused tail: cross-CTA reduction after a grid-wide barrier, optionally followed by the final scaling
     unsigned long long* grid_counter; // monotonically increasing arrival counter (never reset between launches)
@@ -647,7 +648,8 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
         if (warp == NCW && lane == 0)
         {
             const int64_t  rps    = p.rows_per_stage;
-            const uint64_t policy = l2_policy_evict_first();
+            // X larger than L2 is streamed once per evaluation (evict first); a small dataset is kept for the next call
+            const uint64_t policy = p.l2_resident != 0 ? l2_policy_evict_last() : l2_policy_evict_first();
             int            s      = 0;
             uint32_t       phase  = 1; // the first lap passes at once: no consumer has arrived yet
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
