@@ -244,6 +244,26 @@ NB200_API int nb200_lbfgs_minimize(nb200_obj* obj, double* x, int64_t n, double 
                                    void* allreduce_user, double* fx, double* gradient_test, int64_t* stats,
                                    int* status);
 
+/* nano::solver_cgd_t::minimize (src/solver/cgd.cpp:86-143; ids cgd-hs, cgd-fr, cgd-pr (libnano's "cgd"), cgd-cd,
+ * cgd-ls, cgd-dy, cgd-n, cgd-dycd, cgd-dyhs, cgd-frpr = beta 0..9; tolerance (1e-4, 1e-1), lsearch0 = quadratic,
+ * lsearchk = cgdescent) on the same device-resident skeleton: x, g, the previous gradient and the direction stay in
+ * HBM, the beta formula, the update d = -g + beta d and the restart test (cgd.cpp:121-126) are one kernel.
+ * orthotest = solver::cgd::orthotest (default 0.1), eta = solver::cgdN::eta (default 0.01; beta 6 only).
+ * Other arguments, stats and status as nb200_lbfgs_minimize. */
+#define NB200_CGD_HS 0
+#define NB200_CGD_FR 1
+#define NB200_CGD_PR 2
+#define NB200_CGD_CD 3
+#define NB200_CGD_LS 4
+#define NB200_CGD_DY 5
+#define NB200_CGD_N 6
+#define NB200_CGD_DYCD 7
+#define NB200_CGD_DYHS 8
+#define NB200_CGD_FRPR 9
+NB200_API int nb200_cgd_minimize(nb200_obj* obj, double* x, int64_t n, int beta, double epsilon, int64_t max_evals,
+                                 double orthotest, double eta, int64_t n_global, nb200_allreduce_fn allreduce,
+                                 void* allreduce_user, double* fx, double* gradient_test, int64_t* stats, int* status);
+
 /* ---- building blocks exposed on their own (reference: linear::predict, loss_t::value / loss_t::vgrad) -------- */
 
 /* outputs[N,T] (host) = X * W^T + b over the pinned dataset; W[T,D], b[T] host. */

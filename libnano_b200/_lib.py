@@ -67,6 +67,9 @@ SIGNATURES = {
     "nb200_lbfgs_minimize": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.c_double, c_i64, c_i64, c_i64,
                                             ctypes.c_void_p, ctypes.c_void_p, c_double_p, c_double_p,
                                             ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int)]),
+    "nb200_cgd_minimize": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.c_int, ctypes.c_double, c_i64,
+                                          ctypes.c_double, ctypes.c_double, c_i64, ctypes.c_void_p, ctypes.c_void_p,
+                                          c_double_p, c_double_p, ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int)]),
     "nb200_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_double_p, c_double_p, c_double_p]),
     "nb200_loss_value": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p, c_i64,
                                         c_i64, c_double_p]),

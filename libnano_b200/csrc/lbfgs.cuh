@@ -188,6 +188,87 @@ __global__ void solver_negate_kernel(const int64_t n, const double* __restrict__
     }
 }
 
+// CGD direction (src/solver/cgd.cpp:104-127): d = -cg + beta * pd with one of the ten beta formulas of cgd.cpp:7-71,
+// restarted to -cg when it is not a descent direction or consecutive gradients are far from orthogonal. One CTA,
+// fixed-order sums; `d` holds the previous direction on entry and the new one on exit.
+enum cgd_beta : int
+{
+    CGD_HS = 0, CGD_FR = 1, CGD_PR = 2, CGD_CD = 3, CGD_LS = 4, CGD_DY = 5, CGD_N = 6, CGD_DYCD = 7, CGD_DYHS = 8,
+    CGD_FRPR = 9, CGD_COUNT = 10
+};
+
+__global__ void __launch_bounds__(kSolverThreads) cgd_direction_kernel(const int64_t n, const double* __restrict__ cg,
+                                                                       const double* __restrict__ pg, double* d,
+                                                                       const int kind, const double eta0,
+                                                                       const double orthotest)
+{
+    __shared__ double scratch[kSolverThreads / 32];
+    double cg_y = 0.0, pd_y = 0.0, y_y = 0.0, cg_cg = 0.0, pg_pg = 0.0, pd_pg = 0.0, pd_pd = 0.0, cg_pg = 0.0, pd_cg = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += kSolverThreads)
+    {
+        const double c = cg[i], p = pg[i], q = d[i], y = c - p;
+        cg_y  = fma(c, y, cg_y);
+        pd_y  = fma(q, y, pd_y);
+        y_y   = fma(y, y, y_y);
+        cg_cg = fma(c, c, cg_cg);
+        pg_pg = fma(p, p, pg_pg);
+        pd_pg = fma(q, p, pd_pg);
+        pd_pd = fma(q, q, pd_pd);
+        cg_pg = fma(c, p, cg_pg);
+        pd_cg = fma(q, c, pd_cg);
+    }
+    cg_y  = cta_sum(cg_y, scratch);
+    pd_y  = cta_sum(pd_y, scratch);
+    y_y   = cta_sum(y_y, scratch);
+    cg_cg = cta_sum(cg_cg, scratch);
+    pg_pg = cta_sum(pg_pg, scratch);
+    pd_pg = cta_sum(pd_pg, scratch);
+    pd_pd = cta_sum(pd_pd, scratch);
+    cg_pg = cta_sum(cg_pg, scratch);
+    pd_cg = cta_sum(pd_cg, scratch);
+
+    const double HS = cg_y / pd_y, FR = cg_cg / pg_pg, PR = cg_y / pg_pg, CD = -cg_cg / pd_pg, LS = -cg_y / pd_pg,
+                 DY = cg_cg / pd_y;
+    double beta;
+    switch (kind)
+    {
+    case CGD_HS: beta = fmax(HS, 0.0); break;
+    case CGD_FR: beta = FR; break;
+    case CGD_PR: beta = fmax(PR, 0.0); break;
+    case CGD_CD: beta = CD; break;
+    case CGD_LS: beta = fmax(LS, 0.0); break;
+    case CGD_DY: beta = DY; break;
+    case CGD_N:
+    {
+        // max(eta, div * (y - 2 pd |y|^2 div) . cg), the dot product expanded by linearity
+        const double div = 1.0 / pd_y;
+        const double eta = -1.0 / (sqrt(pd_pd) * fmin(eta0, sqrt(pg_pg)));
+        beta             = fmax(eta, div * (cg_y - 2.0 * y_y * div * pd_cg));
+        break;
+    }
+    case CGD_DYCD: beta = cg_cg / fmax(pd_y, -pd_pg); break;
+    case CGD_DYHS: beta = fmax(0.0, fmin(DY, HS)); break;
+    default: beta = (PR < -FR) ? -FR : ((fabs(PR) <= FR) ? PR : FR); break;
+    }
+
+    double dg = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += kSolverThreads)
+    {
+        const double c = cg[i];
+        const double v = fma(beta, d[i], -c);
+        d[i]           = v;
+        dg             = fma(c, v, dg);
+    }
+    dg = cta_sum(dg, scratch);
+    if (!(dg < 0.0) || fabs(cg_pg) >= orthotest * cg_cg)
+    {
+        for (int64_t i = threadIdx.x; i < n; i += kSolverThreads)
+        {
+            d[i] = -cg[i];
+        }
+    }
+}
+
 // s = x - x_prev, y = g - g_prev into one history slot (lbfgs.cpp:107-108)
 __global__ void lbfgs_history_kernel(const int64_t n, const double* __restrict__ x, const double* __restrict__ xp,
                                      const double* __restrict__ g, const double* __restrict__ gp,
@@ -231,15 +312,28 @@ inline double lsearch_secant(const lsearch_step_t& u, const lsearch_step_t& v)
     return (t < lo) ? lo : ((hi < t) ? hi : t); // std::clamp semantics (NaN falls through)
 }
 
+// The line-search solvers that share this skeleton: L-BFGS (lbfgs.cpp) and the CGD family (cgd.cpp) differ in how the
+// descent direction is built and in the curvature tolerance c2 of the line search (0.9 resp. 0.1).
+struct solver_method_t
+{
+    bool   cgd{false};
+    int    beta{CGD_PR};
+    double c2{0.9};
+    double orthotest{0.1}; // solver::cgd::orthotest
+    double eta{0.01};      // solver::cgdN::eta
+};
+
 class device_lbfgs_t
 {
 public:
-    device_lbfgs_t(nb200_obj* obj, const int64_t n_global, nb200_allreduce_fn allreduce, void* allreduce_user)
+    device_lbfgs_t(nb200_obj* obj, const int64_t n_global, nb200_allreduce_fn allreduce, void* allreduce_user,
+                   const solver_method_t method = solver_method_t{})
         : m_obj(obj)
         , m_n(obj->n)
         , m_n_global(n_global)
         , m_allreduce(allreduce)
         , m_allreduce_user(allreduce_user)
+        , m_method(method)
     {
     }
 
@@ -296,8 +390,21 @@ public:
             while (m_fcalls + m_gcalls < max_evals)
             {
                 // descent direction
-                lbfgs_two_loop_kernel<<<1, kSolverThreads, 0, stream>>>(m_n, m_g, m_S, m_Y, count, head, m_cap, m_q,
-                                                                        m_alphas, m_d);
+                if (!m_method.cgd)
+                {
+                    lbfgs_two_loop_kernel<<<1, kSolverThreads, 0, stream>>>(m_n, m_g, m_S, m_Y, count, head, m_cap,
+                                                                            m_q, m_alphas, m_d);
+                }
+                else if (iterations == 0)
+                {
+                    solver_negate_kernel<<<blocks(), 256, 0, stream>>>(m_n, m_g, m_d); // cgd.cpp:106-109
+                }
+                else
+                {
+                    // m_g0 / m_d still hold the previous gradient and direction (cgd.cpp:112-126, restart included)
+                    cgd_direction_kernel<<<1, kSolverThreads, 0, stream>>>(m_n, m_g, m_g0, m_d, m_method.beta,
+                                                                           m_method.eta, m_method.orthotest);
+                }
                 NB200_CUDA_TRY(cudaGetLastError());
                 m_obj->launches += 1;
                 rc = probe(c); // refresh c.dg for the new direction
@@ -305,7 +412,7 @@ public:
                 {
                     return rc;
                 }
-                const bool has_descent = c.dg < 0.0; // lbfgs.cpp:89-94
+                const bool has_descent = m_method.cgd || c.dg < 0.0; // lbfgs.cpp:89-94
                 if (!has_descent)
                 {
                     solver_negate_kernel<<<blocks(), 256, 0, stream>>>(m_n, m_g, m_d);
@@ -349,6 +456,10 @@ public:
                     break;
                 }
 
+                if (m_method.cgd)
+                {
+                    continue; // no curvature history: the next direction needs the previous gradient and direction only
+                }
                 if (has_descent) // lbfgs.cpp:105-120
                 {
                     int slot;
@@ -453,7 +564,8 @@ private:
     // lsearchk_t::get (src/lsearchk.cpp:36-75) + lsearchk_cgdescent_t::do_get (src/lsearchk/cgdescent.cpp)
     int line_search(const solver_point_t& s0, solver_point_t& c, double t, bool& ok_out, double& t_out)
     {
-        constexpr double c1 = 1e-4, c2 = 0.9;                       // lbfgs.cpp:10
+        constexpr double c1 = 1e-4;                                 // lbfgs.cpp:10, cgd.cpp:77
+        const double     c2 = m_method.c2;
         constexpr double theta = 0.5, gamma = 0.66, ro = 5.0;       // cgdescent.cpp:83-91
         constexpr int    max_iterations = 128;                      // lsearchk.cpp:15
         constexpr double epsilon0 = 1e-15, epsilon1 = 1e-10;        // numeric.h:92-105
@@ -658,6 +770,7 @@ private:
     int64_t            m_n_global;
     nb200_allreduce_fn m_allreduce;
     void*              m_allreduce_user;
+    solver_method_t    m_method;
     int                m_cap{50};
     int64_t            m_fcalls{0}, m_gcalls{0};
     double*            m_block{nullptr};

@@ -1656,6 +1656,33 @@ int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const doubl
     return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
 }
 
+int nb200_cgd_minimize(nb200_obj* obj, double* x, const int64_t n, const int beta, const double epsilon,
+                       const int64_t max_evals, const double orthotest, const double eta, const int64_t n_global,
+                       nb200_allreduce_fn allreduce, void* allreduce_user, double* fx, double* gradient_test,
+                       int64_t* stats, int* status)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr && gradient_test != nullptr && stats != nullptr &&
+                      status != nullptr,
+                  "cgd: null argument");
+    NB200_REQUIRE(n == obj->n, "solver: incompatible initial point (" + std::to_string(n) + " dimensions), expecting " +
+                                   std::to_string(obj->n) + " dimensions!");
+    NB200_REQUIRE(beta >= 0 && beta < CGD_COUNT, "cgd: unknown beta formula");
+    NB200_REQUIRE(epsilon > 0.0 && max_evals > 0 && orthotest > 0.0 && orthotest < 1.0 && eta > 0.0 && eta < 1e+6,
+                  "cgd: invalid parameters");
+    NB200_REQUIRE(allreduce == nullptr || n_global > 0, "cgd: a sharded solve needs the global sample count");
+    NB200_REQUIRE(allreduce != nullptr || n_global == 0 || n_global == obj->data->N || obj->peer_world > 1,
+                  "cgd: a sharded solve needs the all-reduce callback or connected peers");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    solver_method_t method;
+    method.cgd       = true;
+    method.beta      = beta;
+    method.c2        = 1e-1; // solver::tolerance of the cgd family (cgd.cpp:77)
+    method.orthotest = orthotest;
+    method.eta       = eta;
+    device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user, method);
+    return solver.run(x, epsilon, max_evals, 1, fx, gradient_test, stats, status);
+}
+
 static int ensure_batch(nb200_obj* obj, const int64_t Kp)
 {
     batch_state&      bs   = obj->batch;

@@ -1,4 +1,4 @@
-"""Device-resident L-BFGS (nb200_lbfgs_minimize): libnano's solver_lbfgs_t with its default line search
+"""Device-resident L-BFGS and CGD (nb200_lbfgs_minimize, nb200_cgd_minimize): libnano's solver_lbfgs_t with its default line search
 (src/solver/lbfgs.cpp:25-124, src/lsearchk/cgdescent.cpp, src/lsearch0/quadratic.cpp) keeping x, g, the (s, y)
 history, the two-loop recursion and the trial points in HBM. libnano's own solvers still work unchanged through
 `function(x, gx)`; this entry is for callers that want the PCIe round trip per evaluation gone."""
@@ -14,11 +14,13 @@ from .function import critical
 STATUS = {0: "max_iters", 1: "gradient_test", 4: "failed"}
 
 
-def lbfgs(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, history: int = 50):
-    """Minimise a GPU objective (LinearFunction, SyntheticFunction or sharded.ShardedFunction) from x0.
+CGD_BETAS = {"hs": 0, "fr": 1, "pr": 2, "cd": 3, "ls": 4, "dy": 5, "n": 6, "dycd": 7, "dyhs": 8, "frpr": 9}
 
-    Defaults are the reference's (src/solver.cpp:45-51: epsilon 1e-8, max_evals 1000; lbfgs.cpp:12: history 50).
-    Returns a dict like solver_state_t: x, fx, gradient_test, status, fcalls, gcalls, iterations."""
+
+def _device_minimize(function, x0, invoke):
+    """Shared plumbing of the device-resident line-search solvers: resolves the rank-local objective and the
+    cross-rank exchange (fused peers / all-reduce callback / none), calls `invoke(handle, x_ptr, n, n_global,
+    callback, fx, gtest, stats, status)` and packs the result like solver_state_t."""
     from .sharded import ShardedFunction
 
     x = np.ascontiguousarray(x0, dtype=np.float64).copy()
@@ -50,14 +52,35 @@ def lbfgs(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, history: i
     fx, gtest = ctypes.c_double(), ctypes.c_double()
     stats = (ctypes.c_int64 * 3)()
     status = ctypes.c_int()
-    _lib.check(_lib.lib().nb200_lbfgs_minimize(
-        local.handle, x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), x.size, float(epsilon), int(max_evals),
-        int(history), int(n_global), ctypes.cast(callback, ctypes.c_void_p) if callback else None, None,
-        ctypes.byref(fx), ctypes.byref(gtest), stats, ctypes.byref(status)))
+    _lib.check(invoke(local.handle, x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), x.size, int(n_global),
+                      ctypes.cast(callback, ctypes.c_void_p) if callback else None, ctypes.byref(fx),
+                      ctypes.byref(gtest), stats, ctypes.byref(status)))
     function._fcalls += int(stats[0])
     function._gcalls += int(stats[1])
     return {"x": x, "fx": fx.value, "gradient_test": gtest.value, "status": STATUS.get(status.value, "failed"),
             "fcalls": int(stats[0]), "gcalls": int(stats[1]), "iterations": int(stats[2])}
+
+
+def lbfgs(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, history: int = 50):
+    """Minimise a GPU objective (LinearFunction, SyntheticFunction or sharded.ShardedFunction) from x0.
+
+    Defaults are the reference's (src/solver.cpp:45-51: epsilon 1e-8, max_evals 1000; lbfgs.cpp:12: history 50).
+    Returns a dict like solver_state_t: x, fx, gradient_test, status, fcalls, gcalls, iterations."""
+    return _device_minimize(function, x0, lambda handle, x, n, n_global, callback, fx, gtest, stats, status:
+                            _lib.lib().nb200_lbfgs_minimize(handle, x, n, float(epsilon), int(max_evals), int(history),
+                                                            n_global, callback, None, fx, gtest, stats, status))
+
+
+def cgd(function, x0, beta: str = "pr", epsilon: float = 1e-8, max_evals: int = 1000, orthotest: float = 0.1,
+        eta: float = 0.01):
+    """Device-resident non-linear conjugate gradient descent, libnano's solver ids cgd-<beta> (src/solver/cgd.cpp;
+    "pr" is the one registered as plain "cgd"): same skeleton and line search as lbfgs() with tolerance (1e-4, 1e-1);
+    the beta formula, the direction update and the restart test run as one kernel on the device."""
+    critical(beta in CGD_BETAS, "solver: unknown cgd variant '", beta, "', expecting one of ", sorted(CGD_BETAS))
+    return _device_minimize(function, x0, lambda handle, x, n, n_global, callback, fx, gtest, stats, status:
+                            _lib.lib().nb200_cgd_minimize(handle, x, n, CGD_BETAS[beta], float(epsilon),
+                                                          int(max_evals), float(orthotest), float(eta), n_global,
+                                                          callback, None, fx, gtest, stats, status))
 
 
 def osga(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, patience: int = 100, lambda_: float = 0.9,

@@ -106,6 +106,9 @@ def lib():
         L.oracle_lbfgs.restype = ctypes.c_int
         L.oracle_lbfgs.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double, _i64, _i64,
                                    _dp, _dp, ctypes.POINTER(_i64)]
+        L.oracle_cgd.restype = ctypes.c_int
+        L.oracle_cgd.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_int, ctypes.c_double, _i64,
+                                 ctypes.c_double, ctypes.c_double, _dp, _dp, ctypes.POINTER(_i64)]
         L.oracle_osga.restype = ctypes.c_int
         L.oracle_osga.argtypes = [L.oracle_solver_callback, ctypes.c_void_p, _i64, _dp, ctypes.c_double,
                                   ctypes.c_double, _i64, _i64, _dp, _dp, ctypes.POINTER(_i64)]
@@ -291,6 +294,22 @@ def lbfgs(function, x0, epsilon=1e-8, max_evals=1000, history=50):
     callback = _make_callback(function, n)
     status = lib().oracle_lbfgs(callback, None, n, _ptr(x), epsilon, max_evals, history, ctypes.byref(fx),
                                 ctypes.byref(gtest), stats)
+    return {"x": x, "fx": fx.value, "gradient_test": gtest.value, "status": SOLVER_STATUS[status],
+            "fcalls": stats[0], "gcalls": stats[1], "iterations": stats[2]}
+
+
+CGD_BETAS = {"hs": 0, "fr": 1, "pr": 2, "cd": 3, "ls": 4, "dy": 5, "n": 6, "dycd": 7, "dyhs": 8, "frpr": 9}
+
+
+def cgd(function, x0, beta="pr", epsilon=1e-8, max_evals=1000, orthotest=0.1, eta=0.01):
+    """solver_cgd_t::minimize, ids cgd-<beta> (src/solver/cgd.cpp:73-143; cgd-pr is libnano's default "cgd")."""
+    x = _f64(x0).copy()
+    n = x.size
+    fx, gtest = ctypes.c_double(), ctypes.c_double()
+    stats = (_i64 * 3)()
+    callback = _make_callback(function, n)
+    status = lib().oracle_cgd(callback, None, n, _ptr(x), CGD_BETAS[beta], epsilon, max_evals, orthotest, eta,
+                              ctypes.byref(fx), ctypes.byref(gtest), stats)
     return {"x": x, "fx": fx.value, "gradient_test": gtest.value, "status": SOLVER_STATUS[status],
             "fcalls": stats[0], "gcalls": stats[1], "iterations": stats[2]}
 

@@ -13,6 +13,7 @@
 //   state predicates  src/solver/state.cpp:165-210, include/nano/solver/state.h:139-146
 //   stopping          src/solver.cpp:114-173, src/solver/track.cpp:11-59
 //   OSGA              src/solver/osga.cpp:8-147        (lambda 0.9, alpha_max 0.7, kappas (0.1, 1.1))
+//   CGD               src/solver/cgd.cpp:7-143,240-299 (ten beta formulas, tolerance (1e-4, 1e-1), orthotest 0.1)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -572,6 +573,141 @@ int oracle_lbfgs(callback_t callback, void* ctx, const int64_t n, double* x, con
     }
 
     return finish(cstate.valid() ? cstate : pstate); // solver_t::choose (src/solver.cpp:219-225)
+}
+
+// solver_cgd_t::do_minimize (src/solver/cgd.cpp:86-143) with lsearch0 = quadratic, lsearchk = cgdescent and the
+// tolerance (1e-4, 1e-1) of cgd.cpp:77. beta: 0 HS+ 1 FR 2 PR+ 3 CD 4 LS+ 5 DY 6 N 7 DYCD 8 DYHS 9 FRPR
+// (cgd.cpp:7-71,240-299). x: in = x0, out = the returned state's x. stats = {fcalls, gcalls, iterations}.
+int oracle_cgd(callback_t callback, void* ctx, const int64_t n, double* x, const int beta_kind, const double epsilon,
+               const int64_t max_evals, const double orthotest, const double eta0, double* fx, double* gradient_test,
+               int64_t* stats)
+{
+    counted_function_t function{callback, ctx};
+    const vec          x0(x, x + n);
+
+    state_t cstate(function, x0);
+    int     status     = STATUS_MAX_ITERS;
+    int64_t iterations = 0;
+
+    const auto finish = [&](const state_t& state)
+    {
+        std::copy(state.m_x.begin(), state.m_x.end(), x);
+        *fx            = state.m_fx;
+        *gradient_test = state.gradient_test();
+        stats[0]       = function.m_fcalls;
+        stats[1]       = function.m_gcalls;
+        stats[2]       = iterations;
+        return status;
+    };
+
+    if (norm_inf(cstate.m_gx) < kEpsilon0) // cgd.cpp:95-99
+    {
+        status = cstate.valid() ? STATUS_GRADIENT_TEST : STATUS_FAILED;
+        return finish(cstate);
+    }
+
+    // the ten formulas, written over the dot products the reference takes (cgd.cpp:7-71)
+    const auto beta = [&](const vec& pg, const vec& pd, const vec& cg)
+    {
+        double cg_y = 0.0, pd_y = 0.0, y_y = 0.0; // y = cg - pg
+        for (int64_t i = 0; i < n; ++i)
+        {
+            const double y = cg[i] - pg[i];
+            cg_y += cg[i] * y;
+            pd_y += pd[i] * y;
+            y_y += y * y;
+        }
+        const double cg_cg = dot(cg, cg), pg_pg = dot(pg, pg), pd_pg = dot(pd, pg);
+        const double HS = cg_y / pd_y, FR = cg_cg / pg_pg, PR = cg_y / pg_pg, CD = -cg_cg / pd_pg, LS = -cg_y / pd_pg,
+                     DY = cg_cg / pd_y;
+        switch (beta_kind)
+        {
+        case 0: return std::max(HS, 0.0);
+        case 1: return FR;
+        case 2: return std::max(PR, 0.0);
+        case 3: return CD;
+        case 4: return std::max(LS, 0.0);
+        case 5: return DY;
+        case 6:
+        {
+            const double div = 1.0 / pd_y;
+            const double eta = -1.0 / (std::sqrt(dot(pd, pd)) * std::min(eta0, std::sqrt(pg_pg)));
+            double       sum = 0.0;
+            for (int64_t i = 0; i < n; ++i)
+            {
+                sum += ((cg[i] - pg[i]) - 2.0 * pd[i] * y_y * div) * cg[i];
+            }
+            return std::max(eta, div * sum);
+        }
+        case 7: return cg_cg / std::max(pd_y, -pd_pg);
+        case 8: return std::max(0.0, std::min(DY, HS));
+        default: return (PR < -FR) ? -FR : ((std::fabs(PR) <= FR) ? PR : FR);
+        }
+    };
+
+    state_t           pstate = cstate;
+    const cgdescent_t lsearchk(1e-4, 1e-1);
+    double            last_step_size = -1.0, prevf = 0.0, prevdg = 1.0;
+    vec               cdescent, pdescent;
+    while (function.calls() < max_evals)
+    {
+        if (cdescent.empty())
+        {
+            cdescent.resize(static_cast<size_t>(n));
+            for (int64_t i = 0; i < n; ++i)
+            {
+                cdescent[i] = -cstate.m_gx[i];
+            }
+        }
+        else
+        {
+            const double b = beta(pstate.m_gx, pdescent, cstate.m_gx);
+            for (int64_t i = 0; i < n; ++i)
+            {
+                cdescent[i] = -cstate.m_gx[i] + b * pdescent[i];
+            }
+            // restart: not a descent direction, or consecutive gradients far from orthogonal (cgd.cpp:121-126)
+            if (!cstate.has_descent(cdescent) ||
+                std::fabs(dot(cstate.m_gx, pstate.m_gx)) >= orthotest * dot(cstate.m_gx, cstate.m_gx))
+            {
+                for (int64_t i = 0; i < n; ++i)
+                {
+                    cdescent[i] = -cstate.m_gx[i];
+                }
+            }
+        }
+        pstate   = cstate;
+        pdescent = cdescent;
+
+        double t0;
+        if (last_step_size < 0.0)
+        {
+            t0 = 1.0;
+        }
+        else
+        {
+            t0 = std::min(1.0, 1.01 * 2.0 * (cstate.m_fx - prevf) / prevdg);
+        }
+        prevf  = cstate.m_fx;
+        prevdg = cstate.dg(cdescent);
+
+        const auto [iter_ok, step_size] = lsearchk.get(cstate, cdescent, t0);
+        last_step_size                  = step_size;
+        ++iterations;
+
+        cstate.m_track.update(cstate.m_x, cstate.m_fx);
+        if (!(iter_ok && cstate.valid()))
+        {
+            status = STATUS_FAILED;
+            break;
+        }
+        if (cstate.gradient_test() < epsilon)
+        {
+            status = STATUS_GRADIENT_TEST;
+            break;
+        }
+    }
+    return finish(cstate.valid() ? cstate : pstate);
 }
 
 // solver_osga_t::do_minimize (src/solver/osga.cpp:59-147). strong_convexity = function.strong_convexity().

@@ -58,11 +58,15 @@ def test_register_hand_over_matches_the_allocation(library):
     # the fused kernel re-distributes registers between its producer and consumer warpgroups (setmaxnreg); asking
     # for more than the CTA's pool would dead-lock, so pin the per-thread launch allocation ptxas chose
     out = subprocess.run(["cuobjdump", "-res-usage", library._name], capture_output=True, text=True).stdout
-    found = re.findall(r"vgrad_t1_kernelILi\d+ELi\d+ELi\d+ELi(\d+)ELi\d+ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
+    found = re.findall(r"vgrad_t1_kernelILi\d+ELi\d+ELi\d+ELi(\d+)ELi\d+ELi\d+ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
     assert len(found) >= 40
     for ncw, regs in found:
         threads = (int(ncw) + 4) * 32
-        assert int(regs) == (65536 // threads) // 8 * 8, (ncw, regs)
+        launch = (65536 // threads) // 8 * 8
+        if launch < 232:  # the producer warpgroup hands registers over: the pool is threads x launch registers
+            assert int(regs) == launch, (ncw, regs)
+        else:  # four consumer warps: every thread already owns more than setmaxnreg could give
+            assert int(regs) <= 255 and int(regs) * threads <= 65536 + 255, (ncw, regs)
 
 
 def test_no_gpu_means_loud_failure_not_fallback(library):

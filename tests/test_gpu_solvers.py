@@ -164,3 +164,56 @@ def test_host_driven_osga_matches_the_restated_driver(ctx, oracle):
         assert abs(mine["iterations"] - ref["iterations"]) <= max(2, ref["iterations"] // 20)
         assert abs(mine["fx"] - ref["fx"]) <= 1e-6 * (1 + abs(ref["fx"]))
         assert mine["fcalls"] == 2 * mine["iterations"] + 1 and mine["gcalls"] == mine["iterations"] + 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-resident CGD (nb200_cgd_minimize): the ten beta formulas of src/solver/cgd.cpp on the same skeleton
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("beta", ["hs", "fr", "pr", "cd", "ls", "dy", "n", "dycd", "dyhs", "frpr"])
+def test_device_resident_cgd_matches_the_restated_driver(ctx, oracle, beta):
+    import libnano_b200 as nb
+    from libnano_b200.solver import cgd
+
+    N, D, l2 = 6000, 48, 1e-2
+    X, Y, _ = make_problem(2, N, D, 1, True)
+    gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss("s-logistic"), 0.0, l2)
+    x0 = np.zeros(gpu.size())
+    epsilon = 1e-8
+    r_dev = cgd(gpu, x0, beta=beta, epsilon=epsilon, max_evals=2000)
+    assert r_dev["status"] == "gradient_test" and r_dev["gradient_test"] < epsilon, r_dev
+    assert (gpu.fcalls(), gpu.gcalls()) == (r_dev["fcalls"], r_dev["gcalls"])
+    # the restated CPU driver over the CPU oracle objective: same optimum within the solver's epsilon, similar effort
+    r_cpu = oracle.cgd(oracle_objective(oracle, X, Y, "s-logistic", 0.0, l2), x0, beta=beta, epsilon=epsilon,
+                       max_evals=2000)
+    assert r_cpu["status"] == "gradient_test"
+    assert abs(r_dev["fx"] - r_cpu["fx"]) <= epsilon * (1 + abs(r_cpu["fx"]))
+    assert np.max(np.abs(r_dev["x"] - r_cpu["x"])) <= 10 * epsilon / (l2 / D)
+    assert abs(r_dev["fcalls"] - r_cpu["fcalls"]) <= max(4, r_cpu["fcalls"] // 3)
+    # the returned point is what it claims
+    g = np.empty_like(x0)
+    f = gpu(r_dev["x"], g)
+    assert abs(f - r_dev["fx"]) <= 1e-12 * (1 + abs(f))
+
+
+def test_device_resident_cgd_contract(ctx):
+    import libnano_b200 as nb
+    from libnano_b200.solver import cgd
+
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (50, 4))
+    W, b = rng.uniform(-1, 1, (1, 4)), rng.uniform(-1, 1, 1)
+    function = nb.LinearFunction(nb.Dataset.pin(ctx, X, X @ W.T + b), nb.Loss("mse"), 0.0, 0.0)
+    result = cgd(function, np.zeros(5), epsilon=1e-10, max_evals=10000)
+    assert result["status"] == "gradient_test" and abs(result["fx"]) < 1e-7
+    assert np.max(np.abs(result["x"] - np.concatenate([W.ravel(), b]))) < 1e-7  # test_linear_function.cpp:152-188
+    at_optimum = cgd(function, np.concatenate([W.ravel(), b]))
+    assert at_optimum["status"] == "gradient_test" and at_optimum["fcalls"] == 1  # cgd.cpp:95-99
+    with pytest.raises(RuntimeError, match="unknown cgd variant"):
+        cgd(function, np.zeros(5), beta="xyz")
+    with pytest.raises(RuntimeError, match="incompatible initial point"):
+        cgd(function, np.zeros(4))
+    # many targets go through the tensor-pipe / generic evaluation paths under the same driver
+    Xm, Ym, _ = make_problem(3, 4000, 128, 4, True)
+    multi = nb.LinearFunction(nb.Dataset.pin(ctx, Xm, Ym), nb.Loss("s-classnll"), 0.0, 1e-2)
+    solved = cgd(multi, np.zeros(multi.size()), epsilon=1e-8)
+    assert solved["status"] == "gradient_test"
