@@ -116,6 +116,10 @@ const t1_variant kT1Variants[] = {
     /*34*/ NB200_T1_VARIANT_ALT(2, 4, 1, 8, 8, 2),
     /*35*/ NB200_T1_VARIANT_ALT(2, 2, 1, 8, 16, 2),
     /*36*/ NB200_T1_VARIANT_ALT(2, 1, 1, 8, 32, 2),
+    // 8 KiB rows split over two warps, four rows per iteration: the register footprint of variant 33 for D = 1024
+    /*37*/ NB200_T1_VARIANT_ALT(2, 8, 2, 8, 4, 2),
+    /*38*/ NB200_T1_VARIANT_ALT(2, 8, 2, 8, 2, 1),
+    /*39*/ NB200_T1_VARIANT_ALT(2, 16, 2, 8, 2, 2),
 };
 constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
 constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
@@ -469,7 +473,10 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
             // streams fp64 from HBM, so the variant with the fewest instructions per row wins the steady state —
             // several rows per warp iteration (one reduction and one loss chain per RW rows), two alternating sets of
             // four consumer warps for rows up to 4 KiB, four consumer warps for 8 KiB rows
-            static const int preferred[] = {36, 35, 34, 33, 27};
+            // 8 KiB rows: four consumer warps with whole rows (27) are 3 % faster than rows split over two warps (37)
+            // on a cool board and 3 % slower at the power cap; 37 does not need the exact width and wins clearly for
+            // D < 1024; 16 KiB rows: two rows per iteration over warp pairs (39)
+            const int preferred[] = {36, 35, 34, 33, D == 1024 ? 27 : 37, 27, 39};
             for (const int v : preferred)
             {
                 if (!ok)
@@ -721,6 +728,8 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.loss           = obj->loss;
         p.loss_param     = obj->loss_param;
         p.l2_resident    = (static_cast<int64_t>(N) * (D + 1) * 8 <= (static_cast<int64_t>(data->l2_bytes) * 3) / 4) ? 1 : 0;
+        static const int wait_hint_ns = env_int("NB200_WAIT_NS", 0);
+        p.wait_hint_ns   = wait_hint_ns;
         p.grid_counter   = obj->d_grid_counter;
         p.grid_target    = obj->grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
         p.reduced        = obj->d_reduced;

@@ -35,7 +35,8 @@
 namespace nb200
 {
 constexpr int kT1MaxStages  = 8;
-constexpr int kT1HeaderSize = 1024; // barriers + dot-exchange slots + tail scratch
+constexpr int kT1HeaderSize    = 1024; // barriers [0, 128) + dot-exchange slots [128, 640) + tail scratch
+constexpr int kT1ExchangeBytes = 512; // tail scratch [640, 1024): 2 x (NCW + 4) doubles
 constexpr int kT1MaxPeers   = 8;    // ranks of one NVSwitch domain
 
 struct t1_params
@@ -56,6 +57,7 @@ struct t1_params
     int           loss;
     double        loss_param;
     int           l2_resident; // 1: X + Y fit in L2 and are re-read by the next evaluation
+    int           wait_hint_ns; // > 0: consumers wait for a stage with this suspend-time hint (tuning knob)
 
     // fused tail: cross-CTA reduction after a grid-wide barrier, optionally followed by the final scaling
     unsigned long long* grid_counter; // monotonically increasing arrival counter (never reset between launches)
@@ -110,7 +112,8 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
                                              double* exchange, const double* w_s, unsigned char* stage_base,
                                              const int warp, const int lane)
 {
-    static_assert(RW >= 1 && RW <= 32 && (RW == 1 || WS == 1), "several rows per iteration need whole rows per warp");
+    static_assert(RW >= 1 && RW <= 32, "rows per iteration");
+    static_assert(WS == 1 || (NCW / WS) * 2 * WS * RW * 8 <= kT1ExchangeBytes, "the dot-exchange slots must fit the header");
     static_assert((RW & (RW - 1)) == 0, "rows per iteration must be a power of two");
     static_assert(ALT >= 1 && NCW % (ALT * WS) == 0, "the alternating warp sets must hold whole row groups");
     constexpr int NG  = NCW / WS;    // row groups of the CTA (all sets): one partial gradient row each in the fold
@@ -155,7 +158,14 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
         // every warp observes EVERY fill of the ring in order and releases it, also the tiles of the other sets: a
         // parity wait can tell only adjacent phases apart, so no warp may fall a whole lap behind the producer
         const int s = stage_index;
-        mbar_wait(full_bar + s, phase);
+        if (p.wait_hint_ns > 0)
+        {
+            mbar_wait_hint(full_bar + s, phase, static_cast<uint32_t>(p.wait_hint_ns));
+        }
+        else
+        {
+            mbar_wait(full_bar + s, phase);
+        }
         const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
         stage_index            = wrapped ? 0 : stage_index + 1;
         phase ^= wrapped;
@@ -266,17 +276,17 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             if constexpr (WS > 1)
             {
                 // combine the column slices of the WS warps sharing this row, in slice order
-                double* slot = exchange + (group * 2 + exparity) * WS;
-                if (lane == 0)
+                double* slot = exchange + (group * 2 + exparity) * (WS * RW); // [WS][RW]
+                if (owner)
                 {
-                    slot[slice] = mine;
+                    slot[slice * RW + my_row] = mine;
                 }
                 named_bar_sync(1 + group, WS * 32);
                 mine = 0.0;
 #pragma unroll
                 for (int q = 0; q < WS; ++q)
                 {
-                    mine += slot[q];
+                    mine += slot[q * RW + my_row];
                 }
                 exparity ^= 1;
             }
@@ -617,8 +627,8 @@ __global__ void __launch_bounds__((NCW + kT1ProducerWarps) * 32, 1) vgrad_t1_ker
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kT1MaxStages;
-    double*   exchange  = reinterpret_cast<double*>(smem + 2 * kT1MaxStages * sizeof(uint64_t)); // [NG][2][WS]
-    double*   scratch   = reinterpret_cast<double*>(smem + 512);                                 // tail: [2][warps]
+    double*   exchange  = reinterpret_cast<double*>(smem + 2 * kT1MaxStages * sizeof(uint64_t)); // [NG][2][WS][RW]
+    double*   scratch   = reinterpret_cast<double*>(smem + 128 + kT1ExchangeBytes);              // tail: [2][warps]
     const int w_bytes   = static_cast<int>((static_cast<int64_t>(p.D) * 8 + 127) / 128 * 128);
     double*   w_s       = reinterpret_cast<double*>(smem + kT1HeaderSize);
     unsigned char* stage_base = smem + kT1HeaderSize + w_bytes;
