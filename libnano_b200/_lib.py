@@ -101,8 +101,11 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise Nb200Error(-1, f"{LIB_PATH} is missing: run `python -m libnano_b200.build` (needs nvcc); "
                                  "libnano_b200 has no CPU fallback")
-        L = ctypes.CDLL(LIB_PATH)
+        override = os.environ.get("NB200_LIBRARY")  # A/B runs of two builds on one GPU box (tools/): never a fallback
+        L = ctypes.CDLL(override or LIB_PATH)
         for name, (restype, argtypes) in SIGNATURES.items():
+            if override and not hasattr(L, name):
+                continue  # an older build under test may predate a symbol
             fn = getattr(L, name)  # AttributeError here means the library does not match include/nb200.h
             fn.restype = restype
             fn.argtypes = argtypes

@@ -20,12 +20,15 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-O3",
     "-std=c++17",
-    "-shared",
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
-    "-cudart", "static",
-    "-split-compile", "0",  # the 50-odd kernel instantiations are optimised in parallel
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+# translation units: the host layer + small kernels, four groups of single-target kernel variants, the tensor-pipe
+# kernels. They compile in parallel, and no kernel family's code depends on what else shares its module.
+UNITS = ["nb200_api.cu", "kernels_t1_a.cu", "kernels_t1_b.cu", "kernels_t1_c.cu", "kernels_t1_d.cu", "kernels_mt.cu"]
+OBJ_DIR = os.path.join(CSRC, "build")
 
 
 def _nvcc() -> str:
@@ -45,7 +48,7 @@ def _fingerprint() -> str:
     """Content hash of every source plus the flags: file times do not survive the snapshot to the GPU box."""
     import hashlib
 
-    digest = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    digest = hashlib.sha256(" ".join(NVCC_FLAGS + LINK_FLAGS + UNITS).encode())
     for path in sources():
         digest.update(os.path.basename(path).encode())
         with open(path, "rb") as handle:
@@ -60,18 +63,35 @@ def is_stale() -> bool:
         return handle.read().strip() != _fingerprint()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB_PATH
+def _compile(unit: str, verbose: bool):
+    obj = os.path.join(OBJ_DIR, unit[:-3] + ".o")
     cmd = [_nvcc(), *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, os.path.join(CSRC, "nb200_api.cu")]
+    cmd += ["-I", os.path.join(ROOT, "include"), "-c", "-o", obj, os.path.join(CSRC, unit)]
     result = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(result.stderr)
+    return obj, cmd, result
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        outcomes = list(pool.map(lambda unit: _compile(unit, verbose), UNITS))
+    objects = []
+    for obj, cmd, result in outcomes:
+        if verbose:
+            sys.stderr.write(result.stderr)
+        if result.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + result.stdout + result.stderr)
+        objects.append(obj)
+    cmd = [_nvcc(), *LINK_FLAGS, "-o", LIB_PATH, *objects]
+    result = subprocess.run(cmd, capture_output=True, text=True)
     if result.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + result.stdout + result.stderr)
+        raise RuntimeError("nvcc (link) failed:\n" + " ".join(cmd) + "\n" + result.stdout + result.stderr)
     with open(STAMP_PATH, "w") as handle:
         handle.write(_fingerprint() + "\n")
     return LIB_PATH

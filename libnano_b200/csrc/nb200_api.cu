@@ -19,9 +19,8 @@
 #include "scale.cuh"
 #include "synth.cuh"
 #include "vgrad_gen.cuh"
-#include "vgrad_mt.cuh"
+#include "kernel_tables.cuh"
 #include "batch.cuh"
-#include "vgrad_t1.cuh"
 
 using namespace nb200;
 
@@ -53,98 +52,28 @@ struct nb200_data
 
 namespace
 {
-using t1_kernel_t = void (*)(const t1_params);
-
-struct t1_variant
+// the kernel variants are instantiated in kernels_t1_{a,b,c,d}.cu and kernels_mt.cu (kernel_tables.cuh)
+struct t1_table_t
 {
-    int         V, KC, WS, NCW, RW, ALT;
-    t1_kernel_t grad;
-    t1_kernel_t value;
-};
-
-#define NB200_T1_VARIANT_ALT(V, KC, WS, NCW, RW, ALT)                                                                  \
-    t1_variant                                                                                                         \
-    {                                                                                                                  \
-        V, KC, WS, NCW, RW, ALT, vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, true>,                                       \
-            vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, false>                                                            \
+    std::vector<t1_variant> entries;
+    t1_table_t()
+    {
+        for (const auto group : {t1_group_a, t1_group_b, t1_group_c, t1_group_d})
+        {
+            int               count = 0;
+            const t1_variant* first = group(&count);
+            entries.insert(entries.end(), first, first + count);
+        }
     }
-#define NB200_T1_VARIANT(V, KC, WS, NCW, RW) NB200_T1_VARIANT_ALT(V, KC, WS, NCW, RW, 1)
-
-// Ordered so that the first variant whose column capacity 32*V*KC*WS covers D is the heuristic choice; the extra
-// entries at the end are alternative decompositions selectable with nb200_objective_set_variant.
-// Short rows are processed RW at a time (64 KiB stages hold 8 * RW rows of <= 8 KiB / RW).
-const t1_variant kT1Variants[] = {
-    /* 0*/ NB200_T1_VARIANT(2, 1, 1, 8, 8),
-    /* 1*/ NB200_T1_VARIANT(2, 2, 1, 8, 8),
-    /* 2*/ NB200_T1_VARIANT(2, 4, 1, 8, 4),
-    /* 3*/ NB200_T1_VARIANT(2, 8, 1, 8, 2),
-    /* 4*/ NB200_T1_VARIANT(2, 16, 1, 8, 1),
-    /* 5*/ NB200_T1_VARIANT(2, 16, 2, 8, 1),
-    /* 6*/ NB200_T1_VARIANT(2, 16, 4, 8, 1),
-    /* 7*/ NB200_T1_VARIANT(2, 16, 8, 8, 1),
-    /* 8*/ NB200_T1_VARIANT(1, 1, 1, 8, 8),
-    /* 9*/ NB200_T1_VARIANT(1, 2, 1, 8, 8),
-    /*10*/ NB200_T1_VARIANT(1, 4, 1, 8, 8),
-    /*11*/ NB200_T1_VARIANT(1, 8, 1, 8, 4),
-    /*12*/ NB200_T1_VARIANT(1, 16, 1, 8, 2),
-    /*13*/ NB200_T1_VARIANT(1, 32, 1, 8, 1),
-    /*14*/ NB200_T1_VARIANT(1, 32, 2, 8, 1),
-    /*15*/ NB200_T1_VARIANT(1, 32, 4, 8, 1),
-    /*16*/ NB200_T1_VARIANT(1, 32, 8, 8, 1),
-    // alternatives (same coverage, different decomposition)
-    /*17*/ NB200_T1_VARIANT(2, 8, 2, 8, 1),
-    /*18*/ NB200_T1_VARIANT(2, 8, 2, 16, 1),
-    /*19*/ NB200_T1_VARIANT(2, 4, 4, 16, 1),
-    /*20*/ NB200_T1_VARIANT(2, 16, 1, 12, 1),
-    /*21*/ NB200_T1_VARIANT(2, 16, 1, 8, 2),
-    /*22*/ NB200_T1_VARIANT(2, 8, 1, 8, 1),
-    /*23*/ NB200_T1_VARIANT(2, 8, 1, 8, 4),
-    /*24*/ NB200_T1_VARIANT(2, 4, 1, 8, 1),
-    /*25*/ NB200_T1_VARIANT(2, 4, 1, 8, 8),
-    /*26*/ NB200_T1_VARIANT(2, 2, 1, 8, 1),
-    // four consumer warps, twice the rows per warp and stage: 64 doubles of X per lane for every width, the loss
-    // chain and the reduction are paid once per RW rows
-    /*27*/ NB200_T1_VARIANT(2, 16, 1, 4, 2),
-    /*28*/ NB200_T1_VARIANT(2, 8, 1, 4, 4),
-    /*29*/ NB200_T1_VARIANT(2, 4, 1, 4, 8),
-    /*30*/ NB200_T1_VARIANT(2, 2, 1, 4, 16),
-    /*31*/ NB200_T1_VARIANT(2, 1, 1, 4, 32),
-    // eight consumer warps in two sets that alternate over the CTA's tiles: the rows per warp and stage of the
-    // four-warp family with two warps per scheduler to hide the loss / reduction chain
-    /*32*/ NB200_T1_VARIANT_ALT(2, 16, 1, 8, 2, 2),
-    /*33*/ NB200_T1_VARIANT_ALT(2, 8, 1, 8, 4, 2),
-    /*34*/ NB200_T1_VARIANT_ALT(2, 4, 1, 8, 8, 2),
-    /*35*/ NB200_T1_VARIANT_ALT(2, 2, 1, 8, 16, 2),
-    /*36*/ NB200_T1_VARIANT_ALT(2, 1, 1, 8, 32, 2),
-    // 8 KiB rows split over two warps, four rows per iteration: the register footprint of variant 33 for D = 1024
-    /*37*/ NB200_T1_VARIANT_ALT(2, 8, 2, 8, 4, 2),
-    /*38*/ NB200_T1_VARIANT_ALT(2, 8, 2, 8, 2, 1),
-    /*39*/ NB200_T1_VARIANT_ALT(2, 16, 2, 8, 2, 2),
 };
-constexpr int kNumT1Variants   = static_cast<int>(sizeof(kT1Variants) / sizeof(kT1Variants[0]));
-constexpr int kNumT1Heuristic  = 17; // entries scanned by the heuristic
+const t1_table_t kT1Table;
+const t1_variant* const kT1Variants    = kT1Table.entries.data();
+const int               kNumT1Variants = static_cast<int>(kT1Table.entries.size());
+constexpr int           kNumT1Heuristic = 17; // entries scanned by the fall-back heuristic
 
-using mt_fwd_kernel_t = void (*)(const mt_forward_params);
-using mt_bwd_kernel_t = void (*)(const mt_backward_params);
-
-struct mt_variant
-{
-    int             NT8; // target tiles of 8: covers T <= 8 * NT8
-    mt_fwd_kernel_t grad;
-    mt_fwd_kernel_t value;
-    mt_bwd_kernel_t backward;
-};
-
-#define NB200_MT_VARIANT(NT8)                                                                                          \
-    mt_variant                                                                                                         \
-    {                                                                                                                  \
-        NT8, mt_forward_kernel<NT8, true>, mt_forward_kernel<NT8, false>, mt_backward_kernel<NT8>                      \
-    }
-
-const mt_variant kMtVariants[] = {NB200_MT_VARIANT(1), NB200_MT_VARIANT(2),  NB200_MT_VARIANT(3),
-                                  NB200_MT_VARIANT(4), NB200_MT_VARIANT(6),  NB200_MT_VARIANT(8),
-                                  NB200_MT_VARIANT(10), NB200_MT_VARIANT(13), NB200_MT_VARIANT(16)};
-constexpr int    kNumMtVariants = static_cast<int>(sizeof(kMtVariants) / sizeof(kMtVariants[0]));
+int               g_num_mt_variants = 0;
+const mt_variant* const kMtVariants    = mt_variants(&g_num_mt_variants);
+const int               kNumMtVariants = g_num_mt_variants;
 
 // launch geometry of the tensor-pipe kernels for an (N, D, T) problem
 struct mt_geometry
@@ -799,6 +728,7 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         f.y_broadcast     = 0;
         f.per_target_loss = 0;
         f.fb_stride       = static_cast<int>(1 + T);
+        f.prefetch_y      = env_int("NB200_MT_PREFETCH_Y", 0);
         (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;

@@ -85,6 +85,25 @@ def test_t1_at_zero_and_at_kinks(ctx, oracle):
         check_against_oracle(oracle, function, X, Y, loss_id, np.zeros(D + 1), 0.1, 0.1)
 
 
+def test_t1_ragged_row_counts(ctx, oracle):
+    # row counts around every boundary of the launch geometry (rows per iteration 1 .. 32, rows per stage 8 .. 128,
+    # alternating warp sets, one tile per CTA, 148 CTAs): partial iterations, partial tiles, idle warps and idle CTAs
+    counts = [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 129, 255, 257, 1183, 1185, 2369, 4737]
+    for D in (2, 64, 100, 128, 256, 512, 1000, 1024, 2048):
+        rng = np.random.default_rng(D)
+        Xall = rng.uniform(-1, 1, (max(counts), D))
+        Yall = np.where(rng.uniform(-1, 1, (max(counts), 1)) < 0, -1.0, 1.0)
+        x = rng.uniform(-1, 1, D + 1) / np.sqrt(D)
+        for N in counts:
+            X, Y = Xall[:N], Yall[:N]
+            function = gpu_function(ctx, X, Y, "s-logistic", 0.0, 1e-2)
+            gx = np.empty_like(x)
+            fx = function(x, gx)
+            f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-logistic", x, l2=1e-2)
+            assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY, (N, D, function.describe())
+            assert rel_f(function(x), f_ref) <= PARITY, (N, D, function.describe())
+
+
 def test_t1_non_finite_flows_back(ctx):
     # numerical failure is not an error: non-finite f/g come back and solver_state_t::valid() decides
     # (src/solver/state.cpp:170-174)

@@ -2,8 +2,12 @@
 // kernels are designed: DFMA issue rate, DMMA (mma.sync f64) rate for the m8n8k4 and m16n8k16 shapes.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fp64_peaks tools/fp64_peaks.cu && /tmp/fp64_peaks
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 constexpr int kIters = 4096;
 
@@ -114,7 +118,68 @@ double time_kernel(K kernel, int blocks, int threads, double* out)
     return best * 1e-3;
 }
 
-int main()
+// NVML through dlopen: board power and SM clock while a kernel runs
+struct nvml_t
+{
+    void* dev{nullptr};
+    int (*power)(void*, unsigned*){nullptr};
+    int (*clock)(void*, int, unsigned*){nullptr};
+    bool open()
+    {
+        void* lib = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+        if (!lib) return false;
+        auto init   = (int (*)())dlsym(lib, "nvmlInit_v2");
+        auto handle = (int (*)(unsigned, void**))dlsym(lib, "nvmlDeviceGetHandleByIndex_v2");
+        power       = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetPowerUsage");
+        clock       = (int (*)(void*, int, unsigned*))dlsym(lib, "nvmlDeviceGetClockInfo");
+        return init && handle && power && clock && init() == 0 && handle(0, &dev) == 0;
+    }
+};
+
+// back-to-back launches for `seconds`: the steady state (second half) is what a 100 ms contraction actually gets
+template <class K>
+void sustained(const char* name, K kernel, int blocks, int threads, double* out, double flops_per_launch,
+               double seconds, nvml_t& nvml)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    std::vector<float>    times;
+    std::vector<unsigned> watts, mhz;
+    const auto start = std::chrono::steady_clock::now();
+    while (std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count() < seconds)
+    {
+        cudaEventRecord(e0);
+        for (int i = 0; i < 20; ++i) kernel<<<blocks, threads>>>(out, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        unsigned mw = 0, clk = 0;
+        if (nvml.dev)
+        {
+            nvml.power(nvml.dev, &mw);
+            nvml.clock(nvml.dev, 1, &clk);
+        }
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        times.push_back(ms / 20);
+        watts.push_back(mw);
+        mhz.push_back(clk);
+    }
+    const size_t h = times.size() / 2;
+    double t = 0, w = 0, c = 0;
+    for (size_t i = h; i < times.size(); ++i) { t += times[i]; w += watts[i]; c += mhz[i]; }
+    const double n = double(times.size() - h);
+    printf("{\"sustained\": \"%s\", \"seconds\": %.1f, \"first_tflops\": %.2f, \"steady_tflops\": %.2f, "
+           "\"steady_sm_mhz\": %.0f, \"steady_power_w\": %.0f}\n",
+           name, seconds, flops_per_launch / (times[0] * 1e-3) / 1e12, flops_per_launch / (t / n * 1e-3) / 1e12, c / n,
+           w / n / 1e3);
+    fflush(stdout);
+    cudaDeviceSynchronize();
+    const auto c0 = std::chrono::steady_clock::now();
+    while (std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count() < 1.5) {}
+}
+
+int main(int argc, char** argv)
 {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
@@ -134,6 +199,16 @@ int main()
                warps, blocks, 2.0 * 16 * kIters * total / t_fma / 1e12,
                2.0 * 8 * 8 * 8 * 4 * kIters * (total / 32) / t_884 / 1e12,
                2.0 * 4 * 16 * 8 * 16 * kIters * (total / 32) / t_16816 / 1e12);
+    }
+    if (argc > 1 && std::strcmp(argv[1], "--sustained") == 0)
+    {
+        nvml_t nvml;
+        if (!nvml.open()) fprintf(stderr, "NVML unavailable\n");
+        const int    threads = 256, blocks = sms * 2;
+        const double total   = static_cast<double>(blocks) * threads;
+        sustained("dfma", dfma_kernel, blocks, threads, out, 2.0 * 16 * kIters * total, 3.0, nvml);
+        sustained("dmma_m8n8k4", dmma884_kernel, blocks, threads, out, 2.0 * 8 * 8 * 8 * 4 * kIters * (total / 32), 3.0,
+                  nvml);
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess)
