@@ -402,10 +402,12 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
             // streams fp64 from HBM, so the variant with the fewest instructions per row wins the steady state —
             // several rows per warp iteration (one reduction and one loss chain per RW rows), two alternating sets of
             // four consumer warps for rows up to 4 KiB, four consumer warps for 8 KiB rows
-            // 8 KiB rows: four consumer warps with whole rows (27) are 3 % faster than rows split over two warps (37)
-            // on a cool board and 3 % slower at the power cap; 37 does not need the exact width and wins clearly for
-            // D < 1024; 16 KiB rows: two rows per iteration over warp pairs (39)
-            const int preferred[] = {36, 35, 34, 33, D == 1024 ? 27 : 37, 27, 39};
+            // 8 KiB rows: four consumer warps with whole rows (27) are 6 % faster than rows split over warp pairs (37)
+            // while the board is cool — a solve on a shard of a few GiB ends before the power cap bites — and 7-10 %
+            // slower at the cap, where every evaluation of a large shard runs (2^23 rows: 10.33 vs 9.62 ms, profiles/);
+            // 37 does not need the exact width and wins clearly for D < 1024; 16 KiB rows: variant 39
+            const bool long_passes = static_cast<double>(N) * static_cast<double>(D) * 8.0 >= 16.0 * 1024 * 1024 * 1024;
+            const int  preferred[] = {36, 35, 34, 33, (D == 1024 && !long_passes) ? 27 : 37, 27, 39};
             for (const int v : preferred)
             {
                 if (!ok)
