@@ -95,22 +95,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity)
                  : "memory");
 }
 
-// the same with a suspend-time hint (ns): the hardware parks the warp for up to that long per attempt instead of
-// returning at once, so a consumer that is ahead of HBM polls (and burns issue slots / power) far less often
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, const uint32_t parity, const uint32_t hint_ns)
-{
-    asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
-                 "NB200_WAITH_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-                 "@p bra NB200_DONEH_%=;\n\t"
-                 "bra NB200_WAITH_%=;\n\t"
-                 "NB200_DONEH_%=:\n\t"
-                 "}" ::"r"(smem_u32(bar)),
-                 "r"(parity), "r"(hint_ns)
-                 : "memory");
-}
-
 // L2 eviction policy for data that is streamed exactly once (X tiles)
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {

@@ -304,8 +304,6 @@ struct nb200_obj
     bool    partial_has_grad{false};
     const double* partial_x{nullptr};
 
-    // how (g, f) reach the host: 0 = the kernel writes into the mapped pinned buffer, 1 = device buffer + one D2H copy
-    int     result_copy{0};
     // host-side wall clock of the public call, microseconds: [stage x + H2D | enqueue | wait + hand-over]
     double  host_us[3] = {0.0, 0.0, 0.0};
     int64_t host_calls{0};
@@ -541,7 +539,6 @@ int make_objective(nb200_data* data, const int loss, const double loss_param, co
         NB200_CUDA_TRY(cudaMallocHost(&obj->h_x, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaHostAlloc(&obj->h_out, (n + 2) * sizeof(double), cudaHostAllocMapped));
         NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->h_out_dev, obj->h_out, 0));
-        obj->result_copy = env_int("NB200_RESULT_COPY", 0);
         if (flavour == NB200_FLAVOUR_SYNTH)
         {
             obj->fixed_bias.assign(fixed_bias, fixed_bias + data->T);
@@ -659,8 +656,6 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.loss           = obj->loss;
         p.loss_param     = obj->loss_param;
         p.l2_resident    = (static_cast<int64_t>(N) * (D + 1) * 8 <= (static_cast<int64_t>(data->l2_bytes) * 3) / 4) ? 1 : 0;
-        static const int wait_hint_ns = env_int("NB200_WAIT_NS", 0);
-        p.wait_hint_ns   = wait_hint_ns;
         p.grid_counter   = obj->d_grid_counter;
         p.grid_target    = obj->grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
         p.reduced        = obj->d_reduced;
@@ -691,18 +686,8 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         // cooperative launch: the grid barrier of the fused tail needs every CTA resident (grid <= #SMs, 1 CTA/SM)
         void*       args[] = {&p};
         const void* kernel = reinterpret_cast<const void*>(want_grad ? var.grad : var.value);
-        static const int plain_launch = env_int("NB200_PLAIN_LAUNCH", 0); // probe: grid <= #SMs is co-resident anyway
-        if (plain_launch != 0)
-        {
-            NB200_CUDA_TRY(cudaLaunchKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32), args,
-                                            static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
-        }
-        else
-        {
-            NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid),
-                                                       dim3((var.NCW + kT1ProducerWarps) * 32), args,
-                                                       static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
-        }
+        NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32),
+                                                   args, static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
         obj->launches += 1;
         return timing_end(obj);
     }
@@ -730,7 +715,6 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         f.y_broadcast     = 0;
         f.per_target_loss = 0;
         f.fb_stride       = static_cast<int>(1 + T);
-        f.prefetch_y      = env_int("NB200_MT_PREFETCH_Y", 0);
         (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;
@@ -831,21 +815,17 @@ int upload_x(nb200_obj* obj, const double* x, const int64_t n)
     return NB200_OK;
 }
 
-// where the kernels of a host-buffer call write (g, f): the mapped pinned buffer, or the device buffer + one copy
+// where the kernels of a host-buffer call write (g, f): the mapped pinned buffer (a device buffer + one D2H copy was
+// measured to be no faster, profiles/r01_e2e_breakdown.jsonl)
 double* result_base(nb200_obj* obj)
 {
-    return obj->result_copy != 0 ? obj->d_out : obj->h_out_dev;
+    return obj->h_out_dev;
 }
 
 // the kernels wrote (g, f): wait for the stream, hand the values to the caller
 int collect_result(nb200_obj* obj, double* gx, double* fx)
 {
     const size_t n = static_cast<size_t>(obj->n);
-    if (obj->result_copy != 0)
-    {
-        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out, obj->d_out, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost,
-                                       obj->stream));
-    }
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
     collect_timing(obj);
     if (gx != nullptr)

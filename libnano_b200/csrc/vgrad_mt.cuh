@@ -50,7 +50,6 @@ struct mt_forward_params
     int           y_broadcast;     // 1: Y is [N, 1] and is used for every column
     int           per_target_loss; // 1: partial row = [total | dL sums (T) | loss sums (T)]
     int           fb_stride;       // doubles per row of partials_fb: 1 + T, or 1 + 2 T with per_target_loss
-    int           prefetch_y;      // 1: fetch the targets of row r + 1 while row r is evaluated (tuning knob)
 };
 
 struct mt_backward_params
@@ -262,42 +261,17 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
         const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
         const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
-        // the targets of row r + 1 are fetched while row r is evaluated (a row of Y is a fresh HBM line every time)
-        const auto load_targets = [&](const int64_t row, double (&dst)[TL])
-        {
-            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
-#pragma unroll
-            for (int k = 0; k < TL; ++k)
-            {
-                const int t = lane + 32 * k;
-                dst[k]      = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
-            }
-        };
-        double ynext[TL];
-        if (p.prefetch_y != 0 && row_count > 0)
-        {
-            load_targets(row_first, ynext);
-        }
         for (int r = 0; r < row_count; ++r)
         {
             const int64_t row  = row_first + r;
             double*       orow = orows + r * TPs;
-            double        y[TL];
-            if (p.prefetch_y != 0)
-            {
+            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
+            double        y[TL]; // (fetching the next row's targets one row ahead was measured: no gain)
 #pragma unroll
-                for (int k = 0; k < TL; ++k)
-                {
-                    y[k] = ynext[k];
-                }
-                if (r + 1 < row_count)
-                {
-                    load_targets(row + 1, ynext);
-                }
-            }
-            else
+            for (int k = 0; k < TL; ++k)
             {
-                load_targets(row, y);
+                const int t = lane + 32 * k;
+                y[k]        = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
             }
 
             if (p.loss == LOSS_CLASSNLL)

@@ -57,7 +57,6 @@ struct t1_params
     int           loss;
     double        loss_param;
     int           l2_resident; // 1: X + Y fit in L2 and are re-read by the next evaluation
-    int           wait_hint_ns; // > 0: consumers wait for a stage with this suspend-time hint (tuning knob)
 
     // fused tail: cross-CTA reduction after a grid-wide barrier, optionally followed by the final scaling
     unsigned long long* grid_counter; // monotonically increasing arrival counter (never reset between launches)
@@ -158,14 +157,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
         // every warp observes EVERY fill of the ring in order and releases it, also the tiles of the other sets: a
         // parity wait can tell only adjacent phases apart, so no warp may fall a whole lap behind the producer
         const int s = stage_index;
-        if (p.wait_hint_ns > 0)
-        {
-            mbar_wait_hint(full_bar + s, phase, static_cast<uint32_t>(p.wait_hint_ns));
-        }
-        else
-        {
-            mbar_wait(full_bar + s, phase);
-        }
+        mbar_wait(full_bar + s, phase);
         const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
         stage_index            = wrapped ? 0 : stage_index + 1;
         phase ^= wrapped;
