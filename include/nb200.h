@@ -212,8 +212,9 @@ NB200_API int    nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, in
 NB200_API int nb200_objective_host_profile(nb200_obj* obj, double* stage_us, double* enqueue_us, double* wait_us,
                                            int64_t* calls, int reset);
 
-/* Tuning knob for the fused T == 1 kernel: variant id (see DESIGN.md "kernel variants"), -1 = heuristic,
- * -2 = force the shape-generic two-kernel path. */
+/* Tuning knob: variant id of the fused T == 1 kernel (see DESIGN.md "kernel variants"), -1 = heuristic,
+ * -2 = force the shape-generic kernels, -3 = shape-generic kernels for T >= 2 only, -4 = the tensor-pipe pair for
+ * T >= 2 even where the few-target one-pass kernel applies. */
 NB200_API int nb200_objective_set_variant(nb200_obj* obj, int variant);
 
 /* Human-readable launch plan (kernel variant, grid, stages, shared memory) into buffer[size]. */
@@ -223,7 +224,7 @@ NB200_API int nb200_objective_describe(const nb200_obj* obj, char* buffer, int64
  * re-read the same X once per trial in the reference, src/machine/tune.cpp:25-42). K single-target models that share
  * the objective's dataset and loss and differ in x_k, l1_k, l2_k: x [K][n], l1 [K], l2 [K] -> gx [K][n] (nullable),
  * fx [K], all host. Runs as one many-"target" problem on the FP64 tensor pipe (two reads of X for K evaluations);
- * shapes outside those kernels (D not a multiple of 128) fall back to K passes of the single-model kernel. */
+ * shapes outside those kernels (odd D, fewer than 6 models) fall back to K passes of the single-model kernel. */
 NB200_API int nb200_vgrad_batch(nb200_obj* obj, int64_t K, const double* x, int64_t n, const double* l1,
                                 const double* l2, double* gx, double* fx);
 

@@ -165,9 +165,8 @@ __host__ __device__ constexpr int log2_of(const int value)
 // the total of row (lane >> (5 - log2 R)); every lane of that group holds the same bits (both partners of an
 // exchange add the same two numbers). values[] is clobbered.
 template <int R>
-__device__ __forceinline__ double warp_reduce_rows(double (&values)[R], const int lane)
+__device__ __forceinline__ double warp_reduce_rows_from(double (&values)[R], const int lane, int offset)
 {
-    int offset = 16;
 #pragma unroll
     for (int n = R; n > 1; n /= 2)
     {
@@ -188,6 +187,12 @@ __device__ __forceinline__ double warp_reduce_rows(double (&values)[R], const in
         total += __shfl_xor_sync(0xffffffffu, total, offset);
     }
     return total;
+}
+
+template <int R>
+__device__ __forceinline__ double warp_reduce_rows(double (&values)[R], const int lane)
+{
+    return warp_reduce_rows_from<R>(values, lane, 16);
 }
 
 __device__ __forceinline__ double warp_allreduce_max(double value)

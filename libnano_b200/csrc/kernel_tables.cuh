@@ -6,6 +6,7 @@
 // variants changed the SASS of mt_backward_kernel and cost config 3 15 %; profiles/README.md).
 #pragma once
 
+#include "vgrad_ft.cuh"
 #include "vgrad_mt.cuh"
 #include "vgrad_t1.cuh"
 
@@ -29,6 +30,15 @@ struct mt_variant
     mt_fwd_kernel_t grad;
     mt_fwd_kernel_t value;
     mt_bwd_kernel_t backward;
+};
+
+using ft_kernel_t = void (*)(const ft_params);
+
+struct ft_variant
+{
+    int         T, KC, RW; // targets (exact), 64 * KC columns per warp (D <= 512 * KC), rows per iteration
+    ft_kernel_t grad;
+    ft_kernel_t value;
 };
 
 // X(V, KC, WS, NCW, RW, ALT). The variant id is the position in A, B, C, D concatenated.
@@ -60,10 +70,11 @@ struct mt_variant
     t1_variant{V, KC, WS, NCW, RW, ALT, vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, true>,                                \
                vgrad_t1_kernel<V, KC, WS, NCW, RW, ALT, false>},
 
-// defined in kernels_t1_{a,b,c,d}.cu / kernels_mt.cu; return the group's entries and their count
+// defined in kernels_t1_{a,b,c,d}.cu / kernels_mt.cu / kernels_ft.cu; return the group's entries and their count
 const t1_variant* t1_group_a(int* count);
 const t1_variant* t1_group_b(int* count);
 const t1_variant* t1_group_c(int* count);
 const t1_variant* t1_group_d(int* count);
 const mt_variant* mt_variants(int* count);
+const ft_variant* ft_variants(int* count);
 } // namespace nb200

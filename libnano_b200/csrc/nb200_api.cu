@@ -71,9 +71,70 @@ const t1_variant* const kT1Variants    = kT1Table.entries.data();
 const int               kNumT1Variants = static_cast<int>(kT1Table.entries.size());
 constexpr int           kNumT1Heuristic = 17; // entries scanned by the fall-back heuristic
 
+int               g_num_ft_variants = 0;
+const ft_variant* const kFtVariants    = ft_variants(&g_num_ft_variants);
+const int               kNumFtVariants = g_num_ft_variants;
+
 int               g_num_mt_variants = 0;
 const mt_variant* const kMtVariants    = mt_variants(&g_num_mt_variants);
 const int               kNumMtVariants = g_num_mt_variants;
+
+// launch geometry of the few-target one-pass kernel (vgrad_ft.cuh)
+struct ft_plan
+{
+    int     variant{0};
+    int     grid{0};
+    int     rows_per_stage{0};
+    int     stages{0};
+    int     stage_stride{0};
+    int     y_offset{0};
+    int     smem_bytes{0};
+    int64_t num_tiles{0};
+};
+
+// an exact-T variant whose 512 * KC columns cover D (even D: rows start on 16-byte boundaries); false otherwise
+bool plan_ft(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, ft_plan& plan)
+{
+    if (!(N > 0 && D > 0 && D % 2 == 0))
+    {
+        return false;
+    }
+    for (int v = 0; v < kNumFtVariants; ++v)
+    {
+        const ft_variant& var = kFtVariants[v];
+        if (var.T != T || D > 512LL * var.KC)
+        {
+            continue;
+        }
+        const int64_t row_b = D * 8;
+        const int64_t avail = static_cast<int64_t>(smem_optin) - kFtHeaderSize;
+        // ~64 KiB stages of whole iterations; rows * T must be even (the Y tile starts on a 16-byte boundary)
+        int64_t rps = std::max<int64_t>(1, 65536 / (row_b + T * 8)) / var.RW * var.RW;
+        rps         = std::max<int64_t>(rps, var.RW);
+        if ((rps * T) % 2 != 0)
+        {
+            rps += var.RW;
+        }
+        const int64_t x_bytes = round_up(rps * row_b, 128);
+        const int64_t y_bytes = round_up(rps * T * 8, 128);
+        const int64_t stride  = x_bytes + y_bytes;
+        const int64_t stages  = std::min<int64_t>(kFtMaxStages, avail / stride);
+        if (stages < 2)
+        {
+            return false;
+        }
+        plan.variant        = v;
+        plan.rows_per_stage = static_cast<int>(rps);
+        plan.stages         = static_cast<int>(std::min<int64_t>(stages, 3)); // deeper rings bought nothing for T = 1
+        plan.stage_stride   = static_cast<int>(stride);
+        plan.y_offset       = static_cast<int>(x_bytes);
+        plan.smem_bytes     = static_cast<int>(kFtHeaderSize + plan.stages * stride);
+        plan.num_tiles      = (N + rps - 1) / rps;
+        plan.grid           = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+        return plan.grid > 0;
+    }
+    return false;
+}
 
 // launch geometry of the tensor-pipe kernels for an (N, D, T) problem
 struct mt_geometry
@@ -89,11 +150,12 @@ int env_int(const char* name, const int fallback)
     return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
 }
 
-// T in [2, 128] even (16-byte row copies of dL), D a multiple of 128; false when the shape is not covered
+// T in [2, 128], D even (rows of X start on 16-byte boundaries; dL rows are padded to an even stride); false when the
+// shape is not covered
 bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin,
              mt_geometry& geo)
 {
-    if (!(T >= 2 && T <= 128 && T % 2 == 0 && D % kMtBwdCols == 0 && D > 0 && N > 0))
+    if (!(T >= 2 && T <= 128 && D % 2 == 0 && D > 0 && N > 0))
     {
         return false;
     }
@@ -112,14 +174,14 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         fwd_stages = std::min<int64_t>(fwd_stages, forced); // tuning knob
     }
     // backward: dL tile rows padded to t_ld = 4 (mod 16) doubles, X tile rows to 132 doubles
-    int64_t t_ld = T;
+    int64_t t_ld = T + (T & 1);
     while (t_ld % 16 != 4)
     {
         t_ld += 2;
     }
     const int64_t bwd_stage  = (round_up(kMtBwdRows * t_ld, 16) + kMtBwdRows * kMtBwdLd) * 8;
     const int64_t bwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - 256) / bwd_stage);
-    const int64_t ctiles     = D / kMtBwdCols;
+    const int64_t ctiles     = (D + kMtBwdCols - 1) / kMtBwdCols;
     const int64_t chunks     = (N + kMtBwdRows - 1) / kMtBwdRows;
     const int64_t splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, sm_count / std::max<int64_t>(ctiles, 1)));
     if (fwd_stages < 2 || bwd_stages < 2 || ctiles > sm_count)
@@ -282,6 +344,9 @@ struct nb200_obj
     int     gen_blocks{0};
     int     gen_splits{0};
     int     gen_smem{0};
+    // few-target one-pass plan (vgrad_ft.cuh)
+    bool    use_ft{false};
+    ft_plan ft{};
     // many-target tensor-pipe plan (vgrad_mt.cuh)
     bool    use_mt{false};
     int     mt_variant{0}; // index into kMtVariants
@@ -431,8 +496,24 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         }
     }
 
-    // many-target tensor-pipe path
+    // few targets: one pass over X (forced_variant -4 skips it and takes the tensor-pipe pair, -3 the generic kernels)
+    obj->use_ft = false;
     obj->use_mt = false;
+    ft_plan few;
+    if (!force_generic && forced_variant != -3 && forced_variant != -4 && T >= 2 &&
+        plan_ft(N, D, T, data->sm_count, data->smem_optin, few))
+    {
+        const ft_variant& var = kFtVariants[few.variant];
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, few.smem_bytes));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, few.smem_bytes));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(few.grid) * (1 + T + T * D) * sizeof(double)));
+        NB200_CUDA_TRY(cudaDeviceSynchronize());
+        obj->ft     = few;
+        obj->use_ft = true;
+        return NB200_OK;
+    }
+
+    // many-target tensor-pipe path
     mt_geometry geo;
     if (!force_generic && forced_variant != -3 && plan_mt(N, D, T, data->sm_count, data->smem_optin, geo))
     {
@@ -451,8 +532,8 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(geo.fwd_grid) * (1 + T) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(geo.splits) * T * D * sizeof(double)));
-        NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * T * sizeof(double)));
-        NB200_CUDA_TRY(cudaMalloc(&obj->d_Wp, static_cast<size_t>(D / kMtBK) * T * kMtLd * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_dL, static_cast<size_t>(N) * (T + (T & 1)) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_Wp, static_cast<size_t>((D + kMtBK - 1) / kMtBK) * T * kMtLd * sizeof(double)));
         NB200_CUDA_TRY(cudaDeviceSynchronize());
         obj->use_mt = true;
         return NB200_OK;
@@ -690,6 +771,41 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
                                                    args, static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
         obj->launches += 1;
         return timing_end(obj);
+    }
+
+    if (obj->use_ft)
+    {
+        const ft_variant& var = kFtVariants[obj->ft.variant];
+        ft_params         f{};
+        f.X              = data->X;
+        f.Y              = data->Y;
+        f.W              = W;
+        f.b              = bias;
+        f.partials       = obj->d_partials;
+        f.N              = N;
+        f.num_tiles      = obj->ft.num_tiles;
+        f.D              = static_cast<int>(D);
+        f.rows_per_stage = obj->ft.rows_per_stage;
+        f.stages         = obj->ft.stages;
+        f.stage_stride   = obj->ft.stage_stride;
+        f.y_offset       = obj->ft.y_offset;
+        f.loss           = obj->loss;
+        f.loss_param     = obj->loss_param;
+        (want_grad ? var.grad : var.value)<<<obj->ft.grid, kFtThreads, obj->ft.smem_bytes, obj->stream>>>(f);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        status = timing_end(obj);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        const int64_t stride = 1 + T + T * D;
+        const int64_t cols   = want_grad ? stride : 1;
+        reduce_partials_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials, obj->ft.grid, stride, cols, obj->d_reduced);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        return finish ? enqueue_finish(obj, x_dev, n_global, gx_out, fx_out) : NB200_OK;
     }
 
     if (obj->use_mt)
@@ -1219,7 +1335,7 @@ int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj)
     NB200_REQUIRE(obj != nullptr && out_obj != nullptr, "objective: null argument");
     const int status = make_objective(obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
                                       obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
-                                      obj->use_t1 ? obj->t1.variant : (obj->use_mt ? -1 : -2), out_obj);
+                                      obj->use_t1 ? obj->t1.variant : (obj->use_ft ? -1 : (obj->use_mt ? -4 : -2)), out_obj);
     if (status == NB200_OK)
     {
         (*out_obj)->timing = obj->timing;
@@ -1541,6 +1657,14 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
                " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
                " smem=" + std::to_string(obj->t1.smem_bytes);
     }
+    else if (obj->use_ft)
+    {
+        const ft_variant& var = kFtVariants[obj->ft.variant];
+        text = "ft T=" + std::to_string(var.T) + " KC=" + std::to_string(var.KC) + " RW=" + std::to_string(var.RW) +
+               " grid=" + std::to_string(obj->ft.grid) + " rows_per_stage=" + std::to_string(obj->ft.rows_per_stage) +
+               " stages=" + std::to_string(obj->ft.stages) + " stage_bytes=" + std::to_string(obj->ft.stage_stride) +
+               " smem=" + std::to_string(obj->ft.smem_bytes);
+    }
     else if (obj->use_mt)
     {
         text = "dmma NT8=" + std::to_string(kMtVariants[obj->mt_variant].NT8) + " fwd_grid=" +
@@ -1626,7 +1750,7 @@ static int ensure_batch(nb200_obj* obj, const int64_t Kp)
     const size_t K = static_cast<size_t>(Kp);
     NB200_CUDA_TRY(cudaMalloc(&bs.d_x, K * (n + 2) * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_W, K * D * sizeof(double)));
-    NB200_CUDA_TRY(cudaMalloc(&bs.d_Wp, static_cast<size_t>(D / kMtBK) * K * kMtLd * sizeof(double)));
+    NB200_CUDA_TRY(cudaMalloc(&bs.d_Wp, static_cast<size_t>((D + kMtBK - 1) / kMtBK) * K * kMtLd * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_b, K * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_l, 2 * K * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_dL, static_cast<size_t>(N) * K * sizeof(double)));

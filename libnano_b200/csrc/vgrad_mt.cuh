@@ -37,10 +37,10 @@ struct mt_forward_params
     const double* Y;  // [N, T]
     const double* W;  // packed by mt_pack_weights_kernel: [D / 16][T][20] (k-chunk major, padded rows)
     const double* b;  // [T] device
-    double*       dL; // [N, T] (GRAD)
+    double*       dL; // [N, T + (T & 1)] (GRAD): even row stride, so that the backward moves rows as 16-byte copies
     double*       partials_fb; // [grid, 1 + T]
     int64_t       N;
-    int           D; // multiple of kMtBK
+    int           D; // even (rows start on 16-byte boundaries); the last k-chunk may be partial
     int           T;
     int           stages;
     int           loss;
@@ -55,11 +55,11 @@ struct mt_forward_params
 struct mt_backward_params
 {
     const double* X;           // [N, D]
-    const double* dL;          // [N, T]
+    const double* dL;          // [N, T + (T & 1)]
     double*       partials_gw; // [splits, T, D]
     int64_t       N;
-    int           D;      // multiple of kMtBwdCols
-    int           T;      // even
+    int           D;      // even; the last column tile may be partial
+    int           T;
     int           t_ld;   // shared row stride of the dL tile (>= T, = 4 mod 16)
     int           splits;
     int           stages;
@@ -72,15 +72,16 @@ struct mt_backward_params
 static __global__ void __launch_bounds__(256) mt_pack_weights_kernel(const double* __restrict__ W, const int T, const int D,
                                                               double* __restrict__ Wp)
 {
-    const int64_t total = static_cast<int64_t>(D / kMtBK) * T * kMtLd;
+    const int64_t total = static_cast<int64_t>((D + kMtBK - 1) / kMtBK) * T * kMtLd;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     {
-        const int     j  = static_cast<int>(i % kMtLd);
-        const int64_t r  = i / kMtLd;
-        const int     t  = static_cast<int>(r % T);
-        const int64_t kc = r / T;
-        Wp[i]            = (j < kMtBK) ? W[static_cast<int64_t>(t) * D + kc * kMtBK + j] : 0.0;
+        const int     j   = static_cast<int>(i % kMtLd);
+        const int64_t r   = i / kMtLd;
+        const int     t   = static_cast<int>(r % T);
+        const int64_t kc  = r / T;
+        const int64_t col = kc * kMtBK + j;
+        Wp[i]             = (j < kMtBK && col < D) ? W[static_cast<int64_t>(t) * D + col] : 0.0;
     }
 }
 
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
     const int     D      = p.D;
     const int     T      = p.T;
-    const int     kchunks = D / kMtBK;
+    const int     kchunks = (D + kMtBK - 1) / kMtBK; // the last one holds D - (kchunks - 1) * 16 features
     const int64_t tiles  = (p.N + kMtBM - 1) / kMtBM;
+    const int     dl_ld  = T + (T & 1);
 
     if (warp >= kMtWarps)
     {
@@ -175,10 +177,16 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                     mbar_arrive_expect_tx(full_bar + s, bytes);
                     bulk_copy_g2s(ws, p.W + static_cast<int64_t>(kc) * T * kMtLd, bytes, full_bar + s, policy_w);
                 }
+                // 16-byte chunks of this k-chunk that exist (D is even): the tail of the last k-chunk is not copied,
+                // the consumers mask those columns
+                const int valid = min(kChunks, (D - kc * kMtBK) / 2);
                 for (int c = pt; c < rows * kChunks; c += kMtProducerWarps * 32)
                 {
                     const int r = c / kChunks, j = c % kChunks;
-                    cp_async_16(xs + r * kMtLd + j * 2, xsrc + static_cast<int64_t>(r) * D + j * 2);
+                    if (j < valid)
+                    {
+                        cp_async_16(xs + r * kMtLd + j * 2, xsrc + static_cast<int64_t>(r) * D + j * 2);
+                    }
                 }
                 cp_async_arrive(full_bar + s);
             }
@@ -222,11 +230,14 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
             const double* ws = xs + kMtBM * kMtLd;
             const double* xa = xs + (warp * 16 + g) * kMtLd + tig;
             const double* wb = ws + g * kMtLd + tig;
+            const int kleft = D - kc * kMtBK; // features in this k-chunk (>= 16 except for the last one)
 #pragma unroll
             for (int kk = 0; kk < kMtBK / 4; ++kk)
             {
-                const double a0 = xa[kk * 4];
-                const double a1 = xa[8 * kMtLd + kk * 4];
+                // columns past D were not copied: whatever the stage holds there must not reach the accumulators
+                const bool   in = kk * 4 + tig < kleft;
+                const double a0 = in ? xa[kk * 4] : 0.0;
+                const double a1 = in ? xa[8 * kMtLd + kk * 4] : 0.0;
 #pragma unroll
                 for (int nt = 0; nt < NT8; ++nt)
                 {
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                         {
                             const double gv =
                                 __dsub_rn(__ddiv_rn(ex[k], sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y[k])));
-                            p.dL[row * T + t] = gv;
+                            p.dL[row * dl_ld + t] = gv;
                             gbacc[k] += gv;
                         }
                     }
@@ -337,12 +348,16 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                         lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
                         if (GRAD)
                         {
-                            p.dL[row * T + t] = gv;
+                            p.dL[row * dl_ld + t] = gv;
                             gbacc[k] += gv;
                         }
                     }
                 }
                 fsum += loss_post(p.loss, warp_allreduce_sum(sum));
+            }
+            if (GRAD && dl_ld != T && lane == 0)
+            {
+                p.dL[row * dl_ld + T] = 0.0; // the pad column of an odd T
             }
         }
         __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
@@ -398,8 +413,10 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
     const int T      = p.T;
     const int D      = p.D;
     const int t_ld   = p.t_ld;
-    const int ctiles = D / kMtBwdCols;
+    const int dl_ld  = T + (T & 1);
+    const int ctiles = (D + kMtBwdCols - 1) / kMtBwdCols;
     const int ct     = blockIdx.x % ctiles;
+    const int cols   = min(kMtBwdCols, D - ct * kMtBwdCols); // even; the last column tile may be partial
     const int split  = blockIdx.x / ctiles;
 
     // stage layout: dL tile [kMtBwdRows][t_ld] then X tile [kMtBwdRows][kMtBwdLd]; each part rounded to 128 bytes
@@ -445,14 +462,14 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
             double*       xs   = gs + dl_doubles;
             if (lane == 0)
             {
-                mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>(rows * (T + kMtBwdCols) * 8));
+                mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>(rows * (dl_ld + cols) * 8));
             }
             __syncwarp();
             if (lane < rows)
             {
-                bulk_copy_g2s(gs + lane * t_ld, p.dL + (row0 + lane) * T, T * 8, full_bar + s, policy_g);
-                bulk_copy_g2s(xs + lane * kMtBwdLd, p.X + (row0 + lane) * D + ct * kMtBwdCols, kMtBwdCols * 8,
-                              full_bar + s, policy_x);
+                bulk_copy_g2s(gs + lane * t_ld, p.dL + (row0 + lane) * dl_ld, dl_ld * 8, full_bar + s, policy_g);
+                bulk_copy_g2s(xs + lane * kMtBwdLd, p.X + (row0 + lane) * D + ct * kMtBwdCols, cols * 8, full_bar + s,
+                              policy_x);
             }
         }
         return;
@@ -509,9 +526,13 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
 #pragma unroll
             for (int j = 0; j < 2; ++j)
             {
+                // columns past the partial tile multiplied whatever the stage held: they are simply not stored
                 const int col = ct * kMtBwdCols + (2 * warp + j) * 8 + tig * 2;
-                *reinterpret_cast<double2*>(out + static_cast<int64_t>(t) * D + col) =
-                    make_double2(acc[mt][j][0], acc[mt][j][1]);
+                if (col < D)
+                {
+                    *reinterpret_cast<double2*>(out + static_cast<int64_t>(t) * D + col) =
+                        make_double2(acc[mt][j][0], acc[mt][j][1]);
+                }
             }
         }
     }

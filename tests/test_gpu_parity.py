@@ -387,10 +387,12 @@ def test_synthetic_config1_sizes(ctx, oracle):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# many-target tensor-pipe path (DMMA kernels, vgrad_mt.cuh): T even in [2, 128], D a multiple of 128
+# many-target tensor-pipe path (DMMA kernels, vgrad_mt.cuh): T in [2, 128], D even — partial last k-chunk (D % 16),
+# partial last column tile (D % 128), odd T (dL rows padded to an even stride), rows not a multiple of 128 / 16
 # ----------------------------------------------------------------------------------------------------------------
 MT_SHAPES = [(1000, 128, 2), (257, 256, 10), (4096, 1024, 100), (129, 2048, 16), (5000, 384, 128), (100, 128, 100),
-             (1, 128, 4), (2049, 512, 26)]
+             (1, 128, 4), (2049, 512, 26), (3000, 784, 10), (999, 100, 10), (500, 130, 3), (77, 18, 5), (40, 2, 2),
+             (1500, 54, 7), (333, 1000, 127), (2050, 14, 128)]
 
 
 @pytest.mark.parametrize("N,D,T", MT_SHAPES)
@@ -400,6 +402,7 @@ def test_many_target_tensor_path_parity(ctx, oracle, N, D, T, loss_id):
     if loss_id.startswith("m-"):
         Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
     function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    function.set_variant(-4)  # the tensor-pipe pair also where the few-target one-pass kernel would be chosen
     assert function.describe().startswith("dmma"), function.describe()
     fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
     # same input => same bits; and the shape-generic kernels agree
@@ -410,6 +413,55 @@ def test_many_target_tensor_path_parity(ctx, oracle, N, D, T, loss_id):
     g3 = np.empty_like(x)
     f3 = function(x, g3)
     assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# few targets: the one-pass kernel (vgrad_ft.cuh): T in {2, 3, 4, 5, 6, 8, 10}, even D <= 512 / 1024 / 2048
+# ----------------------------------------------------------------------------------------------------------------
+FT_SHAPES = [(1000, 128, 2), (257, 256, 10), (3000, 784, 10), (999, 100, 10), (500, 130, 3), (77, 18, 5), (40, 2, 2),
+             (1, 64, 4), (2, 512, 6), (4099, 1024, 8), (1537, 1000, 5), (900, 2048, 4), (333, 1500, 2), (65, 2000, 3),
+             (5000, 54, 6), (129, 512, 3)]
+
+
+@pytest.mark.parametrize("N,D,T", FT_SHAPES)
+@pytest.mark.parametrize("loss_id", ["s-classnll", "mse", "m-logistic", "m-hinge", "mae"])
+def test_few_target_one_pass_parity(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + 5 * D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):
+        Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    assert function.describe().startswith("ft"), function.describe()
+    fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
+    # same input => same bits; the tensor-pipe pair and the shape-generic kernels agree
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)
+    for variant, name in ((-4, "dmma"), (-3, "generic")):
+        function.set_variant(variant)
+        assert function.describe().startswith(name)
+        g3 = np.empty_like(x)
+        f3 = function(x, g3)
+        assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13, (variant, function.describe())
+
+
+def test_few_target_ragged_row_counts(ctx, oracle):
+    # row counts around the iteration (RW = 3 .. 16 rows) and stage boundaries, idle CTAs
+    for D, T in ((100, 10), (512, 2), (784, 3), (1024, 4)):
+        rng = np.random.default_rng(D + T)
+        counts = [1, 2, 3, 4, 5, 7, 9, 15, 17, 31, 33, 63, 65, 127, 129, 1183, 1185, 2371]
+        Xall = rng.uniform(-1, 1, (max(counts), D))
+        labels = rng.integers(0, T, max(counts))
+        Yall = -np.ones((max(counts), T))
+        Yall[np.arange(max(counts)), labels] = 1.0
+        x = rng.uniform(-1, 1, (D + 1) * T) / np.sqrt(D)
+        for N in counts:
+            X, Y = Xall[:N], Yall[:N]
+            function = gpu_function(ctx, X, Y, "s-classnll", 0.0, 1e-2)
+            assert function.describe().startswith("ft")
+            gx = np.empty_like(x)
+            fx = function(x, gx)
+            f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-classnll", x, l2=1e-2)
+            assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY, (N, D, T, function.describe())
+            assert rel_f(function(x), f_ref) <= PARITY
 
 
 def test_many_target_softmax_sample_of_config3(ctx, oracle):

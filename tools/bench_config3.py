@@ -20,6 +20,7 @@ def main():
     parser.add_argument("--targets", type=int, default=100)
     parser.add_argument("--steps", type=int, default=5)
     parser.add_argument("--generic", action="store_true")
+    parser.add_argument("--variant", type=int, default=-1, help="-1 heuristic, -3 generic, -4 tensor-pipe pair")
     parser.add_argument("--no-cublas", action="store_true")
     args = parser.parse_args()
 
@@ -31,6 +32,8 @@ def main():
     function = nb.LinearFunction(data, nb.Loss("s-classnll"), 0.0, 1e-2)
     if args.generic:
         function.set_variant(-3)
+    elif args.variant != -1:
+        function.set_variant(args.variant)
     x = np.random.default_rng(0).uniform(-1, 1, function.size()) / np.sqrt(D)
     gx = np.empty_like(x)
     function(x, gx)
@@ -44,7 +47,8 @@ def main():
             times.append(function.last_pass_ms())
         med = sorted(times)[len(times) // 2]
         result[name] = {"ms_med": round(med, 3), "ms_min": round(min(times), 3), "tflops": round(flops / med / 1e9, 2),
-                        "x_gbs": round((2 if name == "vgrad" else 1) * 8.0 * N * D / med / 1e6, 1), "f": fx}
+                        "x_gbs": round((2 if name == "vgrad" else 1) * 8.0 * N * D / med / 1e6, 1),
+                        "x_once_gbs": round(8.0 * N * D / med / 1e6, 1), "f": fx}
 
     if not args.no_cublas:
         import torch
