@@ -36,7 +36,8 @@ using ft_kernel_t = void (*)(const ft_params);
 
 struct ft_variant
 {
-    int         T, KC, RW; // targets (exact), 64 * KC columns per warp (D <= 512 * KC), rows per iteration
+    int         T, KC, RW, NS; // targets (exact), 64 * KC columns per warp, rows per iteration, alternating warp sets
+                               // (the 8 / NS warps of a set cover D <= 512 * KC / NS columns)
     ft_kernel_t grad;
     ft_kernel_t value;
 };

@@ -79,6 +79,12 @@ int               g_num_mt_variants = 0;
 const mt_variant* const kMtVariants    = mt_variants(&g_num_mt_variants);
 const int               kNumMtVariants = g_num_mt_variants;
 
+int env_int(const char* name, const int fallback)
+{
+    const char* value = std::getenv(name);
+    return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
+}
+
 // launch geometry of the few-target one-pass kernel (vgrad_ft.cuh)
 struct ft_plan
 {
@@ -95,6 +101,7 @@ struct ft_plan
 // an exact-T variant whose 512 * KC columns cover D (even D: rows start on 16-byte boundaries); false otherwise
 bool plan_ft(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, ft_plan& plan)
 {
+    static const bool skip_two_sets = env_int("NB200_FT_ONE_SET", 0) != 0; // A/B knob (tools/gpu_round40.sh)
     if (!(N > 0 && D > 0 && D % 2 == 0))
     {
         return false;
@@ -102,7 +109,7 @@ bool plan_ft(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     for (int v = 0; v < kNumFtVariants; ++v)
     {
         const ft_variant& var = kFtVariants[v];
-        if (var.T != T || D > 512LL * var.KC)
+        if (var.T != T || D > 512LL * var.KC / var.NS || (skip_two_sets && var.NS > 1))
         {
             continue;
         }
@@ -143,12 +150,6 @@ struct mt_geometry
     int fwd_grid{0}, fwd_stages{0}, fwd_smem{0};
     int splits{0}, bwd_grid{0}, bwd_stages{0}, bwd_smem{0}, t_ld{0};
 };
-
-int env_int(const char* name, const int fallback)
-{
-    const char* value = std::getenv(name);
-    return (value != nullptr && *value != '\0') ? std::atoi(value) : fallback;
-}
 
 // T in [2, 128], D even (rows of X start on 16-byte boundaries; dL rows are padded to an even stride); false when the
 // shape is not covered
@@ -1661,6 +1662,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     {
         const ft_variant& var = kFtVariants[obj->ft.variant];
         text = "ft T=" + std::to_string(var.T) + " KC=" + std::to_string(var.KC) + " RW=" + std::to_string(var.RW) +
+               " NS=" + std::to_string(var.NS) +
                " grid=" + std::to_string(obj->ft.grid) + " rows_per_stage=" + std::to_string(obj->ft.rows_per_stage) +
                " stages=" + std::to_string(obj->ft.stages) + " stage_bytes=" + std::to_string(obj->ft.stage_stride) +
                " smem=" + std::to_string(obj->ft.smem_bytes);

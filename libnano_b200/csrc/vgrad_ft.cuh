@@ -32,7 +32,7 @@ constexpr int kFtThreads       = (kFtWarps + kFtProducerWarps) * 32;
 constexpr int kFtMaxStages     = 8;
 constexpr int kFtExchange      = 128;                                  // [2][kFtWarps][32] doubles
 constexpr int kFtScratch       = kFtExchange + 2 * kFtWarps * 32 * 8;  // [kFtWarps][32] doubles (dL of the iteration)
-constexpr int kFtTail          = kFtScratch + kFtWarps * 32 * 8;       // [2][32] doubles (loss / dL sums)
+constexpr int kFtTail          = kFtScratch + kFtWarps * 32 * 8;       // [sets][2][32] doubles (loss / dL sums)
 constexpr int kFtHeaderSize    = 8192;
 
 struct ft_params
@@ -65,9 +65,13 @@ __host__ __device__ constexpr int ft_pow2_ceil(const int value)
     return p;
 }
 
-template <int T, int KC, int RW, bool GRAD>
+template <int T, int KC, int RW, int NS, bool GRAD>
 __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params p)
 {
+    // NS sets of WPS consumer warps take the iterations in turn (NS = 2: while one set is in its reduction / loss
+    // chain the other one multiplies); the warps of a set share every row of their iterations
+    constexpr int WPS = kFtWarps / NS;
+    static_assert(NS == 1 || NS == 2, "one or two alternating warp sets");
     constexpr int PAIRS = RW * T;               // (row, target) pairs of one iteration
     constexpr int P     = ft_pow2_ceil(PAIRS);  // padded to a power of two for the halving reduction
     constexpr int SHIFT = 5 - log2_of(P);       // pair q lives in lanes [q << SHIFT, (q + 1) << SHIFT)
@@ -130,7 +134,9 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
 
     // ===== consumer warps =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
-    const int cbase = warp * CPW;
+    const int set   = warp / WPS;
+    const int wis   = warp % WPS; // warp in set: which column slice
+    const int cbase = wis * CPW;
 
     // this lane's slice of W and of the gradient accumulator
     double w[T][2 * KC];
@@ -162,6 +168,8 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
     int      stage_index = 0;
     uint32_t phase       = 0;
     int      parity      = 0;
+    int      turn        = 0; // whose iteration comes next (iterations are dealt round-robin over the sets)
+    double*  set_exchange = exchange + static_cast<int64_t>(set) * (2 * WPS * 32);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
     {
         const int s = stage_index;
@@ -175,8 +183,33 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
         const double*        ys    = reinterpret_cast<const double*>(stage + p.y_offset);
         const int            rows  = static_cast<int>(min(rps, p.N - tile * rps));
 
-        for (int i = 0; i < rows; i += RW)
+        // the last iteration of this tile that belongs to this warp's set: the stage is released right after its
+        // rows are in registers (at once when the set has no iteration in the tile)
+        const int n_iter   = (rows + RW - 1) / RW;
+        int       last_own = n_iter - 1;
+        if constexpr (NS > 1)
         {
+            last_own -= ((turn + n_iter - 1) % NS == set) ? 0 : 1; // NS == 2: the last or the one before
+            if (last_own < 0)
+            {
+                if (lane == 0)
+                {
+                    mbar_arrive(empty_bar + s);
+                }
+            }
+        }
+
+        for (int i = 0, j = 0; i < rows; i += RW, ++j)
+        {
+            if constexpr (NS > 1)
+            {
+                const bool mine_now = turn == set;
+                turn                = (turn + 1 == NS) ? 0 : turn + 1;
+                if (!mine_now)
+                {
+                    continue;
+                }
+            }
             const int nrows = min(RW, rows - i);
 
             // RW row slices -> registers
@@ -201,7 +234,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
             const double y = (owner && my_r < nrows) ? ys[(i + my_r) * T + my_t] : 0.0;
 
             // the stage can be refilled as soon as its last rows (and targets) are in registers
-            if (i + RW >= rows)
+            if (j == last_own)
             {
                 __syncwarp();
                 if (lane == 0)
@@ -245,17 +278,17 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
             }
 
             // combine the eight column slices in warp order
-            double* slot = exchange + static_cast<int64_t>(parity) * (kFtWarps * 32);
+            double* slot = set_exchange + static_cast<int64_t>(parity) * (WPS * 32);
             if (owner)
             {
-                slot[warp * 32 + my_pair] = mine;
+                slot[wis * 32 + my_pair] = mine;
             }
-            named_bar_sync(1, kFtWarps * 32);
+            named_bar_sync(1 + set, WPS * 32);
             mine = 0.0;
             if (my_pair < PAIRS)
             {
 #pragma unroll
-                for (int q = 0; q < kFtWarps; ++q)
+                for (int q = 0; q < WPS; ++q)
                 {
                     mine += slot[q * 32 + my_pair];
                 }
@@ -333,6 +366,51 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
 
     // ----- this CTA's partial row: [loss | sum dL (T) | sum dL x^T (T * D)] -----
     double* out = p.partials + static_cast<int64_t>(blockIdx.x) * (1 + T + static_cast<int64_t>(T) * D);
+    if constexpr (NS > 1)
+    {
+        // both sets cover the same columns: set 1 parks its gradient slices in the (now idle) stage area, set 0 adds
+        named_bar_sync(15, kFtWarps * 32); // every issued copy has been consumed
+        double* park = reinterpret_cast<double*>(stage_base);
+        if (GRAD && set == 1)
+        {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+            {
+#pragma unroll
+                for (int k = 0; k < 2 * KC; ++k)
+                {
+                    park[(static_cast<int64_t>(wis) * T * 2 * KC + t * 2 * KC + k) * 32 + lane] = g[t][k];
+                }
+            }
+        }
+        if (wis == 0 && (lane & ((1 << SHIFT) - 1)) == 0)
+        {
+            tail[set * 64 + (lane >> SHIFT)]      = owner ? fsum : 0.0;
+            tail[set * 64 + 32 + (lane >> SHIFT)] = owner ? gbsum : 0.0;
+        }
+        named_bar_sync(15, kFtWarps * 32);
+        if (set == 1)
+        {
+            return;
+        }
+        if constexpr (GRAD)
+        {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+            {
+#pragma unroll
+                for (int k = 0; k < 2 * KC; ++k)
+                {
+                    g[t][k] += park[(static_cast<int64_t>(wis) * T * 2 * KC + t * 2 * KC + k) * 32 + lane];
+                }
+            }
+        }
+    }
+    else if (warp == 0 && (lane & ((1 << SHIFT) - 1)) == 0)
+    {
+        tail[lane >> SHIFT]        = owner ? fsum : 0.0;
+        tail[32 + (lane >> SHIFT)] = owner ? gbsum : 0.0;
+    }
     if constexpr (GRAD)
     {
 #pragma unroll
@@ -354,28 +432,29 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
     }
     if (warp == 0)
     {
-        // every warp carries identical loss / dL sums: warp 0 folds its pair slots in pair order
-        if ((lane & ((1 << SHIFT) - 1)) == 0)
-        {
-            tail[lane >> SHIFT]      = owner ? fsum : 0.0;
-            tail[32 + (lane >> SHIFT)] = owner ? gbsum : 0.0;
-        }
+        // the warps of a set carry identical loss / dL sums: warp 0 folds the pair slots of every set in order
         __syncwarp();
         if (lane == 0)
         {
             double f = 0.0;
-            for (int q = 0; q < PAIRS; ++q)
+            for (int a = 0; a < NS; ++a)
             {
-                f += tail[q];
+                for (int q = 0; q < PAIRS; ++q)
+                {
+                    f += tail[a * 64 + q];
+                }
             }
             out[0] = f;
         }
         if (GRAD && lane < T)
         {
             double b = 0.0;
-            for (int r = 0; r < RW; ++r)
+            for (int a = 0; a < NS; ++a)
             {
-                b += tail[32 + r * T + lane];
+                for (int r = 0; r < RW; ++r)
+                {
+                    b += tail[a * 64 + 32 + r * T + lane];
+                }
             }
             out[1 + lane] = b;
         }
