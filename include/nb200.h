@@ -213,8 +213,8 @@ NB200_API int nb200_objective_host_profile(nb200_obj* obj, double* stage_us, dou
                                            int64_t* calls, int reset);
 
 /* Tuning knob: variant id of the fused T == 1 kernel (see DESIGN.md "kernel variants"), -1 = heuristic,
- * -2 = force the shape-generic kernels, -3 = shape-generic kernels for T >= 2 only, -4 = the tensor-pipe pair for
- * T >= 2 even where the few-target one-pass kernel applies. */
+ * -2 = force the shape-generic kernels, -3 = shape-generic kernels for T >= 2 only, -4 = the two-pass tensor-pipe
+ * pair for T >= 2 even where a one-pass kernel applies, -5 / -6 = the one-pass tensor-pipe / CUDA-core kernel. */
 NB200_API int nb200_objective_set_variant(nb200_obj* obj, int variant);
 
 /* Human-readable launch plan (kernel variant, grid, stages, shared memory) into buffer[size]. */

@@ -6,6 +6,7 @@
 // variants changed the SASS of mt_backward_kernel and cost config 3 15 %; profiles/README.md).
 #pragma once
 
+#include "vgrad_fd.cuh"
 #include "vgrad_ft.cuh"
 #include "vgrad_mt.cuh"
 #include "vgrad_t1.cuh"
@@ -40,6 +41,16 @@ struct ft_variant
                                // (the 8 / NS warps of a set cover D <= 512 * KC / NS columns)
     ft_kernel_t grad;
     ft_kernel_t value;
+};
+
+using fd_kernel_t = void (*)(const fd_params);
+
+struct fd_variant
+{
+    int         NT8, NS8; // covers T <= 8 * NT8 and D <= 64 * NS8
+    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader)
+    fd_kernel_t grad;
+    fd_kernel_t value;
 };
 
 // X(V, KC, WS, NCW, RW, ALT). The variant id is the position in A, B, C, D concatenated.
@@ -78,4 +89,5 @@ const t1_variant* t1_group_c(int* count);
 const t1_variant* t1_group_d(int* count);
 const mt_variant* mt_variants(int* count);
 const ft_variant* ft_variants(int* count);
+const fd_variant* fd_variants(int* count);
 } // namespace nb200

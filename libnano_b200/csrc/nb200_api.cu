@@ -71,6 +71,10 @@ const t1_variant* const kT1Variants    = kT1Table.entries.data();
 const int               kNumT1Variants = static_cast<int>(kT1Table.entries.size());
 constexpr int           kNumT1Heuristic = 17; // entries scanned by the fall-back heuristic
 
+int               g_num_fd_variants = 0;
+const fd_variant* const kFdVariants    = fd_variants(&g_num_fd_variants);
+const int               kNumFdVariants = g_num_fd_variants;
+
 int               g_num_ft_variants = 0;
 const ft_variant* const kFtVariants    = ft_variants(&g_num_ft_variants);
 const int               kNumFtVariants = g_num_ft_variants;
@@ -138,6 +142,60 @@ bool plan_ft(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         plan.smem_bytes     = static_cast<int>(kFtHeaderSize + plan.stages * stride);
         plan.num_tiles      = (N + rps - 1) / rps;
         plan.grid           = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+        return plan.grid > 0;
+    }
+    return false;
+}
+
+// launch geometry of the one-pass tensor-pipe kernel for a handful of targets (vgrad_fd.cuh)
+struct fd_plan
+{
+    int     variant{0};
+    int     grid{0};
+    int     slice{0}, ld{0};
+    int     stages{0};
+    int     stage_stride{0}, y_offset{0}, w_offset{0}, stage_offset{0};
+    int     smem_bytes{0};
+    int64_t num_tiles{0};
+};
+
+// W (T x ld) and at least two stages of 8 padded rows must fit next to the header; false otherwise
+bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan)
+{
+    if (!(N > 0 && D > 0 && D % 2 == 0 && T >= 2))
+    {
+        return false;
+    }
+    for (int v = 0; v < kNumFdVariants; ++v)
+    {
+        const fd_variant& var = kFdVariants[v];
+        if (8 * var.NT8 < T || 64LL * var.NS8 < D)
+        {
+            continue;
+        }
+        const int64_t slice    = 8LL * var.NS8;
+        const int64_t ld       = kFdWarps * slice + 4; // = 4 mod 16: conflict-free 64-bit fragment loads
+        const int64_t w_bytes  = round_up(T * ld * 8, 128);
+        const int64_t x_bytes  = kFdRows * ld * 8;
+        const int64_t y_bytes  = round_up(kFdRows * T * 8, 128);
+        const int64_t stride   = round_up(x_bytes + y_bytes, 128);
+        const int64_t offset   = var.header + w_bytes;
+        const int64_t stages   = std::min<int64_t>(kFdMaxStages, (smem_optin - offset) / stride);
+        if (stages < 2)
+        {
+            return false;
+        }
+        plan.variant      = v;
+        plan.slice        = static_cast<int>(slice);
+        plan.ld           = static_cast<int>(ld);
+        plan.stages       = static_cast<int>(stages);
+        plan.stage_stride = static_cast<int>(stride);
+        plan.y_offset     = static_cast<int>(x_bytes);
+        plan.w_offset     = var.header;
+        plan.stage_offset = static_cast<int>(offset);
+        plan.smem_bytes   = static_cast<int>(offset + stages * stride);
+        plan.num_tiles    = (N + kFdRows - 1) / kFdRows;
+        plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
         return plan.grid > 0;
     }
     return false;
@@ -345,9 +403,11 @@ struct nb200_obj
     int     gen_blocks{0};
     int     gen_splits{0};
     int     gen_smem{0};
-    // few-target one-pass plan (vgrad_ft.cuh)
+    // few-target one-pass plans (vgrad_ft.cuh: CUDA cores; vgrad_fd.cuh: tensor pipe)
     bool    use_ft{false};
     ft_plan ft{};
+    bool    use_fd{false};
+    fd_plan fd{};
     // many-target tensor-pipe plan (vgrad_mt.cuh)
     bool    use_mt{false};
     int     mt_variant{0}; // index into kMtVariants
@@ -497,11 +557,30 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         }
     }
 
-    // few targets: one pass over X (forced_variant -4 skips it and takes the tensor-pipe pair, -3 the generic kernels)
+    // few targets: one pass over X. forced_variant: -3 the generic kernels, -4 the two-pass tensor-pipe pair, -5 the
+    // one-pass tensor-pipe kernel, -6 the one-pass CUDA-core kernel; heuristic: CUDA cores up to T = 4 (HBM-bound
+    // there), the tensor pipe from T = 5 (profiles/r01_few_targets_*.jsonl)
     obj->use_ft = false;
+    obj->use_fd = false;
     obj->use_mt = false;
+    const bool one_pass = !force_generic && forced_variant != -3 && forced_variant != -4 && T >= 2;
+    fd_plan    handful;
+    if (one_pass && forced_variant != -6 && ((T >= 5 && D > 256) || forced_variant == -5) &&
+        plan_fd(N, D, T, data->sm_count, data->smem_optin, handful))
+    {
+        const fd_variant& var = kFdVariants[handful.variant];
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, handful.smem_bytes));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, handful.smem_bytes));
+        NB200_CUDA_TRY(
+            cudaMalloc(&obj->d_partials, static_cast<size_t>(handful.grid) * (1 + T + T * D) * sizeof(double)));
+        NB200_CUDA_TRY(cudaDeviceSynchronize());
+        obj->fd     = handful;
+        obj->use_fd = true;
+        return NB200_OK;
+    }
     ft_plan few;
-    if (!force_generic && forced_variant != -3 && forced_variant != -4 && T >= 2 &&
+    // (rows of 2 KiB or less with five or more targets: the two-pass pair is faster than either one-pass kernel)
+    if (one_pass && forced_variant != -5 && (T <= 4 || D > 256 || forced_variant == -6) &&
         plan_ft(N, D, T, data->sm_count, data->smem_optin, few))
     {
         const ft_variant& var = kFtVariants[few.variant];
@@ -772,6 +851,45 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
                                                    args, static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
         obj->launches += 1;
         return timing_end(obj);
+    }
+
+    if (obj->use_fd)
+    {
+        const fd_variant& var = kFdVariants[obj->fd.variant];
+        fd_params         f{};
+        f.X            = data->X;
+        f.Y            = data->Y;
+        f.W            = W;
+        f.b            = bias;
+        f.partials     = obj->d_partials;
+        f.N            = N;
+        f.num_tiles    = obj->fd.num_tiles;
+        f.D            = static_cast<int>(D);
+        f.T            = static_cast<int>(T);
+        f.slice        = obj->fd.slice;
+        f.ld           = obj->fd.ld;
+        f.stages       = obj->fd.stages;
+        f.stage_stride = obj->fd.stage_stride;
+        f.y_offset     = obj->fd.y_offset;
+        f.w_offset     = obj->fd.w_offset;
+        f.stage_offset = obj->fd.stage_offset;
+        f.loss         = obj->loss;
+        f.loss_param   = obj->loss_param;
+        (want_grad ? var.grad : var.value)<<<obj->fd.grid, kFdThreads, obj->fd.smem_bytes, obj->stream>>>(f);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        status = timing_end(obj);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        const int64_t stride = 1 + T + T * D;
+        const int64_t cols   = want_grad ? stride : 1;
+        reduce_partials_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, obj->stream>>>(
+            obj->d_partials, obj->fd.grid, stride, cols, obj->d_reduced);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        return finish ? enqueue_finish(obj, x_dev, n_global, gx_out, fx_out) : NB200_OK;
     }
 
     if (obj->use_ft)
@@ -1336,7 +1454,7 @@ int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj)
     NB200_REQUIRE(obj != nullptr && out_obj != nullptr, "objective: null argument");
     const int status = make_objective(obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
                                       obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
-                                      obj->use_t1 ? obj->t1.variant : (obj->use_ft ? -1 : (obj->use_mt ? -4 : -2)), out_obj);
+                                      obj->use_t1 ? obj->t1.variant : (obj->use_fd ? -5 : (obj->use_ft ? -6 : (obj->use_mt ? -4 : -2))), out_obj);
     if (status == NB200_OK)
     {
         (*out_obj)->timing = obj->timing;
@@ -1657,6 +1775,14 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
                " grid=" + std::to_string(obj->t1.grid) + " rows_per_stage=" + std::to_string(obj->t1.rows_per_stage) +
                " stages=" + std::to_string(obj->t1.stages) + " stage_bytes=" + std::to_string(obj->t1.stage_stride) +
                " smem=" + std::to_string(obj->t1.smem_bytes);
+    }
+    else if (obj->use_fd)
+    {
+        const fd_variant& var = kFdVariants[obj->fd.variant];
+        text = "fd NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " grid=" +
+               std::to_string(obj->fd.grid) + " ld=" + std::to_string(obj->fd.ld) + " stages=" +
+               std::to_string(obj->fd.stages) + " stage_bytes=" + std::to_string(obj->fd.stage_stride) +
+               " smem=" + std::to_string(obj->fd.smem_bytes);
     }
     else if (obj->use_ft)
     {

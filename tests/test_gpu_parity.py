@@ -430,6 +430,7 @@ def test_few_target_one_pass_parity(ctx, oracle, N, D, T, loss_id):
     if loss_id.startswith("m-"):
         Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
     function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    function.set_variant(-6)  # the CUDA-core one-pass kernel also where the tensor-pipe one would be chosen (T >= 5)
     assert function.describe().startswith("ft"), function.describe()
     fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
     # same input => same bits; the tensor-pipe pair and the shape-generic kernels agree
@@ -456,7 +457,54 @@ def test_few_target_ragged_row_counts(ctx, oracle):
         for N in counts:
             X, Y = Xall[:N], Yall[:N]
             function = gpu_function(ctx, X, Y, "s-classnll", 0.0, 1e-2)
+            function.set_variant(-6)
             assert function.describe().startswith("ft")
+            gx = np.empty_like(x)
+            fx = function(x, gx)
+            f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-classnll", x, l2=1e-2)
+            assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY, (N, D, T, function.describe())
+            assert rel_f(function(x), f_ref) <= PARITY
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# a handful of targets: the one-pass tensor-pipe kernel (vgrad_fd.cuh): T <= 16, even D <= 1024 (W must fit in
+# shared memory next to two stages)
+# ----------------------------------------------------------------------------------------------------------------
+FD_SHAPES = [(3000, 784, 10), (999, 100, 10), (77, 18, 5), (40, 2, 2), (1, 64, 4), (2, 512, 6), (4099, 1024, 8),
+             (1537, 1000, 5), (129, 512, 16), (2051, 832, 13), (500, 130, 3), (65, 640, 15), (1000, 128, 7)]
+
+
+@pytest.mark.parametrize("N,D,T", FD_SHAPES)
+@pytest.mark.parametrize("loss_id", ["s-classnll", "mse", "m-logistic", "m-hinge", "mae"])
+def test_handful_of_targets_one_pass_tensor_parity(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + 7 * D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):
+        Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    function.set_variant(-5)
+    assert function.describe().startswith("fd"), function.describe()
+    fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
+    function.set_variant(-3)
+    g3 = np.empty_like(x)
+    f3 = function(x, g3)
+    assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+def test_handful_of_targets_ragged_row_counts_and_heuristic(ctx, oracle):
+    for D, T in ((300, 10), (784, 10), (512, 16)):
+        rng = np.random.default_rng(D + T)
+        counts = [1, 2, 7, 8, 9, 15, 17, 63, 65, 1183, 1185, 2371]
+        Xall = rng.uniform(-1, 1, (max(counts), D))
+        labels = rng.integers(0, T, max(counts))
+        Yall = -np.ones((max(counts), T))
+        Yall[np.arange(max(counts)), labels] = 1.0
+        x = rng.uniform(-1, 1, (D + 1) * T) / np.sqrt(D)
+        for N in counts:
+            X, Y = Xall[:N], Yall[:N]
+            function = gpu_function(ctx, X, Y, "s-classnll", 0.0, 1e-2)
+            assert function.describe().startswith("fd"), function.describe()  # the heuristic choice from T = 5
             gx = np.empty_like(x)
             fx = function(x, gx)
             f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-classnll", x, l2=1e-2)
