@@ -565,7 +565,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     obj->use_mt = false;
     const bool one_pass = !force_generic && forced_variant != -3 && forced_variant != -4 && T >= 2;
     fd_plan    handful;
-    if (one_pass && forced_variant != -6 && ((T >= 5 && D > 256) || forced_variant == -5) &&
+    if (one_pass && forced_variant != -6 && ((T >= 5 && D >= 200) || forced_variant == -5) &&
         plan_fd(N, D, T, data->sm_count, data->smem_optin, handful))
     {
         const fd_variant& var = kFdVariants[handful.variant];
@@ -579,8 +579,8 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         return NB200_OK;
     }
     ft_plan few;
-    // (rows of 2 KiB or less with five or more targets: the two-pass pair is faster than either one-pass kernel)
-    if (one_pass && forced_variant != -5 && (T <= 4 || D > 256 || forced_variant == -6) &&
+    // (rows shorter than ~1.6 KiB with five or more targets: the two-pass pair is faster than either one-pass kernel)
+    if (one_pass && forced_variant != -5 && (T <= 4 || D >= 200 || forced_variant == -6) &&
         plan_ft(N, D, T, data->sm_count, data->smem_optin, few))
     {
         const ft_variant& var = kFtVariants[few.variant];

@@ -56,13 +56,16 @@ struct fd_params
     double        loss_param;
 };
 
-// shared memory header: barriers [0, 128) | exchange [2][8 warps][8][TP] doubles | per-warp dL tiles [8][8][kFdLdd]
+// shared memory header: barriers [0, 128) | exchange [2][8 warps][8][TPS] doubles | per-warp dL tiles [8][8][kFdLdd]
 template <int NT8>
 struct fd_layout
 {
     static constexpr int TP        = 8 * NT8;
+    // row stride of the exchange tiles: 128-bit accesses go a quarter warp (rows g, g + 1) at a time, so the stride
+    // must be 4 (mod 8) in 16-byte units
+    static constexpr int TPS       = (NT8 == 1) ? 8 : TP + 8;
     static constexpr int kExchange = 128;
-    static constexpr int kDl       = kExchange + 2 * kFdWarps * kFdRows * TP * 8;
+    static constexpr int kDl       = kExchange + 2 * kFdWarps * kFdRows * TPS * 8;
     static constexpr int kHeader   = (kDl + kFdWarps * kFdRows * kFdLdd * 8 + 127) / 128 * 128;
 };
 
@@ -72,7 +75,7 @@ template <int NT8, int NS8, bool GRAD> // NS8: n8 column tiles per warp slice (s
 __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params p)
 {
     using L          = fd_layout<NT8>;
-    constexpr int TP = L::TP;
+    constexpr int TPS = L::TPS;
 
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                 t_in[nt] = nt * 8 + g < T;
             }
             static_assert((2 * NS8) % CH == 0, "the k-steps of a slice must split evenly over the chains");
-#pragma unroll 2
+#pragma unroll 4
             for (int kk = 0; kk < 2 * NS8; kk += CH) // slice / 4 k-steps, CH at a time
             {
 #pragma unroll
@@ -258,33 +261,26 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                 acc[nt][1] = s1;
             }
         }
-        // exchange: every warp ends up with the full outputs in fragment layout, summed in warp order
-        double* slot = exchange + static_cast<int64_t>(parity) * (kFdWarps * kFdRows * TP);
-#pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
+        // the rows' second use — the B fragments of the backward product — is fetched into registers now, together
+        // with the targets, so that the stage goes back to the producer before the exchange / loss / backward phase
+        // (with W resident only two or three stages fit: holding one for the whole tile exposed the HBM latency)
+        // Measured: + 5-13 % with two target tiles (T > 8), - 8 % with one, where it stays at the end of the tile.
+        constexpr bool EARLY = NT8 > 1;
+        double         xb[kFdRows / 4][NS8];
+        if constexpr (GRAD && EARLY)
         {
-            *reinterpret_cast<double2*>(slot + (warp * kFdRows + g) * TP + nt * 8 + tig * 2) =
-                make_double2(acc[nt][0], acc[nt][1]);
-        }
-        named_bar_sync(1, kFdWarps * 32);
-        double o[NT8][2];
 #pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
-        {
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < kFdWarps; ++q)
+            for (int kk = 0; kk < kFdRows / 4; ++kk)
             {
-                const double2 v = *reinterpret_cast<const double2*>(slot + (q * kFdRows + g) * TP + nt * 8 + tig * 2);
-                s0 += v.x;
-                s1 += v.y;
+                const int     r   = kk * 4 + tig;
+                const double* src = xs + r * ld + c0 + g;
+#pragma unroll
+                for (int ns = 0; ns < NS8; ++ns)
+                {
+                    xb[kk][ns] = (r < rows) ? src[ns * 8] : 0.0; // stale rows: 0 x NaN would poison the sums
+                }
             }
-            o[nt][0] = s0 + bias[nt][0]; // product first, then + bias (src/linear/util.cpp:19-20)
-            o[nt][1] = s1 + bias[nt][1];
         }
-        parity ^= 1;
-
-        // ----- loss + dL from the fragments: lane (g, tig) holds row g, targets 8 nt + 2 tig + {0, 1} -----
         const bool row_ok = g < rows;
         double     y[NT8][2];
 #pragma unroll
@@ -297,6 +293,42 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                 y[nt][j]    = (row_ok && t < T) ? ys[g * T + t] : 0.0;
             }
         }
+        if constexpr (EARLY || !GRAD)
+        {
+            __syncwarp();
+            if (lane == 0)
+            {
+                mbar_arrive(empty_bar + s);
+            }
+        }
+
+        // exchange: every warp ends up with the full outputs in fragment layout, summed in warp order
+        double* slot = exchange + static_cast<int64_t>(parity) * (kFdWarps * kFdRows * TPS);
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+            *reinterpret_cast<double2*>(slot + (warp * kFdRows + g) * TPS + nt * 8 + tig * 2) =
+                make_double2(acc[nt][0], acc[nt][1]);
+        }
+        named_bar_sync(1, kFdWarps * 32);
+        double o[NT8][2];
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < kFdWarps; ++q)
+            {
+                const double2 v = *reinterpret_cast<const double2*>(slot + (q * kFdRows + g) * TPS + nt * 8 + tig * 2);
+                s0 += v.x;
+                s1 += v.y;
+            }
+            o[nt][0] = s0 + bias[nt][0]; // product first, then + bias (src/linear/util.cpp:19-20)
+            o[nt][1] = s1 + bias[nt][1];
+        }
+        parity ^= 1;
+
+        // ----- loss + dL from the fragments: lane (g, tig) holds row g, targets 8 nt + 2 tig + {0, 1} -----
         double dl[NT8][2];
 #pragma unroll
         for (int nt = 0; nt < NT8; ++nt)
@@ -396,9 +428,8 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 #pragma unroll
             for (int kk = 0; kk < kFdRows / 4; ++kk)
             {
-                const int     r  = kk * 4 + tig;
-                const double* xb = xs + r * ld + c0 + g;
-                double        a[NT8];
+                const int r = kk * 4 + tig;
+                double    a[NT8];
 #pragma unroll
                 for (int mt = 0; mt < NT8; ++mt)
                 {
@@ -407,7 +438,15 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 #pragma unroll
                 for (int ns = 0; ns < NS8; ++ns)
                 {
-                    const double bv = (r < rows) ? xb[ns * 8] : 0.0; // stale rows: 0 x NaN would poison the sums
+                    double bv;
+                    if constexpr (EARLY)
+                    {
+                        bv = xb[kk][ns];
+                    }
+                    else
+                    {
+                        bv = (r < rows) ? xs[r * ld + c0 + g + ns * 8] : 0.0; // stale rows: 0 x NaN would poison
+                    }
 #pragma unroll
                     for (int mt = 0; mt < NT8; ++mt)
                     {
@@ -416,10 +455,13 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0)
+        if constexpr (GRAD && !EARLY)
         {
-            mbar_arrive(empty_bar + s);
+            __syncwarp();
+            if (lane == 0)
+            {
+                mbar_arrive(empty_bar + s);
+            }
         }
     }
 
