@@ -47,7 +47,7 @@ using fd_kernel_t = void (*)(const fd_params);
 
 struct fd_variant
 {
-    int         NT8, NS8; // covers T <= 8 * NT8 and D <= 64 * NS8
+    int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8
     int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader)
     fd_kernel_t grad;
     fd_kernel_t value;

@@ -5,13 +5,17 @@ namespace nb200
 {
 namespace
 {
-#define NB200_FD_ENTRY(NT8, NS8)                                                                                       \
-    fd_variant{NT8, NS8, fd_layout<NT8>::kHeader, vgrad_fd_kernel<NT8, NS8, true>, vgrad_fd_kernel<NT8, NS8, false>}
-// ordered by NT8, then NS8: the first entry that covers (T, D) is taken
+#define NB200_FD_ENTRY(NT8, NS8, NSETS)                                                                                \
+    fd_variant{NT8, NS8, NSETS, fd_layout<NT8>::kHeader, vgrad_fd_kernel<NT8, NS8, NSETS, true>,                       \
+               vgrad_fd_kernel<NT8, NS8, NSETS, false>}
+// the first entry that covers (T, D) is taken: for T <= 8 two alternating sets of four warps (each warp twice the columns)
 const fd_variant kVariants[] = {
-    NB200_FD_ENTRY(1, 2), NB200_FD_ENTRY(1, 4), NB200_FD_ENTRY(1, 6), NB200_FD_ENTRY(1, 8), NB200_FD_ENTRY(1, 10),
-    NB200_FD_ENTRY(1, 14), NB200_FD_ENTRY(1, 16), NB200_FD_ENTRY(2, 2), NB200_FD_ENTRY(2, 4), NB200_FD_ENTRY(2, 6),
-    NB200_FD_ENTRY(2, 8), NB200_FD_ENTRY(2, 10), NB200_FD_ENTRY(2, 13), NB200_FD_ENTRY(2, 16),
+    NB200_FD_ENTRY(1, 8, 2),  NB200_FD_ENTRY(1, 16, 2), NB200_FD_ENTRY(1, 24, 2), NB200_FD_ENTRY(1, 28, 2),
+    NB200_FD_ENTRY(1, 32, 2),
+    NB200_FD_ENTRY(1, 2, 1),  NB200_FD_ENTRY(1, 4, 1),  NB200_FD_ENTRY(1, 6, 1),  NB200_FD_ENTRY(1, 8, 1),
+    NB200_FD_ENTRY(1, 10, 1), NB200_FD_ENTRY(1, 14, 1), NB200_FD_ENTRY(1, 16, 1),
+    NB200_FD_ENTRY(2, 2, 1),  NB200_FD_ENTRY(2, 4, 1),  NB200_FD_ENTRY(2, 6, 1),  NB200_FD_ENTRY(2, 8, 1),
+    NB200_FD_ENTRY(2, 10, 1), NB200_FD_ENTRY(2, 13, 1), NB200_FD_ENTRY(2, 16, 1),
 };
 } // namespace
 

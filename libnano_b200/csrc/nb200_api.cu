@@ -162,6 +162,7 @@ struct fd_plan
 // W (T x ld) and at least two stages of 8 padded rows must fit next to the header; false otherwise
 bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan)
 {
+    static const bool fd_one_set = env_int("NB200_FD_ONE_SET", 0) != 0; // A/B knob (tools/gpu_round44.sh)
     if (!(N > 0 && D > 0 && D % 2 == 0 && T >= 2))
     {
         return false;
@@ -169,12 +170,12 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     for (int v = 0; v < kNumFdVariants; ++v)
     {
         const fd_variant& var = kFdVariants[v];
-        if (8 * var.NT8 < T || 64LL * var.NS8 < D)
+        if (8 * var.NT8 < T || (64LL / var.NSETS) * var.NS8 < D || (fd_one_set && var.NSETS > 1))
         {
             continue;
         }
         const int64_t slice    = 8LL * var.NS8;
-        const int64_t ld       = kFdWarps * slice + 4; // = 4 mod 16: conflict-free 64-bit fragment loads
+        const int64_t ld       = (kFdWarps / var.NSETS) * slice + 4; // = 4 mod 16: conflict-free fragment loads
         const int64_t w_bytes  = round_up(T * ld * 8, 128);
         const int64_t x_bytes  = kFdRows * ld * 8;
         const int64_t y_bytes  = round_up(kFdRows * T * 8, 128);
@@ -558,14 +559,17 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     }
 
     // few targets: one pass over X. forced_variant: -3 the generic kernels, -4 the two-pass tensor-pipe pair, -5 the
-    // one-pass tensor-pipe kernel, -6 the one-pass CUDA-core kernel; heuristic: CUDA cores up to T = 4 (HBM-bound
-    // there), the tensor pipe from T = 5 (profiles/r01_few_targets_*.jsonl)
+    // one-pass tensor-pipe kernel, -6 the one-pass CUDA-core kernel; heuristic: CUDA cores for T = 2 (HBM-bound
+    // there), the tensor pipe from T = 5, in between by width (profiles/r01_few_targets_*.jsonl, r01_handful_*.jsonl)
     obj->use_ft = false;
     obj->use_fd = false;
     obj->use_mt = false;
     const bool one_pass = !force_generic && forced_variant != -3 && forced_variant != -4 && T >= 2;
     fd_plan    handful;
-    if (one_pass && forced_variant != -6 && ((T >= 5 && D >= 200) || forced_variant == -5) &&
+    // (T = 3, 4: the CUDA-core kernel wins where D fills its 512- / 1024-column layouts, the tensor-pipe one elsewhere)
+    const bool ft_sweet  = (D > 384 && D <= 512) || D > 896;
+    const bool prefer_fd = D >= 200 && (T >= 5 || (T >= 3 && !ft_sweet));
+    if (one_pass && forced_variant != -6 && (prefer_fd || forced_variant == -5) &&
         plan_fd(N, D, T, data->sm_count, data->smem_optin, handful))
     {
         const fd_variant& var = kFdVariants[handful.variant];
@@ -1779,7 +1783,8 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     else if (obj->use_fd)
     {
         const fd_variant& var = kFdVariants[obj->fd.variant];
-        text = "fd NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " grid=" +
+        text = "fd NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
+               std::to_string(var.NSETS) + " grid=" +
                std::to_string(obj->fd.grid) + " ld=" + std::to_string(obj->fd.ld) + " stages=" +
                std::to_string(obj->fd.stages) + " stage_bytes=" + std::to_string(obj->fd.stage_stride) +
                " smem=" + std::to_string(obj->fd.smem_bytes);

@@ -71,9 +71,13 @@ struct fd_layout
 
 #ifdef __CUDACC__
 
-template <int NT8, int NS8, bool GRAD> // NS8: n8 column tiles per warp slice (slice = 8 * NS8)
+// NS8: n8 column tiles per warp slice (slice = 8 * NS8); NSETS: 1, or 2 sets of four warps that take the tiles in
+// turn (one set multiplies while the other is between its barrier and the end of its loss chain)
+template <int NT8, int NS8, int NSETS, bool GRAD>
 __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params p)
 {
+    constexpr int WPS = kFdWarps / NSETS; // warps per set: together they cover all columns
+    static_assert(NSETS == 1 || NSETS == 2, "one or two alternating warp sets");
     using L          = fd_layout<NT8>;
     constexpr int TPS = L::TPS;
 
@@ -161,7 +165,9 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 
     // ===== consumer warps =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
-    const int c0 = warp * p.slice; // first column of this warp's slice (forward: K range, backward: N range)
+    const int set = warp / WPS;
+    const int wis = warp % WPS;    // warp in set
+    const int c0  = wis * p.slice; // first column of this warp's slice (forward: K range, backward: N range)
 
     double gacc[NT8][NS8][2]; // gW[8 mt + g][c0 + 8 ns + 2 tig + {0, 1}]
 #pragma unroll
@@ -193,13 +199,30 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     int      stage_index = 0;
     uint32_t phase       = 0;
     int      parity      = 0;
+    int      turn        = 0;
+    double*  set_exchange = exchange + static_cast<int64_t>(set) * (2 * WPS * kFdRows * TPS);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
     {
+        // every warp observes and releases every stage, also the other set's tiles (parity waits tell only adjacent
+        // phases apart)
         const int s = stage_index;
         mbar_wait(full_bar + s, phase);
         const uint32_t wrapped = (stage_index + 1 == p.stages) ? 1u : 0u;
         stage_index            = wrapped ? 0 : stage_index + 1;
         phase ^= wrapped;
+        if constexpr (NSETS > 1)
+        {
+            const bool mine = turn == set;
+            turn            = (turn + 1 == NSETS) ? 0 : turn + 1;
+            if (!mine)
+            {
+                if (lane == 0)
+                {
+                    mbar_arrive(empty_bar + s);
+                }
+                continue;
+            }
+        }
 
         const unsigned char* stage = smem + p.stage_offset + static_cast<int64_t>(s) * p.stage_stride;
         const double*        xs    = reinterpret_cast<const double*>(stage);
@@ -303,21 +326,21 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         }
 
         // exchange: every warp ends up with the full outputs in fragment layout, summed in warp order
-        double* slot = exchange + static_cast<int64_t>(parity) * (kFdWarps * kFdRows * TPS);
+        double* slot = set_exchange + static_cast<int64_t>(parity) * (WPS * kFdRows * TPS);
 #pragma unroll
         for (int nt = 0; nt < NT8; ++nt)
         {
-            *reinterpret_cast<double2*>(slot + (warp * kFdRows + g) * TPS + nt * 8 + tig * 2) =
+            *reinterpret_cast<double2*>(slot + (wis * kFdRows + g) * TPS + nt * 8 + tig * 2) =
                 make_double2(acc[nt][0], acc[nt][1]);
         }
-        named_bar_sync(1, kFdWarps * 32);
+        named_bar_sync(1 + set, WPS * 32);
         double o[NT8][2];
 #pragma unroll
         for (int nt = 0; nt < NT8; ++nt)
         {
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int q = 0; q < kFdWarps; ++q)
+            for (int q = 0; q < WPS; ++q)
             {
                 const double2 v = *reinterpret_cast<const double2*>(slot + (q * kFdRows + g) * TPS + nt * 8 + tig * 2);
                 s0 += v.x;
@@ -467,6 +490,94 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 
     // ----- this CTA's partial row: [loss | sum dL (T) | sum dL x^T (T * D)] -----
     double* out = p.partials + static_cast<int64_t>(blockIdx.x) * (1 + T + static_cast<int64_t>(T) * D);
+
+    // loss and dL sums of this warp's set: fold the 8 row slots (g) in order; every warp of a set carries the same
+    double f = (tig == 0) ? fsum : 0.0;
+    f += __shfl_xor_sync(0xffffffffu, f, 4);
+    f += __shfl_xor_sync(0xffffffffu, f, 8);
+    f += __shfl_xor_sync(0xffffffffu, f, 16);
+    if constexpr (GRAD)
+    {
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                double b = gbsum[nt][j];
+                b += __shfl_xor_sync(0xffffffffu, b, 4);
+                b += __shfl_xor_sync(0xffffffffu, b, 8);
+                b += __shfl_xor_sync(0xffffffffu, b, 16);
+                gbsum[nt][j] = b;
+            }
+        }
+    }
+
+    if constexpr (NSETS > 1)
+    {
+        // both sets cover the same columns: set 1 parks its sums in the (now idle) exchange / stage areas, set 0 adds
+        named_bar_sync(15, kFdWarps * 32); // every issued copy has been consumed, every exchange slot is dead
+        double* park  = reinterpret_cast<double*>(smem + p.stage_offset);
+        double* parkf = exchange; // [1 + TP]
+        if (set == 1)
+        {
+            if constexpr (GRAD)
+            {
+#pragma unroll
+                for (int mt = 0; mt < NT8; ++mt)
+                {
+#pragma unroll
+                    for (int ns = 0; ns < NS8; ++ns)
+                    {
+                        park[((static_cast<int64_t>(wis) * NT8 + mt) * NS8 + ns) * 64 + lane * 2]     = gacc[mt][ns][0];
+                        park[((static_cast<int64_t>(wis) * NT8 + mt) * NS8 + ns) * 64 + lane * 2 + 1] = gacc[mt][ns][1];
+                    }
+                }
+            }
+            if (wis == 0)
+            {
+                if (lane == 0)
+                {
+                    parkf[0] = f;
+                }
+                if (GRAD && g == 0)
+                {
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt)
+                    {
+                        parkf[1 + nt * 8 + tig * 2]     = gbsum[nt][0];
+                        parkf[1 + nt * 8 + tig * 2 + 1] = gbsum[nt][1];
+                    }
+                }
+            }
+        }
+        named_bar_sync(15, kFdWarps * 32);
+        if (set == 1)
+        {
+            return;
+        }
+        if constexpr (GRAD)
+        {
+#pragma unroll
+            for (int mt = 0; mt < NT8; ++mt)
+            {
+#pragma unroll
+                for (int ns = 0; ns < NS8; ++ns)
+                {
+                    gacc[mt][ns][0] += park[((static_cast<int64_t>(wis) * NT8 + mt) * NS8 + ns) * 64 + lane * 2];
+                    gacc[mt][ns][1] += park[((static_cast<int64_t>(wis) * NT8 + mt) * NS8 + ns) * 64 + lane * 2 + 1];
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+                gbsum[nt][0] += parkf[1 + nt * 8 + tig * 2];
+                gbsum[nt][1] += parkf[1 + nt * 8 + tig * 2 + 1];
+            }
+        }
+        f += parkf[0];
+    }
+
     if constexpr (GRAD)
     {
 #pragma unroll
@@ -491,17 +602,11 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     }
     if (warp == 0)
     {
-        // every warp carries identical sums; fold the 8 row slots (g) in order
-        // loss: one value per quad (tig == 0 speaks), dL sums: lane (g, tig) holds targets 8 nt + 2 tig + {0, 1} of row g
-        double f = (tig == 0) ? fsum : 0.0;
-        f += __shfl_xor_sync(0xffffffffu, f, 4);
-        f += __shfl_xor_sync(0xffffffffu, f, 8);
-        f += __shfl_xor_sync(0xffffffffu, f, 16);
         if (lane == 0)
         {
             out[0] = f;
         }
-        if constexpr (GRAD)
+        if (GRAD && g == 0)
         {
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt)
@@ -509,14 +614,10 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
                 {
-                    double b = gbsum[nt][j];
-                    b += __shfl_xor_sync(0xffffffffu, b, 4);
-                    b += __shfl_xor_sync(0xffffffffu, b, 8);
-                    b += __shfl_xor_sync(0xffffffffu, b, 16);
                     const int t = nt * 8 + tig * 2 + j;
-                    if (g == 0 && t < T)
+                    if (t < T)
                     {
-                        out[1 + t] = b;
+                        out[1 + t] = gbsum[nt][j];
                     }
                 }
             }
