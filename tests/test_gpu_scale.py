@@ -204,3 +204,62 @@ def test_full_size_properties(ctx, oracle, N, D, loss_id):
     # (e) determinism at size
     g2 = np.empty_like(x)
     assert function(x, g2) == fx and np.array_equal(g2, gx)
+
+
+@pytest.mark.parametrize("N,D,T,path", [(1 << 18, 2048, 100, "dmma"), (1 << 20, 784, 10, "fd"), (1 << 21, 512, 2, "ft"),
+                                        (1 << 20, 1024, 8, "fd"), (1 << 20, 1000, 4, "ft")])
+def test_full_size_properties_many_targets(ctx, oracle, N, D, T, path):
+    # the multi-target paths at sizes the oracle cannot hold: BASELINE config 3's width (tensor-pipe pair) and the
+    # one-pass kernels; same size-independent properties as above
+    import libnano_b200 as nb
+    from libnano_b200.sharded import shard_rows
+
+    data = nb.Dataset.synth(ctx, nb.SYNTH_MULTICLASS, N, D, T=T, seed=42)
+    l2 = 1e-2
+    function = nb.LinearFunction(data, nb.Loss("s-classnll"), 0.0, l2)
+    assert function.describe().startswith(path), function.describe()
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (D + 1) * T) / np.sqrt(D)
+    gx = np.empty_like(x)
+    fx = function(x, gx)
+    assert np.isfinite(fx) and np.all(np.isfinite(gx))
+    assert rel_f(function(x), fx) <= 1e-15
+
+    # (a) shards recombine to the whole; (b) the oracle on a bounded sub-sample of one shard
+    k = 3
+    f_sum, g_sum = 0.0, np.zeros_like(x)
+    for rank in range(k):
+        row0, rows = shard_rows(N, k, rank)
+        part = nb.Dataset.synth(ctx, nb.SYNTH_MULTICLASS, rows, D, T=T, seed=42, row_offset=row0)
+        fn = nb.LinearFunction(part, nb.Loss("s-classnll"), 0.0, 0.0)
+        g = np.empty_like(x)
+        f_sum += fn(x, g) * rows
+        g_sum += g * rows
+        if rank == 1:
+            Xs, Ys = part.read(777, 1500)
+            sub = nb.LinearFunction(nb.Dataset.pin(ctx, Xs, Ys), nb.Loss("s-classnll"), 0.0, 0.0)
+            gs = np.empty_like(x)
+            fs = sub(x, gs)
+            fo, go = oracle.linear_vgrad(Xs, Ys, "s-classnll", x)
+            assert rel_f(fs, fo) <= PARITY and rel_g(gs, go) <= PARITY
+    whole0 = nb.LinearFunction(data, nb.Loss("s-classnll"), 0.0, 0.0)
+    g0 = np.empty_like(x)
+    f0 = whole0(x, g0)
+    assert rel_f(f_sum / N, f0) <= 1e-13 and rel_g(g_sum / N, g0) <= 1e-13
+
+    # (c) additive regulariser; (d) directional derivative; (e) determinism; (f) the other kernels agree at size
+    W = x[: T * D]
+    assert abs((fx - f0) - 0.5 * l2 * np.mean(W * W)) <= 1e-14 * (1 + abs(fx))
+    d = rng.uniform(-1, 1, x.size)
+    d /= np.linalg.norm(d)
+    h = 1e-5
+    fd = (function(x + h * d) - function(x - h * d)) / (2 * h)
+    assert abs(fd - float(gx @ d)) <= 1e-8 * (1 + abs(fd))
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)
+    if path != "dmma":
+        function.set_variant(-4)
+        g3 = np.empty_like(x)
+        f3 = function(x, g3)
+        assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
