@@ -36,7 +36,10 @@ def main():
     ok = True
     for (N, D, T, loss_id, kind) in ((300001, 1024, 1, "s-logistic", nb.SYNTH_CLASSIFICATION),
                                      (50000, 512, 1, "s-hinge", nb.SYNTH_CLASSIFICATION),
-                                     (20000, 256, 10, "s-classnll", nb.SYNTH_MULTICLASS)):
+                                     (20000, 256, 10, "s-classnll", nb.SYNTH_MULTICLASS),
+                                     (40001, 784, 10, "s-classnll", nb.SYNTH_MULTICLASS),
+                                     (30001, 512, 2, "s-classnll", nb.SYNTH_MULTICLASS),
+                                     (9001, 2048, 40, "s-classnll", nb.SYNTH_MULTICLASS)):
         row0, rows = shard_rows(N, world, rank)
         part = nb.Dataset.synth(ctx, kind, rows, D, T=T, seed=7, row_offset=row0)
         local = nb.LinearFunction(part, nb.Loss(loss_id), 0.01 if loss_id == "s-hinge" else 0.0, 1e-2)
@@ -55,7 +58,8 @@ def main():
             same = all(torch.equal(gathered[0], t) for t in gathered)
         else:
             same = True
-        case = {"N": N, "D": D, "T": T, "loss": loss_id, "identical_across_ranks": bool(same), "fused_peers": fused}
+        case = {"N": N, "D": D, "T": T, "loss": loss_id, "identical_across_ranks": bool(same), "fused_peers": fused,
+                "kernel": local.describe().split(" ")[0]}
         for _ in range(5):  # repeated evaluations exercise the mailbox parity / epoch logic
             g2 = np.empty_like(x)
             same = same and sharded(x, g2) == fx and np.array_equal(g2, gx) and sharded(x) == fv
