@@ -223,8 +223,9 @@ NB200_API int nb200_objective_describe(const nb200_obj* obj, char* buffer, int64
 /* Many models in ONE pass over X (the tuner's grid of (l1, l2) values and cross-validation trials
  * re-read the same X once per trial in the reference, src/machine/tune.cpp:25-42). K single-target models that share
  * the objective's dataset and loss and differ in x_k, l1_k, l2_k: x [K][n], l1 [K], l2 [K] -> gx [K][n] (nullable),
- * fx [K], all host. Runs as one many-"target" problem on the FP64 tensor pipe (two reads of X for K evaluations);
- * shapes outside those kernels (odd D, fewer than 6 models) fall back to K passes of the single-model kernel. */
+ * fx [K], all host. Runs as one many-"target" problem on the FP64 tensor pipe: ONE read of X per 8 models for K <= 24
+ * (one-pass kernel, D >= 200), two reads of X for larger batches; shapes outside those kernels (odd D, D < 200 with
+ * fewer than 6 models) fall back to K passes of the single-model kernel. */
 NB200_API int nb200_vgrad_batch(nb200_obj* obj, int64_t K, const double* x, int64_t n, const double* l1,
                                 const double* l2, double* gx, double* fx);
 

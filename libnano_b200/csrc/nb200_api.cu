@@ -265,6 +265,8 @@ struct batch_state
 {
     int64_t     Kp{0}; // padded (even) model count the buffers are sized for
     mt_geometry geo{};
+    bool        one_pass{false}; // the one-pass tensor-pipe kernel (vgrad_fd.cuh) covers (D, Kp)
+    fd_plan     fd{};
     double *    d_x{nullptr}, *d_W{nullptr}, *d_Wp{nullptr}, *d_b{nullptr}, *d_l{nullptr}, *d_dL{nullptr};
     double *    d_partials_fb{nullptr}, *d_partials_gw{nullptr}, *d_red_fb{nullptr}, *d_red_gw{nullptr};
     double *    h_in{nullptr}, *h_out{nullptr}, *h_out_dev{nullptr};
@@ -1861,6 +1863,13 @@ int nb200_cgd_minimize(nb200_obj* obj, double* x, const int64_t n, const int bet
     return solver.run(x, epsilon, max_evals, 1, fx, gradient_test, stats, status);
 }
 
+// the one-pass tensor-pipe kernel for a batch of Kp single-target models (Y has one column)
+static bool plan_fd_batch(const int64_t N, const int64_t D, const int64_t Kp, const int sm_count, const int smem_optin,
+                          fd_plan& plan)
+{
+    return Kp <= 16 && D >= 200 && plan_fd(N, D, Kp, sm_count, smem_optin, plan);
+}
+
 static int ensure_batch(nb200_obj* obj, const int64_t Kp)
 {
     batch_state&      bs   = obj->batch;
@@ -1872,21 +1881,37 @@ static int ensure_batch(nb200_obj* obj, const int64_t Kp)
     }
     bs.release();
     mt_geometry geo;
-    if (!plan_mt(N, D, Kp, data->sm_count, data->smem_optin, geo))
+    fd_plan     one;
+    const bool  one_pass = plan_fd_batch(N, D, Kp, data->sm_count, data->smem_optin, one);
+    if (one_pass)
     {
-        return fail(NB200_ERR_UNSUPPORTED, "batch: this (D, K) is not covered by the tensor-pipe kernels");
+        const fd_variant& var = kFdVariants[one.variant];
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, one.smem_bytes));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, one.smem_bytes));
+        geo.fwd_grid = one.grid; // rows of the two partial buffers
+        geo.splits   = one.grid;
     }
-    const mt_variant& var = kMtVariants[geo.variant];
-    NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
-    NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
-    NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
+    else
+    {
+        if (!plan_mt(N, D, Kp, data->sm_count, data->smem_optin, geo))
+        {
+            return fail(NB200_ERR_UNSUPPORTED, "batch: this (D, K) is not covered by the tensor-pipe kernels");
+        }
+        const mt_variant& var = kMtVariants[geo.variant];
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
+    }
     const size_t K = static_cast<size_t>(Kp);
     NB200_CUDA_TRY(cudaMalloc(&bs.d_x, K * (n + 2) * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_W, K * D * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_Wp, static_cast<size_t>((D + kMtBK - 1) / kMtBK) * K * kMtLd * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_b, K * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_l, 2 * K * sizeof(double)));
-    NB200_CUDA_TRY(cudaMalloc(&bs.d_dL, static_cast<size_t>(N) * K * sizeof(double)));
+    if (!one_pass)
+    {
+        NB200_CUDA_TRY(cudaMalloc(&bs.d_dL, static_cast<size_t>(N) * K * sizeof(double)));
+    }
     NB200_CUDA_TRY(cudaMalloc(&bs.d_partials_fb, static_cast<size_t>(geo.fwd_grid) * (1 + 2 * K) * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_partials_gw, static_cast<size_t>(geo.splits) * K * D * sizeof(double)));
     NB200_CUDA_TRY(cudaMalloc(&bs.d_red_fb, (1 + 2 * K) * sizeof(double)));
@@ -1895,13 +1920,15 @@ static int ensure_batch(nb200_obj* obj, const int64_t Kp)
     NB200_CUDA_TRY(cudaHostAlloc(&bs.h_out, K * (n + 1) * sizeof(double), cudaHostAllocMapped));
     NB200_CUDA_TRY(cudaHostGetDevicePointer(&bs.h_out_dev, bs.h_out, 0));
     NB200_CUDA_TRY(cudaDeviceSynchronize());
-    bs.Kp  = Kp;
-    bs.geo = geo;
+    bs.Kp       = Kp;
+    bs.geo      = geo;
+    bs.one_pass = one_pass;
+    bs.fd       = one;
     return NB200_OK;
 }
 
-int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const int64_t n, const double* l1,
-                      const double* l2, double* gx, double* fx)
+static int vgrad_batch_impl(nb200_obj* obj, const int64_t K, const double* x, const int64_t n, const double* l1,
+                            const double* l2, double* gx, double* fx, const int64_t Kp_min)
 {
     NB200_REQUIRE(obj != nullptr && x != nullptr && l1 != nullptr && l2 != nullptr && fx != nullptr,
                   "batch: null argument");
@@ -1912,11 +1939,31 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     const nb200_data* data = obj->data;
     const int64_t     N = data->N, D = data->D;
-    const int64_t     Kp = (K % 2 == 0) ? K : K + 1;
+    // padded model count (even; the chunks of a split batch all use 8 so that the scratch is allocated once)
+    const int64_t     Kp = std::max<int64_t>((K % 2 == 0) ? K : K + 1, Kp_min);
 
     // fewer than 6 models: K single passes at ~6.4 TB/s beat the two tensor-pipe passes (measured cross-over K ~ 5)
+    // 9 .. 24 models: chunks of 8 on the one-pass kernel with ONE target tile (2.5 ms per chunk at 2^20 x 1024) beat
+    // both the two-target-tile one-pass kernel and the two-pass pair (7.2-7.6 ms for 12-16 models, ~8 ms for 32)
+    {
+        fd_plan chunk;
+        if (Kp_min == 0 && K > 8 && K <= 24 && plan_fd_batch(N, D, 8, data->sm_count, data->smem_optin, chunk))
+        {
+            int status = NB200_OK;
+            for (int64_t k0 = 0; k0 < K && status == NB200_OK; k0 += 8)
+            {
+                const int64_t kc = std::min<int64_t>(8, K - k0);
+                status = vgrad_batch_impl(obj, kc, x + k0 * n, n, l1 + k0, l2 + k0, gx != nullptr ? gx + k0 * n : nullptr,
+                                          fx + k0, 8);
+            }
+            return status;
+        }
+    }
+    // ... unless the one-pass kernel covers the shape: it reads X once for any K >= 2
     mt_geometry probe;
-    if (Kp < 6 || !plan_mt(N, D, Kp, data->sm_count, data->smem_optin, probe))
+    fd_plan     probe_one;
+    const bool  one_pass_fits = K >= 2 && plan_fd_batch(N, D, Kp, data->sm_count, data->smem_optin, probe_one);
+    if (!one_pass_fits && (Kp < 6 || !plan_mt(N, D, Kp, data->sm_count, data->smem_optin, probe)))
     {
         // shapes outside the tensor-pipe kernels: K passes of the single-model path (still the GPU, just not fused)
         const double keep1 = obj->l1, keep2 = obj->l2;
@@ -1959,6 +2006,46 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     NB200_CUDA_TRY(cudaGetLastError());
     obj->launches += 1;
 
+    if (bs.one_pass)
+    {
+        status = timing_begin(obj);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        const fd_variant& one = kFdVariants[bs.fd.variant];
+        fd_params         q{};
+        q.X            = data->X;
+        q.Y            = data->Y;
+        q.W            = bs.d_W;
+        q.b            = bs.d_b;
+        q.partials     = bs.d_partials_fb;
+        q.partials_gw  = bs.d_partials_gw;
+        q.y_broadcast  = 1;
+        q.N            = N;
+        q.num_tiles    = bs.fd.num_tiles;
+        q.D            = static_cast<int>(D);
+        q.T            = static_cast<int>(Kp);
+        q.slice        = bs.fd.slice;
+        q.ld           = bs.fd.ld;
+        q.stages       = bs.fd.stages;
+        q.stage_stride = bs.fd.stage_stride;
+        q.y_offset     = bs.fd.y_offset;
+        q.w_offset     = bs.fd.w_offset;
+        q.stage_offset = bs.fd.stage_offset;
+        q.loss         = obj->loss;
+        q.loss_param   = obj->loss_param;
+        (grad ? one.grad : one.value)<<<bs.fd.grid, kFdThreads, bs.fd.smem_bytes, st>>>(q);
+        NB200_CUDA_TRY(cudaGetLastError());
+        obj->launches += 1;
+        status = timing_end(obj);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+    }
+    else
+    {
     mt_pack_weights_kernel<<<static_cast<unsigned>(std::min<int64_t>((Kp * D + 255) / 256, 2048)), 256, 0, st>>>(
         bs.d_W, static_cast<int>(Kp), static_cast<int>(D), bs.d_Wp);
     NB200_CUDA_TRY(cudaGetLastError());
@@ -2009,6 +2096,7 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
     {
         return status;
     }
+    } // two-pass pair
     const int64_t cols_fb = 1 + 2 * Kp;
     reduce_partials_kernel<<<static_cast<unsigned>((cols_fb + 127) / 128), 128, 0, st>>>(
         bs.d_partials_fb, geo.fwd_grid, cols_fb, cols_fb, bs.d_red_fb);
@@ -2037,6 +2125,12 @@ int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const in
         fx[k] = bs.h_out[k * (n + 1) + n];
     }
     return NB200_OK;
+}
+
+int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const int64_t n, const double* l1,
+                      const double* l2, double* gx, double* fx)
+{
+    return vgrad_batch_impl(obj, K, x, n, l1, l2, gx, fx, 0);
 }
 
 int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const double* b, double* outputs)

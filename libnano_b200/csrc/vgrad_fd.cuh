@@ -40,7 +40,12 @@ struct fd_params
     const double* Y;        // [N, T], padded by >= 16 bytes at the end
     const double* W;        // [T, D] device
     const double* b;        // [T] device
-    double*       partials; // [grid, 1 + T + T * D]
+    double*       partials; // [grid, 1 + T + T * D]: per-CTA rows [loss | sum dL (T) | sum dL x^T (T * D)]
+    // batched single-target models (nb200_vgrad_batch): the K weight vectors play the targets, every
+    // output column is compared with the same y_i, losses are kept per column, and the partial rows are split in two
+    // buffers: partials = [grid, 1 + 2 T] rows [total | sum dL (T) | loss sums (T)], partials_gw = [grid, T * D]
+    double*       partials_gw; // nullptr: the single-buffer layout above
+    int           y_broadcast; // 1: Y is [N, 1]
     int64_t       N;
     int64_t       num_tiles;
     int           D;      // even
@@ -79,6 +84,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     constexpr int WPS = kFdWarps / NSETS; // warps per set: together they cover all columns
     static_assert(NSETS == 1 || NSETS == 2, "one or two alternating warp sets");
     using L          = fd_layout<NT8>;
+    constexpr int TP  = L::TP;
     constexpr int TPS = L::TPS;
 
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -141,12 +147,13 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
             mbar_wait(empty_bar + s, phase);
             const int64_t  row0    = tile * kFdRows;
             const int      rows    = static_cast<int>(min(static_cast<int64_t>(kFdRows), p.N - row0));
-            const uint32_t bytes_y = static_cast<uint32_t>((rows * T * 8 + 15) / 16 * 16);
+            const int      ty      = p.y_broadcast ? 1 : T; // targets stored per row of Y
+            const uint32_t bytes_y = static_cast<uint32_t>((rows * ty * 8 + 15) / 16 * 16);
             unsigned char* stage   = smem + p.stage_offset + static_cast<int64_t>(s) * p.stage_stride;
             if (lane == 0)
             {
                 mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>(rows) * D * 8 + bytes_y);
-                bulk_copy_g2s(stage + p.y_offset, p.Y + row0 * T, bytes_y, full_bar + s, policy);
+                bulk_copy_g2s(stage + p.y_offset, p.Y + row0 * ty, bytes_y, full_bar + s, policy);
             }
             __syncwarp();
             if (lane < rows)
@@ -189,10 +196,12 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     }
     double  fsum = 0.0;          // loss of the rows g this lane has seen (identical on the 4 lanes of a quad)
     double  gbsum[NT8][2];       // sum over rows of dL[g][8 nt + 2 tig + j]
+    double  lsum[NT8][2];        // per-target loss sums (batched models)
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt)
     {
         gbsum[nt][0] = gbsum[nt][1] = 0.0;
+        lsum[nt][0] = lsum[nt][1] = 0.0;
     }
     double* my_dl = dl_tiles + warp * (kFdRows * kFdLdd);
 
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
             for (int j = 0; j < 2; ++j)
             {
                 const int t = nt * 8 + tig * 2 + j;
-                y[nt][j]    = (row_ok && t < T) ? ys[g * T + t] : 0.0;
+                y[nt][j]    = (row_ok && t < T) ? (p.y_broadcast ? ys[g] : ys[g * T + t]) : 0.0;
             }
         }
         if constexpr (EARLY || !GRAD)
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         {
             dl[nt][0] = dl[nt][1] = 0.0;
         }
-        if (p.loss == LOSS_CLASSNLL)
+        if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
         {
             // classnll.h:19-37: the four lanes of a quad hold the whole row
             double omax = -INFINITY;
@@ -429,6 +438,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                         double term;
                         loss_term<GRAD>(p.loss, p.loss_param, y[nt][j], o[nt][j], term, dl[nt][j]);
                         sum += term;
+                        lsum[nt][j] += loss_post(p.loss, term); // one output per model: the factor applies per term
                     }
                 }
             }
@@ -489,7 +499,10 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     }
 
     // ----- this CTA's partial row: [loss | sum dL (T) | sum dL x^T (T * D)] -----
-    double* out = p.partials + static_cast<int64_t>(blockIdx.x) * (1 + T + static_cast<int64_t>(T) * D);
+    const bool batched = p.partials_gw != nullptr;
+    double*    out     = p.partials + static_cast<int64_t>(blockIdx.x) *
+                                   (batched ? (1 + 2 * T) : (1 + T + static_cast<int64_t>(T) * D));
+    double*    out_gw  = batched ? p.partials_gw + static_cast<int64_t>(blockIdx.x) * T * D : out + 1 + T;
 
     // loss and dL sums of this warp's set: fold the 8 row slots (g) in order; every warp of a set carries the same
     double f = (tig == 0) ? fsum : 0.0;
@@ -512,13 +525,29 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
             }
         }
     }
+    if (p.partials_gw != nullptr)
+    {
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                double l = lsum[nt][j];
+                l += __shfl_xor_sync(0xffffffffu, l, 4);
+                l += __shfl_xor_sync(0xffffffffu, l, 8);
+                l += __shfl_xor_sync(0xffffffffu, l, 16);
+                lsum[nt][j] = l;
+            }
+        }
+    }
 
     if constexpr (NSETS > 1)
     {
         // both sets cover the same columns: set 1 parks its sums in the (now idle) exchange / stage areas, set 0 adds
         named_bar_sync(15, kFdWarps * 32); // every issued copy has been consumed, every exchange slot is dead
         double* park  = reinterpret_cast<double*>(smem + p.stage_offset);
-        double* parkf = exchange; // [1 + TP]
+        double* parkf = exchange; // [1 + 2 TP]
         if (set == 1)
         {
             if constexpr (GRAD)
@@ -540,13 +569,15 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                 {
                     parkf[0] = f;
                 }
-                if (GRAD && g == 0)
+                if (g == 0)
                 {
 #pragma unroll
                     for (int nt = 0; nt < NT8; ++nt)
                     {
-                        parkf[1 + nt * 8 + tig * 2]     = gbsum[nt][0];
-                        parkf[1 + nt * 8 + tig * 2 + 1] = gbsum[nt][1];
+                        parkf[1 + nt * 8 + tig * 2]          = gbsum[nt][0];
+                        parkf[1 + nt * 8 + tig * 2 + 1]      = gbsum[nt][1];
+                        parkf[1 + TP + nt * 8 + tig * 2]     = lsum[nt][0];
+                        parkf[1 + TP + nt * 8 + tig * 2 + 1] = lsum[nt][1];
                     }
                 }
             }
@@ -568,12 +599,14 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                     gacc[mt][ns][1] += park[((static_cast<int64_t>(wis) * NT8 + mt) * NS8 + ns) * 64 + lane * 2 + 1];
                 }
             }
+        }
 #pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
-            {
-                gbsum[nt][0] += parkf[1 + nt * 8 + tig * 2];
-                gbsum[nt][1] += parkf[1 + nt * 8 + tig * 2 + 1];
-            }
+        for (int nt = 0; nt < NT8; ++nt)
+        {
+            gbsum[nt][0] += parkf[1 + nt * 8 + tig * 2];
+            gbsum[nt][1] += parkf[1 + nt * 8 + tig * 2 + 1];
+            lsum[nt][0] += parkf[1 + TP + nt * 8 + tig * 2];
+            lsum[nt][1] += parkf[1 + TP + nt * 8 + tig * 2 + 1];
         }
         f += parkf[0];
     }
@@ -592,7 +625,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                     const int col = c0 + ns * 8 + tig * 2;
                     if (col < D)
                     {
-                        double* dst = out + 1 + T + static_cast<int64_t>(t) * D + col; // 8-byte aligned only
+                        double* dst = out_gw + static_cast<int64_t>(t) * D + col; // 8-byte aligned only
                         dst[0]      = gacc[mt][ns][0];
                         dst[1]      = gacc[mt][ns][1];
                     }
@@ -606,7 +639,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         {
             out[0] = f;
         }
-        if (GRAD && g == 0)
+        if (g == 0)
         {
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt)
@@ -617,7 +650,14 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
                     const int t = nt * 8 + tig * 2 + j;
                     if (t < T)
                     {
-                        out[1 + t] = gbsum[nt][j];
+                        if (GRAD || batched)
+                        {
+                            out[1 + t] = GRAD ? gbsum[nt][j] : 0.0;
+                        }
+                        if (batched)
+                        {
+                            out[1 + T + t] = lsum[nt][j];
+                        }
                     }
                 }
             }

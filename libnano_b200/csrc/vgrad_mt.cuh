@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                 y[k]        = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
             }
 
-            if (p.loss == LOSS_CLASSNLL)
+            if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
             {
                 // classnll.h:19-37
                 double omax = -INFINITY;
