@@ -54,12 +54,16 @@ def main():
         for l2 in (0.0, 1e-2):
             local = nb.LinearFunction(data, nb.Loss("s-logistic"), 0.0, l2)
             function = ShardedFunction.from_local(local, rows * world)
+            fused = bool(world > 1 and function.connect_peers())  # all-reduce inside the kernel over NVLink peers
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             result = lbfgs(function, np.zeros(function.size()), epsilon=1e-8, max_evals=args.max_evals or 1000)
             seconds = time.perf_counter() - t0
             report(f"config{args.config} s-logistic l2={l2} lbfgs(device-resident)", result, seconds,
-                   {"rows_per_gpu": rows, "features": D, "plan": local.describe()})
+                   {"rows_per_gpu": rows, "features": D, "plan": local.describe(),
+                    "collective": "fused peers" if world > 1 and fused else ("nccl" if world > 1 else "none")})
     else:
         rows = args.rows_per_gpu or (1 << 24)
         D = 512
