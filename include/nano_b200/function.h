@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "../nb200.h"
 
@@ -142,6 +143,12 @@ public:
     tensor_size_t fcalls() const { return m_fcalls; }
     tensor_size_t gcalls() const { return m_gcalls; }
     void          clear_statistics() const { m_fcalls = m_gcalls = 0; }
+    // evaluations made on the device on this function's behalf (the device-resident solvers below)
+    void          count_calls(const tensor_size_t fcalls, const tensor_size_t gcalls) const
+    {
+        m_fcalls += fcalls;
+        m_gcalls += gcalls;
+    }
 
 protected:
     void convex(const bool value) { m_convex = value; }
@@ -216,6 +223,8 @@ public:
         return std::make_unique<function_t>(m_dataset, m_loss_id, m_l1reg, m_l2reg, m_loss_param);
     }
 
+    nb200_obj* handle() const { return m_handle.get(); }
+
     // include/nano/linear/function.h:30-59
     const scalar_t* weights(const scalar_t* x) const { return x; }
     const scalar_t* bias(const scalar_t* x) const { return x + m_dataset.inputs() * m_dataset.targets(); }
@@ -243,4 +252,75 @@ private:
     std::unique_ptr<nb200_obj, release_t> m_handle;
 };
 } // namespace linear
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-resident solvers: nano::solver_lbfgs_t / solver_cgd_*_t (src/solver/lbfgs.cpp, src/solver/cgd.cpp) with the
+// vectors in HBM (nb200_lbfgs_minimize / nb200_cgd_minimize). The result mirrors solver_state_t's fields.
+// ---------------------------------------------------------------------------------------------------------------
+enum class solver_status
+{
+    max_iters     = 0, // include/nano/solver/status.h
+    gradient_test = 1,
+    failed        = 4
+};
+
+struct solver_state_t
+{
+    std::vector<scalar_t> m_x;
+    scalar_t              m_fx{0.0};
+    scalar_t              m_gradient_test{0.0};
+    solver_status         m_status{solver_status::max_iters};
+    tensor_size_t         m_fcalls{0}, m_gcalls{0}, m_iterations{0};
+};
+
+namespace detail
+{
+template <typename tcall>
+solver_state_t minimize(const linear::function_t& function, const std::vector<scalar_t>& x0, const tcall& call)
+{
+    critical(static_cast<tensor_size_t>(x0.size()) == function.size(),
+             "solver: incompatible initial point (" + std::to_string(x0.size()) + " dimensions), expecting " +
+                 std::to_string(function.size()) + " dimensions!");
+    function.clear_statistics(); // solver_t::minimize, src/solver.cpp:107
+    solver_state_t state;
+    state.m_x       = x0;
+    int64_t stats[3] = {0, 0, 0};
+    int     status   = 0;
+    check(call(function.handle(), state.m_x.data(), static_cast<int64_t>(state.m_x.size()), &state.m_fx,
+               &state.m_gradient_test, stats, &status));
+    state.m_status     = static_cast<solver_status>(status);
+    state.m_fcalls     = stats[0];
+    state.m_gcalls     = stats[1];
+    state.m_iterations = stats[2];
+    function.count_calls(stats[0], stats[1]);
+    return state;
+}
+} // namespace detail
+
+// defaults: src/solver.cpp:45-51 (epsilon 1e-8, max_evals 1000), src/solver/lbfgs.cpp:12 (history 50)
+inline solver_state_t minimize_lbfgs(const linear::function_t& function, const std::vector<scalar_t>& x0,
+                                     const scalar_t epsilon = 1e-8, const tensor_size_t max_evals = 1000,
+                                     const tensor_size_t history = 50)
+{
+    return detail::minimize(function, x0,
+                            [&](nb200_obj* obj, scalar_t* x, int64_t n, scalar_t* fx, scalar_t* gtest, int64_t* stats,
+                                int* status) {
+                                return nb200_lbfgs_minimize(obj, x, n, epsilon, max_evals, history, 0, nullptr, nullptr,
+                                                            fx, gtest, stats, status);
+                            });
+}
+
+// beta: NB200_CGD_HS ... NB200_CGD_FRPR (libnano's "cgd-hs" ... "cgd-frpr"; NB200_CGD_PR is its plain "cgd")
+inline solver_state_t minimize_cgd(const linear::function_t& function, const std::vector<scalar_t>& x0,
+                                   const int beta = NB200_CGD_PR, const scalar_t epsilon = 1e-8,
+                                   const tensor_size_t max_evals = 1000, const scalar_t orthotest = 0.1,
+                                   const scalar_t eta = 0.01)
+{
+    return detail::minimize(function, x0,
+                            [&](nb200_obj* obj, scalar_t* x, int64_t n, scalar_t* fx, scalar_t* gtest, int64_t* stats,
+                                int* status) {
+                                return nb200_cgd_minimize(obj, x, n, beta, epsilon, max_evals, orthotest, eta, 0, nullptr,
+                                                          nullptr, fx, gtest, stats, status);
+                            });
+}
 } // namespace nano_b200

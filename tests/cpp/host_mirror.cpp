@@ -99,6 +99,44 @@ int main()
     function.clear_statistics();
     CHECK(function.fcalls() == 0);
 
+    // device-resident solvers through the C++ mirror: noise-free targets => the generating (W, b) come back
+    // (test/test_linear_function.cpp:152-188, minimize_noreg)
+    {
+        const tensor_size_t M = 200, E = 5;
+        std::vector<double> Xs(M * E), Ws(E), Ys(M);
+        for (auto& v : Xs) v = udist(rng);
+        for (auto& v : Ws) v = udist(rng);
+        const double bs = udist(rng);
+        for (tensor_size_t i = 0; i < M; ++i)
+        {
+            double o = bs;
+            for (tensor_size_t j = 0; j < E; ++j) o += Xs[i * E + j] * Ws[j];
+            Ys[i] = o;
+        }
+        dataset_t          small(ctx, Xs.data(), Ys.data(), M, E, 1);
+        linear::function_t objective(small, "mse", 0.0, 0.0);
+        const std::vector<double> x0(E + 1, 0.0);
+        for (const auto& state : {minimize_lbfgs(objective, x0, 1e-10, 10000), minimize_cgd(objective, x0, NB200_CGD_PR, 1e-10, 10000),
+                                  minimize_cgd(objective, x0, NB200_CGD_N, 1e-10, 10000)})
+        {
+            CHECK(state.m_status == solver_status::gradient_test && state.m_gradient_test < 1e-10);
+            CHECK(std::fabs(state.m_fx) < 1e-7 && state.m_fcalls == state.m_gcalls && state.m_fcalls > 3);
+            for (tensor_size_t j = 0; j < E; ++j) CHECK(std::fabs(state.m_x[j] - Ws[j]) < 1e-7);
+            CHECK(std::fabs(state.m_x[E] - bs) < 1e-7);
+        }
+        CHECK(objective.fcalls() > 3); // the last solve's evaluations were counted on the function
+        bool refused = false;
+        try
+        {
+            minimize_lbfgs(objective, std::vector<double>(E, 0.0));
+        }
+        catch (const std::runtime_error& e)
+        {
+            refused = std::string(e.what()).find("incompatible initial point") != std::string::npos;
+        }
+        CHECK(refused);
+    }
+
     std::printf("OK f=%.15g |g|_inf=%.6g\n", f1, gmax);
     return 0;
 }
