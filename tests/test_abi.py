@@ -52,6 +52,11 @@ def test_library_is_sm100a_native(library):
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", library._name], capture_output=True, text=True).stdout
     assert "vgrad_t1_kernel" in sass and "UBLKCP" in sass and "SYNCS.PHASECHK" in sass and "DFMA" in sass
+    # every kernel family is in the library, and the many-target ones run on the FP64 tensor pipe (DMMA)
+    for family in ("vgrad_ft_kernel", "vgrad_fd_kernel", "mt_forward_kernel", "mt_backward_kernel", "gen_forward_kernel",
+                   "lbfgs_two_loop_kernel", "cgd_direction_kernel", "column_stats_kernel"):
+        assert family in sass, family
+    assert "DMMA.8x8x4" in sass and "USETMAXREG" in sass
 
 
 def test_register_hand_over_matches_the_allocation(library):
