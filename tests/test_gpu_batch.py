@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 #  K single passes otherwise)
 @pytest.mark.parametrize("N,D,K", [(3000, 128, 4), (5000, 256, 7), (2049, 1024, 16), (700, 384, 1), (1000, 100, 3),
                                    (4000, 512, 5), (3001, 1024, 8), (2500, 784, 2), (1500, 512, 16), (999, 300, 11),
-                                   (6000, 640, 31)])
+                                   (6000, 640, 31), (1200, 512, 9), (1300, 256, 17), (800, 1024, 24), (900, 512, 25)])
 @pytest.mark.parametrize("loss_id", ["s-logistic", "mse", "s-hinge", "mae"])
 def test_batched_models_match_separate_evaluations(ctx, oracle, N, D, K, loss_id):
     import libnano_b200 as nb
