@@ -1,0 +1,96 @@
+// oracle/ref_loss.cpp — TEST INFRASTRUCTURE: C entry points over the reference's OWN loss headers, compiled in place from
+// /root/reference (make -C oracle ref -> oracle/_ref/libref_loss.so; the stand-in for <Eigen/Core> is oracle/ref_shim/).
+// kind follows oracle/__init__.py LOSS_KINDS: 0 mse 1 mae 2 cauchy 3 hinge 4 squared-hinge 5 classnll 6 savage 7 tangent
+// 8 logistic 9 exponential (pinball lives in src/loss/pinball.cpp behind tensor maps: its golden vectors are the
+// reference's test/test_loss.cpp:271-307).
+#include <nano/loss/cauchy.h>
+#include <nano/loss/classnll.h>
+#include <nano/loss/exponential.h>
+#include <nano/loss/hinge.h>
+#include <nano/loss/logistic.h>
+#include <nano/loss/mae.h>
+#include <nano/loss/mse.h>
+#include <nano/loss/savage.h>
+#include <nano/loss/squared_hinge.h>
+#include <nano/loss/tangent.h>
+
+#include <cstdint>
+
+namespace
+{
+struct no_error_t // the terror base class only contributes error(), which is not on the vgrad path
+{
+};
+using array_t     = nano::refshim::array_t;
+using array_ref_t = nano::refshim::array_ref_t;
+
+template <template <class> class tloss>
+double value(const array_t& target, const array_t& output)
+{
+    return tloss<no_error_t>::value(target, output);
+}
+
+template <template <class> class tloss>
+void vgrad(const array_t& target, const array_t& output, array_t& out)
+{
+    tloss<no_error_t>::vgrad(target, output, array_ref_t{out});
+}
+} // namespace
+
+extern "C" {
+// values[N]; targets / outputs [N, T] row-major (one sample = one array of T, as flatten_loss_t::do_value loops)
+int ref_loss_value(const int kind, const double* targets, const double* outputs, const int64_t N, const int64_t T,
+                   double* values)
+{
+    using namespace nano::detail;
+    for (int64_t i = 0; i < N; ++i)
+    {
+        const array_t t(targets + i * T, T), o(outputs + i * T, T);
+        switch (kind)
+        {
+        case 0: values[i] = value<mse_t>(t, o); break;
+        case 1: values[i] = value<mae_t>(t, o); break;
+        case 2: values[i] = value<cauchy_t>(t, o); break;
+        case 3: values[i] = value<hinge_t>(t, o); break;
+        case 4: values[i] = value<squared_hinge_t>(t, o); break;
+        case 5: values[i] = value<classnll_t>(t, o); break;
+        case 6: values[i] = value<savage_t>(t, o); break;
+        case 7: values[i] = value<tangent_t>(t, o); break;
+        case 8: values[i] = value<logistic_t>(t, o); break;
+        case 9: values[i] = value<exponential_t>(t, o); break;
+        default: return 1;
+        }
+    }
+    return 0;
+}
+
+int ref_loss_vgrad(const int kind, const double* targets, const double* outputs, const int64_t N, const int64_t T,
+                   double* vgrads)
+{
+    using namespace nano::detail;
+    for (int64_t i = 0; i < N; ++i)
+    {
+        const array_t t(targets + i * T, T), o(outputs + i * T, T);
+        array_t       g(T);
+        switch (kind)
+        {
+        case 0: vgrad<mse_t>(t, o, g); break;
+        case 1: vgrad<mae_t>(t, o, g); break;
+        case 2: vgrad<cauchy_t>(t, o, g); break;
+        case 3: vgrad<hinge_t>(t, o, g); break;
+        case 4: vgrad<squared_hinge_t>(t, o, g); break;
+        case 5: vgrad<classnll_t>(t, o, g); break;
+        case 6: vgrad<savage_t>(t, o, g); break;
+        case 7: vgrad<tangent_t>(t, o, g); break;
+        case 8: vgrad<logistic_t>(t, o, g); break;
+        case 9: vgrad<exponential_t>(t, o, g); break;
+        default: return 1;
+        }
+        for (int64_t k = 0; k < T; ++k)
+        {
+            vgrads[i * T + k] = g(k);
+        }
+    }
+    return 0;
+}
+}

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_loss_golden.json from the REFERENCE'S OWN loss code.
+
+oracle/_ref/libref_loss.so (make -C oracle ref) is /root/reference/include/nano/loss/{mse,mae,cauchy,hinge,squared_hinge,
+classnll,savage,tangent,logistic,exponential}.h compiled unmodified, in place, over the stand-in for the slice of Eigen's
+array API they use (oracle/ref_shim/nano/tensor/eigen.h; Eigen3 itself is not installed in this image). This script runs
+only where /root/reference exists; the JSON it writes is committed, and tests/ compare the oracle (CPU) and the CUDA
+loss kernels (GPU) with it. Numbers are stored as float.hex() strings: bit-exact round trip.
+
+    make -C oracle ref && python tests/golden/make_ref_golden.py
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+KINDS = {"mse": 0, "mae": 1, "cauchy": 2, "hinge": 3, "squared-hinge": 4, "classnll": 5, "savage": 6, "tangent": 7,
+         "logistic": 8, "exponential": 9}
+CLASSIFICATION = {"hinge", "squared-hinge", "classnll", "savage", "tangent", "logistic", "exponential"}
+
+
+def main():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_loss.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    for fn in (lib.ref_loss_value, lib.ref_loss_vgrad):
+        fn.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int64, ctypes.c_int64, dp]
+    rng = np.random.default_rng(20261020)
+    cases = []
+    for name, kind in KINDS.items():
+        for T in (1, 3, 10):
+            N = 24
+            outputs = rng.normal(0.0, 2.0, (N, T))
+            outputs[0] *= 10.0  # large margins: exp / log1p branches of logistic, saturation of savage / tangent
+            outputs[1] *= 0.01
+            if name in CLASSIFICATION:
+                if T == 1:
+                    targets = np.where(rng.uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+                else:
+                    targets = -np.ones((N, T))
+                    targets[np.arange(N), rng.integers(0, T, N)] = 1.0  # one-hot +-1 (include/nano/loss/class.h:51-58)
+                if name == "exponential":
+                    outputs = np.clip(outputs, -20.0, 20.0)
+                # exactly on the hinge kink (t * o == 1) and exactly zero outputs
+                outputs[2] = targets[2]
+                outputs[3] = 0.0
+            else:
+                targets = rng.normal(0.0, 2.0, (N, T))
+                outputs[2] = targets[2]  # zero residual: sign(0) == 0, |0|
+                outputs[3] = targets[3] + 1e-300
+            targets = np.ascontiguousarray(targets)
+            outputs = np.ascontiguousarray(outputs)
+            values = np.empty(N)
+            vgrads = np.empty((N, T))
+            assert lib.ref_loss_value(kind, targets.ctypes.data_as(dp), outputs.ctypes.data_as(dp), N, T,
+                                      values.ctypes.data_as(dp)) == 0
+            assert lib.ref_loss_vgrad(kind, targets.ctypes.data_as(dp), outputs.ctypes.data_as(dp), N, T,
+                                      vgrads.ctypes.data_as(dp)) == 0
+            assert np.all(np.isfinite(values)) and np.all(np.isfinite(vgrads)), (name, T)
+            cases.append({"loss": name, "T": T, "N": N,
+                          "targets": [float(v).hex() for v in targets.ravel()],
+                          "outputs": [float(v).hex() for v in outputs.ravel()],
+                          "values": [float(v).hex() for v in values],
+                          "vgrads": [float(v).hex() for v in vgrads.ravel()]})
+    payload = {"source": "reference loss headers include/nano/loss/*.h compiled in place (oracle/ref_loss.cpp, "
+                         "oracle/ref_shim/: stand-in for the Eigen array API, sequential sums)",
+               "generator": "tests/golden/make_ref_golden.py", "cases": cases}
+    path = os.path.join(HERE, "ref_loss_golden.json")
+    with open(path, "w") as handle:
+        json.dump(payload, handle)
+    print(path, len(cases), "cases", os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
