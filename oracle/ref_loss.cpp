@@ -14,6 +14,12 @@
 #include <nano/loss/squared_hinge.h>
 #include <nano/loss/tangent.h>
 
+// objective (B): the reference's src/function/mlearn/loss.{h,cpp}, unmodified; <function/mlearn/linear.h> resolves to
+// the stand-in in oracle/ref_shim/ (the real one needs Eigen3 proper)
+#include <function/mlearn/loss.h>
+
+#include "src/function/mlearn/loss.cpp" // -I /root/reference: compiled in place
+
 #include <cstdint>
 
 namespace
@@ -93,4 +99,30 @@ int ref_loss_vgrad(const int kind, const double* targets, const double* outputs,
     }
     return 0;
 }
+}
+
+// objective (B) losses, kind: 0 mse 1 mae 2 cauchy 3 hinge 4 logistic (oracle/__init__.py SYNTH_LOSSES).
+// outputs / targets [N, T] row-major -> fx (already divided by N, src/function/mlearn/loss.cpp) and gx [N, T]
+extern "C" int ref_synth_loss(const int kind, const double* outputs, const double* targets, const int64_t N, const int64_t T,
+                              double* fx, double* gx)
+{
+    using nano::refshim::array_t;
+    using nano::refshim::matrix_out_t;
+    using nano::refshim::matrix_val_t;
+    const matrix_val_t O(N, T, array_t(outputs, N * T)), Y(N, T, array_t(targets, N * T));
+    matrix_val_t       G(N, T, array_t(N * T));
+    switch (kind)
+    {
+    case 0: *fx = nano::loss_mse_t::fx(O, Y); nano::loss_mse_t::gx(O, Y, matrix_out_t{G}); break;
+    case 1: *fx = nano::loss_mae_t::fx(O, Y); nano::loss_mae_t::gx(O, Y, matrix_out_t{G}); break;
+    case 2: *fx = nano::loss_cauchy_t::fx(O, Y); nano::loss_cauchy_t::gx(O, Y, matrix_out_t{G}); break;
+    case 3: *fx = nano::loss_hinge_t::fx(O, Y); nano::loss_hinge_t::gx(O, Y, matrix_out_t{G}); break;
+    case 4: *fx = nano::loss_logistic_t::fx(O, Y); nano::loss_logistic_t::gx(O, Y, matrix_out_t{G}); break;
+    default: return 1;
+    }
+    for (int64_t i = 0; i < N * T; ++i)
+    {
+        gx[i] = G.data()(i);
+    }
+    return 0;
 }

@@ -99,6 +99,10 @@ public:
         return (*this)(best);
     }
 
+    // (Eigen: array -> vector -> diagonal matrix; only named by Hessian members that are never called)
+    const array_t& matrix() const { return *this; }
+    const array_t& asDiagonal() const { return *this; }
+
     array_t  operator-() const { return map([](const scalar_t v) { return -v; }); }
     array_t& operator/=(const scalar_t s)
     {

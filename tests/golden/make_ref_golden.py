@@ -64,13 +64,36 @@ def main():
                           "outputs": [float(v).hex() for v in outputs.ravel()],
                           "values": [float(v).hex() for v in values],
                           "vgrads": [float(v).hex() for v in vgrads.ravel()]})
-    payload = {"source": "reference loss headers include/nano/loss/*.h compiled in place (oracle/ref_loss.cpp, "
-                         "oracle/ref_shim/: stand-in for the Eigen array API, sequential sums)",
+    # objective (B): src/function/mlearn/loss.cpp (fx is already divided by the sample count; T = 1)
+    lib.ref_synth_loss.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int64, ctypes.c_int64, dp, dp]
+    synth = []
+    for name, kind in (("mse", 0), ("mae", 1), ("cauchy", 2), ("hinge", 3), ("logistic", 4)):
+        N = 24
+        outputs = rng.normal(0.0, 2.0, (N, 1))
+        outputs[0] *= 10.0
+        if name in ("hinge", "logistic"):
+            targets = np.where(rng.uniform(-1, 1, (N, 1)) < 0, -1.0, 1.0)
+            outputs[2] = targets[2]  # on the hinge kink
+        else:
+            targets = rng.normal(0.0, 2.0, (N, 1))
+            outputs[2] = targets[2]  # zero residual
+        fx = ctypes.c_double()
+        gx = np.empty((N, 1))
+        assert lib.ref_synth_loss(kind, outputs.ctypes.data_as(dp), targets.ctypes.data_as(dp), N, 1, ctypes.byref(fx),
+                                  gx.ctypes.data_as(dp)) == 0
+        assert np.isfinite(fx.value) and np.all(np.isfinite(gx))
+        synth.append({"loss": name, "N": N, "outputs": [float(v).hex() for v in outputs.ravel()],
+                      "targets": [float(v).hex() for v in targets.ravel()], "fx": float(fx.value).hex(),
+                      "gx": [float(v).hex() for v in gx.ravel()]})
+
+    payload = {"synth": synth, "source": "reference loss code compiled in place: include/nano/loss/*.h (cases) and "
+                         "src/function/mlearn/loss.cpp (synth); oracle/ref_loss.cpp over oracle/ref_shim/ (stand-in for "
+                         "the Eigen array / matrix vocabulary, sequential sums)",
                "generator": "tests/golden/make_ref_golden.py", "cases": cases}
     path = os.path.join(HERE, "ref_loss_golden.json")
     with open(path, "w") as handle:
         json.dump(payload, handle)
-    print(path, len(cases), "cases", os.path.getsize(path), "bytes")
+    print(path, len(cases), "cases +", len(synth), "synth cases", os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
