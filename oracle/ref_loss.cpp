@@ -20,6 +20,12 @@
 
 #include "src/function/mlearn/loss.cpp" // -I /root/reference: compiled in place
 
+// the random stream of the builtin test functions (linear_model_t, src/function/mlearn/linear.cpp:15-20): the
+// reference's own make_rng / make_udist (std-only sources, compiled in place)
+#include <nano/core/random.h>
+
+#include "src/core/random.cpp"
+
 #include <cstdint>
 
 namespace
@@ -123,6 +129,18 @@ extern "C" int ref_synth_loss(const int kind, const double* outputs, const doubl
     for (int64_t i = 0; i < N * T; ++i)
     {
         gx[i] = G.data()(i);
+    }
+    return 0;
+}
+
+// the first n draws of `auto rng = make_rng(seed); auto udist = make_udist<scalar_t>(0.0, 1.0);` (linear.cpp:15-16)
+extern "C" int ref_rng_draws(const uint64_t seed, const int64_t n, double* out)
+{
+    auto rng   = nano::make_rng(seed);
+    auto udist = nano::make_udist<nano::scalar_t>(0.0, 1.0);
+    for (int64_t i = 0; i < n; ++i)
+    {
+        out[i] = udist(rng);
     }
     return 0;
 }

@@ -86,7 +86,15 @@ def main():
                       "targets": [float(v).hex() for v in targets.ravel()], "fx": float(fx.value).hex(),
                       "gx": [float(v).hex() for v in gx.ravel()]})
 
-    payload = {"synth": synth, "source": "reference loss code compiled in place: include/nano/loss/*.h (cases) and "
+    # the random stream of linear_model_t (seed 42 as in BASELINE config 1, and another seed)
+    lib.ref_rng_draws.argtypes = [ctypes.c_uint64, ctypes.c_int64, dp]
+    draws = {}
+    for seed in (42, 7):
+        out = np.empty(32)
+        assert lib.ref_rng_draws(seed, out.size, out.ctypes.data_as(dp)) == 0
+        draws[str(seed)] = [float(v).hex() for v in out]
+
+    payload = {"rng_draws": draws, "synth": synth, "source": "reference loss code compiled in place: include/nano/loss/*.h (cases) and "
                          "src/function/mlearn/loss.cpp (synth); oracle/ref_loss.cpp over oracle/ref_shim/ (stand-in for "
                          "the Eigen array / matrix vocabulary, sequential sums)",
                "generator": "tests/golden/make_ref_golden.py", "cases": cases}
