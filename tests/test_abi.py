@@ -74,6 +74,31 @@ def test_register_hand_over_matches_the_allocation(library):
             assert int(regs) <= 255 and int(regs) * threads <= 65536 + 255, (ncw, regs)
 
 
+def test_hot_kernels_keep_their_code_generation(library):
+    # guards against silent code-generation regressions of the kind found in round 1 (one translation unit under
+    # -split-compile: adding unrelated kernels changed mt_backward_kernel's SASS and cost config 3 15 %): the hot
+    # kernels of each family must not spill beyond what was measured, and the backward kernel keeps its size
+    out = subprocess.run(["cuobjdump", "-res-usage", library._name], capture_output=True, text=True).stdout
+    stack = dict(re.findall(r"Function (\w+):\s*\n\s*REG:\d+ STACK:(\d+)", out))
+    limits = {
+        "_ZN5nb20015vgrad_t1_kernelILi2ELi16ELi1ELi4ELi2ELi1ELb1EEEvNS_9t1_paramsE": 32,   # config 2 (variant 27)
+        "_ZN5nb20015vgrad_t1_kernelILi2ELi8ELi2ELi8ELi4ELi2ELb1EEEvNS_9t1_paramsE": 128,   # config 4 shards (37)
+        "_ZN5nb20015vgrad_t1_kernelILi2ELi8ELi1ELi8ELi4ELi2ELb1EEEvNS_9t1_paramsE": 128,   # config 5 (33)
+        "_ZN5nb20018mt_backward_kernelILi13EEEvNS_18mt_backward_paramsE": 0,               # config 3
+        "_ZN5nb20017mt_forward_kernelILi13ELb1EEEvNS_17mt_forward_paramsE": 0,
+        "_ZN5nb20015vgrad_fd_kernelILi2ELi13ELi1ELb1EEEvNS_9fd_paramsE": 32,               # 784 x 10
+        "_ZN5nb20015vgrad_fd_kernelILi1ELi32ELi2ELb1EEEvNS_9fd_paramsE": 0,                # 1024 x 8
+        "_ZN5nb20015vgrad_ft_kernelILi2ELi2ELi8ELi1ELb1EEEvNS_9ft_paramsE": 0,             # 1024 x 2
+    }
+    for name, limit in limits.items():
+        assert name in stack, name
+        assert int(stack[name]) <= limit, (name, stack[name])
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN5nb20018mt_backward_kernelILi13EEEvNS_18mt_backward_paramsE",
+                           library._name], capture_output=True, text=True).stdout
+    instructions = len(re.findall(r"^\s+/\*[0-9a-f]{4,5}\*/", sass, flags=re.M))
+    assert 1200 <= instructions <= 1900, instructions  # 1.6 k when compiled on its own; 2.1 k in the regressed build
+
+
 def test_no_gpu_means_loud_failure_not_fallback(library):
     from libnano_b200 import Context, Nb200Error, _lib
 
