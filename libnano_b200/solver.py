@@ -186,3 +186,336 @@ def osga(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, patience: i
 
     return {"x": best_x, "fx": best_f, "eta": float(eta), "status": status, "fcalls": function.fcalls(),
             "gcalls": function.gcalls(), "iterations": iterations}
+
+
+def _simplex_qp(K, h, max_iters: int = 200):
+    """argmin_a  a.K.a / 2 - h.a  over the unit simplex (K symmetric positive semi-definite, m x m, m <= ~100).
+
+    This is the DUAL of the bundle's quadratic program (bundle.cpp:109-168 builds the PRIMAL in n + 1 variables and
+    hands it to libnano's interior-point solver): here the program has one variable per cutting plane instead of one
+    per model parameter, which is what a linear model with n = (D + 1) T parameters wants. Mehrotra predictor-corrector
+    on the KKT system  K a - h + nu 1 - s = 0,  1.a = 1,  a o s = 0,  a, s >= 0; returns the multipliers a."""
+    m = h.size
+    if m == 1:
+        return np.ones(1)
+    scale = max(float(np.max(np.abs(K))), float(np.max(np.abs(h))), 1e-300)
+    K, h = K / scale, h / scale
+    a = np.full(m, 1.0 / m)
+    s = np.ones(m)
+    nu = 0.0
+    ones = np.ones(m)
+    for _ in range(max_iters):
+        rd = K @ a - h + nu - s
+        rp = float(a.sum()) - 1.0
+        mu = float(a @ s) / m
+        if max(float(np.max(np.abs(rd))), abs(rp)) <= 1e-14 and mu <= 1e-16:
+            break
+        H = K + np.diag(s / a)
+        Hinv = None
+        for ridge in (0.0, 1e-14, 1e-11, 1e-8):               # K is only semi-definite up to rounding
+            try:
+                Hinv = np.linalg.inv(H + ridge * (1.0 + float(np.max(np.abs(np.diag(H))))) * np.eye(m))
+            except np.linalg.LinAlgError:
+                continue
+            if np.all(np.isfinite(Hinv)):
+                break
+            Hinv = None
+        critical(Hinv is not None, "solver: the bundle's quadratic program is singular (degenerate metric)")
+        z2 = Hinv @ ones
+        z2_sum = float(z2.sum())
+        critical(z2_sum > 0.0, "solver: the bundle's quadratic program is not convex (indefinite metric)")
+
+        def solve(rc):
+            # (K + S/A) da + 1 dnu = -rd - rc / a,  1.da = -rp   with rc = the complementarity residual a o s - target
+            z1 = Hinv @ (-rd - rc / a)
+            dnu = (float(z1.sum()) + rp) / z2_sum
+            da = z1 - dnu * z2
+            ds = -(rc + s * da) / a
+            return da, dnu, ds
+
+        def step_to_boundary(v, dv):
+            neg = dv < 0.0
+            return min(1.0, float(np.min(-v[neg] / dv[neg]))) if np.any(neg) else 1.0
+
+        da, dnu, ds = solve(a * s)                                          # predictor (affine scaling)
+        alpha_aff = min(step_to_boundary(a, da), step_to_boundary(s, ds))
+        mu_aff = float((a + alpha_aff * da) @ (s + alpha_aff * ds)) / m
+        sigma = (mu_aff / mu) ** 3 if mu > 0.0 else 0.0
+        da, dnu, ds = solve(a * s + da * ds - sigma * mu)                   # corrector
+        alpha_p = min(1.0, 0.995 * step_to_boundary(a, da)) if np.any(da < 0) else 1.0
+        alpha_d = min(1.0, 0.995 * step_to_boundary(s, ds)) if np.any(ds < 0) else 1.0
+        a = a + alpha_p * da
+        s = s + alpha_d * ds
+        nu = nu + alpha_d * dnu
+    # planes on the inactive side of the complementarity pairs get an exact zero (the bundle drops them), then one
+    # equality-constrained solve on the support removes the interior-point method's O(mu) bias when it stays feasible
+    support = a > s
+    if not np.any(support):
+        support = a >= float(np.max(a))
+    a = np.where(support, a, 0.0)
+    a /= float(a.sum())
+    k = int(support.sum())
+    kkt = np.zeros((k + 1, k + 1))
+    kkt[:k, :k] = K[np.ix_(support, support)]
+    kkt[:k, k] = kkt[k, :k] = 1.0
+    polished = np.linalg.lstsq(kkt, np.append(h[support], 1.0), rcond=None)[0]
+    if np.all(np.isfinite(polished)) and np.all(polished[:k] > 0.0) and abs(float(polished[:k].sum()) - 1.0) < 1e-9:
+        candidate = np.zeros(m)
+        candidate[support] = polished[:k] / float(polished[:k].sum())
+
+        def objective(v):
+            return 0.5 * float(v @ (K @ v)) - float(h @ v)
+
+        if objective(candidate) <= objective(a):
+            a = candidate
+    return a
+
+
+class _Bundle:
+    """The bundle of cutting planes of libnano's proximal bundle solvers (bundle_t, src/solver/bundle/bundle.cpp):
+    rows (g_j, h_j) with h_j = f_j + g_j.(x - x_j) relative to the stability centre x, kept small by dropping the
+    planes with zero multipliers and, at capacity, the two smallest ones in favour of the aggregate plane."""
+
+    def __init__(self, x, gx, fx, max_size):
+        n = x.size
+        self.G = np.zeros((max_size + 1, n))
+        self.H = np.zeros(max_size + 1)
+        self.size = 0
+        self.x, self.gx, self.fx = x.copy(), gx.copy(), float(fx)
+        self.alphas = np.zeros(0)
+        self.solution_x = x.copy()
+        self.solution_g = np.zeros(n)
+        self._gram = None                                     # (M^-1 G', G M^-1 G') of the current planes and metric
+        self._append(x, gx, fx, True)
+
+    def capacity(self):
+        return self.H.size
+
+    def tol(self, epsilon):                                   # etol == gtol (bundle.cpp:66-74)
+        return epsilon * (1.0 + abs(self.fx))
+
+    def fhat(self, z):                                        # bundle.cpp:170-180
+        return float(np.max(self.H[:self.size] + self.G[:self.size] @ (z - self.x)))
+
+    def solve(self, apply_inverse_metric, t):
+        """Proximal point y = argmin fhat(z) + (z - x).M.(z - x) / (2 t)  (bundle.cpp:95-168 without the level
+        constraint, which RQB never sets). Through the dual:  y = x - t M^-1 G'a  with a = _simplex_qp(t G M^-1 G', h)."""
+        G, H = self.G[:self.size], self.H[:self.size]
+        if self._gram is None:                                # planes and metric are fixed during one curve search
+            Z = apply_inverse_metric(G.T)                     # n x m
+            K = G @ Z
+            self._gram = (Z, 0.5 * (K + K.T))
+        Z, K = self._gram
+        self.alphas = _simplex_qp(t * K, H)
+        self.solution_g = G.T @ self.alphas
+        self.solution_x = self.x - t * (Z @ self.alphas)
+        return self.solution_x
+
+    def _remove(self, drop):
+        keep = np.flatnonzero(~drop)
+        self.G[:keep.size] = self.G[keep]
+        self.H[:keep.size] = self.H[keep]
+        self.alphas = self.alphas[keep]
+        self.size = keep.size
+
+    def _append(self, y, gy, fy, serious_step):               # bundle.cpp:247-275
+        if self.size + 1 == self.capacity() and self.alphas.size == self.size:
+            # delete_inactive(epsilon0) (bundle.cpp:182-188) - only once the bundle is full: the dual solve returns
+            # exact zeros for every inactive plane, where the reference's interior-point multipliers stay above
+            # 1e-15 for all but the far-away planes, so dropping zeros after every step would discard most of the
+            # model each time
+            self._remove(self.alphas < 1e-15)
+            if self.size + 1 == self.capacity():              # delete_smallest(2) + aggregate (bundle.cpp:190-245)
+                # the aggregate plane: (sum_j a_j g_j, fhat(y)); the reference writes (x - y) / tau for its gradient
+                # (bundle.cpp:232), which equals this only under the identity metric - under RQB's variable metric
+                # that plane is not a minorant of f, so the true aggregate is used here
+                agg_h = self.fhat(self.solution_x) + float(self.solution_g @ (self.x - self.solution_x))
+                agg_g = self.solution_g.copy()
+                order = np.argsort(self.alphas, kind="stable")[:2]
+                drop = np.zeros(self.size, dtype=bool)
+                drop[order] = True
+                self._remove(drop)
+                self.G[self.size], self.H[self.size] = agg_g, agg_h
+                self.alphas = np.append(self.alphas, 1.0)
+                self.size += 1
+        if serious_step:
+            self.H[:self.size] += self.G[:self.size] @ (y - self.x)
+            self.x, self.gx, self.fx = y.copy(), gy.copy(), float(fy)
+        self.G[self.size] = gy
+        self.H[self.size] = fy + float(gy @ (self.x - y))
+        self.size += 1
+        self.alphas = np.zeros(0)                             # multipliers are recomputed by the next solve
+        self._gram = None
+
+    def moveto(self, y, gy, fy):
+        self._append(y, gy, fy, True)
+
+    def append(self, y, gy, fy):
+        self._append(y, gy, fy, False)
+
+
+def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: int = 100, prox_type: str = "sr1",
+        tau_min: float = 1e-5, m1m2=(0.5, 0.9), m3: float = 1.0, m4: float = 1.0, interpol: float = 0.3,
+        extrapol: float = 5.0, reference_init: bool = False):
+    """Host-driven RQB, the reversal quasi-Newton proximal bundle solver BASELINE config 5 names next to OSGA
+    (solver_rqb_t::do_minimize src/solver/rqb.cpp:23-71; curve search src/solver/bundle/csearch.cpp:40-153; metric
+    src/solver/bundle/quasi.cpp; bundle src/solver/bundle/bundle.cpp) over `function(x, gx)`.
+
+    One f(y, gy) through the host-buffer call per trial point, exactly how libnano's RQB drives a function_t; the
+    bundle algebra stays on the host (at most max_size + 1 planes of n doubles). prox_type "sr1" keeps an n x n
+    metric (n <= 8192); "miu" the scaled identity at any n. Defaults: src/solver.cpp:45-51, csearch.cpp:155-162,
+    quasi.cpp:116-120, bundle.cpp:277-280.
+
+    Same algorithm, different numerics behind the proximal point (the reference keeps its own RQB tests disabled,
+    test/test_solver_bundle.cpp:11, so there is no reference trajectory to pin; tests/test_host_solvers.py checks
+    the optimum against a linear program instead):
+      * the quadratic program is solved in its dual - one variable per plane (_simplex_qp) - instead of the
+        reference's interior-point solve in n + 1 variables, and the inverse metric is carried along by the matching
+        rank-one formula (W += e e' / e.v) instead of being factorised per solve;
+      * inactive planes are dropped only when the bundle is full, and the aggregate plane is the true aggregate
+        (_Bundle._append);
+      * the metric starts at I / tau0 (reference_init=True restores quasi.cpp:33's tau0 I), the scaled-identity
+        update keeps positive candidates only and moves at most a decade per step (quasi_update);
+      * the convexity tests of the curve search get the parity bar's 1e-12 relative slack (csearch.cpp:99)."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = function.size()
+    critical(x0.ndim == 1 and x0.size == n, "solver: incompatible initial point (", x0.size, " dimensions), expecting ",
+             n, " dimensions!")
+    critical(prox_type in ("sr1", "miu"), "solver: unknown rqb metric '", prox_type, "', expecting sr1 or miu")
+    critical(prox_type == "miu" or n <= 8192, "solver: rqb with the sr1 metric keeps two ", n, " x ", n,
+             " matrices on the host, use prox_type='miu'")
+    m1, m2 = m1m2
+    eps0 = 1e-15
+
+    function.clear_statistics()
+    g = np.empty(n)
+    x, fx = x0.copy(), float(function(x0, g))
+    gx = g.copy()
+
+    def evals():
+        return function.fcalls() + function.gcalls()
+
+    def valid():
+        return np.isfinite(fx) and bool(np.all(np.isfinite(x))) and bool(np.all(np.isfinite(gx)))
+
+    result_status, iterations = "max_iters", 0
+    if not valid():
+        return {"x": x, "fx": fx, "status": "failed", "fcalls": function.fcalls(), "gcalls": function.gcalls(),
+                "iterations": 0}
+
+    # quasi_t (quasi.cpp:9-41): M0 = tau0 I, history of (x, g, G) at the last two serious iterates
+    gg = float(gx @ gx)
+    tau0 = max(1.0, abs(fx)) / (5.0 * gg) if gg > 0.0 else np.inf
+    tau0 = max(tau0, tau_min) if np.isfinite(tau0) else tau_min
+    # The proximal term is (z - x).M.(z - x) / (2 t), so M is a curvature (1 / step size). quasi.cpp:33 starts it at
+    # tau0 I, the step size of (6) itself; with that start the metric is ~|g|^-4 too stiff in every direction the
+    # rank-one updates have not touched yet and the solver crawls (the reference keeps its own RQB tests disabled,
+    # test/test_solver_bundle.cpp:11, test/test_linear_elastic_net.cpp:11). M0 = I / tau0 unless reference_init.
+    miu = tau0 if reference_init else 1.0 / tau0
+    M = np.eye(n) * miu if prox_type == "sr1" else None
+    W = np.eye(n) / miu if prox_type == "sr1" else None
+    xn1, gn1, Gn1 = x.copy(), gx.copy(), gx.copy()
+    xn, gn, Gn = xn1, gn1, Gn1
+
+    def apply_metric(v):
+        return M @ v if M is not None else miu * v
+
+    def apply_inverse_metric(v):
+        return W @ v if W is not None else v / miu
+
+    def quasi_update(y, gy, G, is_descent_step):              # quasi.cpp:43-114
+        nonlocal xn, gn, Gn, xn1, gn1, Gn1, miu, M, W
+        xn, gn, Gn = xn1, gn1, Gn1
+        xn1, gn1, Gn1 = y.copy(), gy.copy(), G.copy()
+        if not is_descent_step:
+            return
+        e = xn1 - xn
+        if prox_type == "miu":
+            v1 = Gn1 - Gn
+            candidates = []
+            with np.errstate(all="ignore"):
+                for v in (v1, Gn1 - gn, gn1 - Gn, gn1 - gn):
+                    value = 1.0 / (np.float64(v @ e) / np.float64(v1 @ v) + 1.0 / miu)
+                    # the reference keeps any finite candidate (quasi.cpp:80-83); a negative one makes the metric
+                    # indefinite and the quadratic program unbounded, so only positive ones are kept here
+                    candidates.append(float(value) if np.isfinite(value) and value > 0.0 else np.finfo(float).max)
+            if min(candidates) != np.finfo(float).max:
+                miu = min(max(min(candidates), 0.1 * miu), 10.0 * miu)    # safeguard: at most a decade per serious step
+            return
+        v = gn1 - gn
+        Me = M @ e
+        denom = float(e @ (Me + v))
+        if abs(denom) >= 1e-8 * float(np.linalg.norm(e)) * float(np.linalg.norm(Me + v)):
+            M -= np.outer(Me, Me) / denom
+            ev = float(e @ v)                                 # Sherman-Morrison: (M - Me Me'/c)^-1 = W + e e' / (c - e.Me)
+            if abs(ev) > 1e-300 * max(1.0, abs(denom)):
+                W += np.outer(e, e) / ev
+            else:
+                W[...] = np.linalg.pinv(M)
+
+    bundle = _Bundle(x, gx, fx, max_size)
+    y, gy = x.copy(), np.empty(n)
+
+    while evals() < max_evals:
+        # csearch_t::search (csearch.cpp:40-153)
+        t, tL, tR = 1.0, 0.0, np.inf
+        status = "budget"
+        while evals() < max_evals:
+            cx, cfx = bundle.x, bundle.fx
+            try:
+                y = bundle.solve(apply_inverse_metric, t)
+            except RuntimeError:                              # indefinite metric: the reference's QP solver fails too
+                status = "failed"
+                break
+            fy = float(function(y, gy))
+            fyhat = bundle.fhat(y)
+            gyhat = apply_metric(cx - y) / t
+            step = y - cx
+            delta = cfx - fyhat + 0.5 * float(gyhat @ step)
+            error = cfx - fy + float(gy @ step)
+            epsil = cfx - fyhat + float(gyhat @ step)
+            gnorm = float(np.linalg.norm(gyhat))
+            tol = bundle.tol(epsilon)
+            econv, gconv = epsil <= tol, gnorm <= tol
+            if econv and gconv:                               # stopping criterion (35)
+                status = "converged"
+                break
+            # delta and error are non-negative for a convex f in exact arithmetic; f itself is only pinned to 1e-12
+            # relative (the parity bar), so the reference's `< 0` tests (csearch.cpp:99) get that much slack
+            slack = 1e-12 * (1.0 + abs(cfx))
+            if not np.isfinite(fy) or delta < -slack or error < -slack:
+                status = "failed"
+                break
+            if fy < cfx - m1 * delta:                         # descent test (31)
+                tL = t
+                if float(gy @ step) >= -m2 * delta:           # test (34)
+                    status = "descent_step"
+                    break
+                if not np.isfinite(tR) and (gconv or float(gyhat @ step) >= -m4 * epsil):   # cutting-plane test (36)
+                    status = "cutting_plane_step"
+                    break
+            else:
+                tR = t
+                if tL < eps0 and error <= m3 * delta:         # null-step test (33)
+                    status = "null_step"
+                    break
+            t = (1.0 - interpol) * tL + interpol * tR if np.isfinite(tR) else t * extrapol
+
+        iterations += 1
+        if status == "budget":
+            break
+        if status == "failed" or not valid():                 # solver_t::done_specific_test (src/solver.cpp:175-182)
+            result_status = "failed"
+            break
+        if status == "converged":
+            result_status = "specific_test"
+            break
+        if status in ("descent_step", "cutting_plane_step"):
+            quasi_update(y, gy, gyhat, status == "descent_step")
+            bundle.moveto(y, gy, fy)
+            x, gx, fx = y.copy(), gy.copy(), fy
+        else:
+            bundle.append(y, gy, fy)
+
+    return {"x": x, "fx": fx, "status": result_status, "fcalls": function.fcalls(), "gcalls": function.gcalls(),
+            "iterations": iterations}

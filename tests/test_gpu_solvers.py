@@ -166,6 +166,31 @@ def test_host_driven_osga_matches_the_restated_driver(ctx, oracle):
         assert mine["fcalls"] == 2 * mine["iterations"] + 1 and mine["gcalls"] == mine["iterations"] + 1
 
 
+@pytest.mark.parametrize("loss_id,l1,l2", [("s-hinge", 1e-2, 0.0), ("s-hinge", 1e-2, 1e-2), ("mae", 1e-2, 0.0)])
+def test_host_driven_rqb_on_nonsmooth_objectives(ctx, oracle, loss_id, l1, l2):
+    # BASELINE config 5 in small, second driver: the RQB proximal bundle solver through the GPU vgrad. Same driver
+    # over the CPU oracle objective (and, for lasso, the linear program's exact optimum) is the check.
+    import libnano_b200 as nb
+    from libnano_b200.solver import rqb
+    from test_host_solvers import OracleFunction, informative_problem, lasso_linear_program
+
+    N, D = 600, 8
+    X, Y = informative_problem(4, N, D, loss_id != "mae")
+    gpu = nb.LinearFunction(nb.Dataset.pin(ctx, X, Y), nb.Loss(loss_id), l1, l2)
+    cpu = OracleFunction(oracle, X, Y, loss_id, l1=l1, l2=l2)
+    x0 = np.zeros(gpu.size())
+    epsilon = 1e-8
+    r_gpu = rqb(gpu, x0, epsilon=epsilon, max_evals=4000)
+    r_cpu = rqb(cpu, x0, epsilon=epsilon, max_evals=4000)
+    assert r_gpu["status"] == "specific_test" and r_cpu["status"] == "specific_test", (r_gpu, r_cpu)
+    assert abs(r_gpu["fx"] - r_cpu["fx"]) <= 10 * epsilon * (1 + abs(r_cpu["fx"]))
+    assert abs(cpu(r_gpu["x"]) - r_gpu["fx"]) <= 1e-12 * (1 + abs(r_gpu["fx"]))
+    assert r_gpu["fcalls"] == r_gpu["gcalls"] == gpu.fcalls() and gpu.launches() > 0
+    if l2 == 0.0:
+        f_star = lasso_linear_program(X, Y, loss_id, l1)
+        assert f_star - 1e-10 <= r_gpu["fx"] <= f_star + 10 * epsilon * (1 + abs(f_star))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # device-resident CGD (nb200_cgd_minimize): the ten beta formulas of src/solver/cgd.cpp on the same skeleton
 # ----------------------------------------------------------------------------------------------------------------

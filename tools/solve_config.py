@@ -21,6 +21,7 @@ def main():
     parser.add_argument("--config", type=int, required=True, choices=[2, 4, 5])
     parser.add_argument("--rows-per-gpu", type=int, default=None)
     parser.add_argument("--max-evals", type=int, default=None)
+    parser.add_argument("--nonsmooth-solvers", default="osga", help="config 5: comma-separated subset of osga,rqb")
     args = parser.parse_args()
 
     import torch
@@ -28,7 +29,7 @@ def main():
 
     import libnano_b200 as nb
     from libnano_b200.sharded import ShardedFunction
-    from libnano_b200.solver import lbfgs, osga
+    from libnano_b200.solver import lbfgs, osga, rqb
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -71,12 +72,14 @@ def main():
         for name, l1, l2 in (("lasso", 1e-2, 0.0), ("elastic-net", 1e-2, 1e-2)):
             local = nb.LinearFunction(data, nb.Loss("s-hinge"), l1, l2)
             function = ShardedFunction.from_local(local, rows * world)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            result = osga(function, np.zeros(function.size()), epsilon=1e-6, max_evals=args.max_evals or 5000)
-            seconds = time.perf_counter() - t0
-            report(f"config5 s-hinge {name} osga(host-driven)", result, seconds,
-                   {"rows_per_gpu": rows, "features": D, "smooth": function.smooth(), "plan": local.describe()})
+            for solver_id in args.nonsmooth_solvers.split(","):
+                solver = {"osga": osga, "rqb": rqb}[solver_id]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                result = solver(function, np.zeros(function.size()), epsilon=1e-6, max_evals=args.max_evals or 5000)
+                seconds = time.perf_counter() - t0
+                report(f"config5 s-hinge {name} {solver_id}(host-driven)", result, seconds,
+                       {"rows_per_gpu": rows, "features": D, "smooth": function.smooth(), "plan": local.describe()})
     if world > 1:
         dist.destroy_process_group()
 
