@@ -63,6 +63,16 @@ typedef enum nb200_loss
     NB200_LOSS_COUNT          = 13
 } nb200_loss;
 
+/* error measures behind loss_t::error (include/nano/loss/error.h:11-70): which one a libnano loss id uses is its
+ * prefix (include/nano/loss/flatten.h:103-122): none -> absdiff, "s-" -> sclass, "m-" -> mclass. */
+typedef enum nb200_error
+{
+    NB200_ERROR_ABSDIFF = 0, /* regression: L1 distance between target and output                            */
+    NB200_ERROR_SCLASS  = 1, /* single-label: 0-1 error of the arg-max label (of the sign when T == 1)        */
+    NB200_ERROR_MCLASS  = 2, /* multi-label: number of labels with target * output < epsilon                  */
+    NB200_ERROR_COUNT   = 3
+} nb200_error;
+
 typedef enum nb200_flavour
 {
     /* nano::linear::function_t (src/linear/function.cpp): x = [W (T x D row-major) | b (T)], n = (D+1)*T,
@@ -277,6 +287,16 @@ NB200_API int nb200_loss_value(nb200_ctx* ctx, int loss, double loss_param, cons
                                const double* outputs, int64_t N, int64_t T, double* values);
 NB200_API int nb200_loss_vgrad(nb200_ctx* ctx, int loss, double loss_param, const double* targets,
                                const double* outputs, int64_t N, int64_t T, double* vgrads);
+
+/* per-sample errors[N] (loss_t::error, src/loss.cpp:50-55) for host targets/outputs[N,T]; error_kind: nb200_error. */
+NB200_API int nb200_loss_error(nb200_ctx* ctx, int error_kind, const double* targets, const double* outputs, int64_t N,
+                               int64_t T, double* errors);
+
+/* linear::evaluate (src/linear/util.cpp:30-49) over the pinned dataset: outputs = X W^T + b stay in HBM, the
+ * per-sample errors[N] and loss values[N] (either may be NULL) come back to the host. W[T,D], b[T] host. The
+ * pinball loss reports its value as its error (src/loss/pinball.cpp:20-23) whatever error_kind says. */
+NB200_API int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, int loss, double loss_param, int error_kind,
+                             const double* W, const double* b, double* errors, double* values);
 
 /* Host-side data of the builtin synthetic test functions: the random part of the linear_model_t constructor
  * (src/function/mlearn/linear.cpp:15-33): rng = std::mt19937_64(seed), u ~ uniform_real_distribution(0, 1);

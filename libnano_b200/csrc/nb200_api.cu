@@ -2224,6 +2224,96 @@ int nb200_loss_vgrad(nb200_ctx* ctx, const int loss, const double loss_param, co
     return loss_rows(ctx, loss, loss_param, targets, outputs, N, T, nullptr, vgrads);
 }
 
+int nb200_loss_error(nb200_ctx* ctx, const int error_kind, const double* targets, const double* outputs,
+                     const int64_t N, const int64_t T, double* errors)
+{
+    NB200_REQUIRE(ctx != nullptr && targets != nullptr && outputs != nullptr && errors != nullptr,
+                  "loss error: null argument");
+    NB200_REQUIRE(error_kind >= 0 && error_kind < NB200_ERROR_COUNT, "loss error: unknown error kind");
+    NB200_REQUIRE(N >= 0 && T > 0, "loss error: invalid dimensions");
+    if (N == 0)
+    {
+        return NB200_OK;
+    }
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t bytes = static_cast<size_t>(N) * T * sizeof(double);
+    double *     dT = nullptr, *dO = nullptr, *dE = nullptr;
+    const auto   run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&dT, bytes));
+        NB200_CUDA_TRY(cudaMalloc(&dO, bytes));
+        NB200_CUDA_TRY(cudaMalloc(&dE, static_cast<size_t>(N) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dT, targets, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dO, outputs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        loss_error_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, ctx->stream>>>(error_kind, dT, dO, N, T, dE);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaMemcpyAsync(errors, dE, static_cast<size_t>(N) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(dT);
+    cudaFree(dO);
+    cudaFree(dE);
+    return status;
+}
+
+int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, const int loss, const double loss_param,
+                   const int error_kind, const double* W, const double* b, double* errors, double* values)
+{
+    NB200_REQUIRE(ctx != nullptr && data != nullptr && W != nullptr && b != nullptr, "evaluate: null argument");
+    NB200_REQUIRE(errors != nullptr || values != nullptr, "evaluate: nothing to compute");
+    NB200_REQUIRE(ctx->device == data->device, "evaluate: context and dataset live on different devices");
+    NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "evaluate: unknown loss");
+    NB200_REQUIRE(error_kind >= 0 && error_kind < NB200_ERROR_COUNT, "evaluate: unknown error kind");
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t N = data->N, D = data->D, T = data->T;
+    const size_t  rows = static_cast<size_t>(N) * sizeof(double);
+    double *      dW = nullptr, *db = nullptr, *dO = nullptr, *dE = nullptr, *dV = nullptr;
+    const auto    run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaMalloc(&dW, static_cast<size_t>(T) * D * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&db, static_cast<size_t>(T) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&dO, rows * T));
+        NB200_CUDA_TRY(cudaMalloc(&dE, rows));
+        NB200_CUDA_TRY(cudaMalloc(&dV, rows));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dW, W, static_cast<size_t>(T) * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        NB200_CUDA_TRY(cudaMemcpyAsync(db, b, static_cast<size_t>(T) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        predict_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(data->X, dW, db, N, D, T, dO);
+        NB200_CUDA_TRY(cudaGetLastError());
+        const unsigned blocks = static_cast<unsigned>((N + 255) / 256);
+        // pinball's error is its value (src/loss/pinball.cpp:20-23)
+        const bool error_is_value = loss == NB200_LOSS_PINBALL;
+        if (values != nullptr || error_is_value)
+        {
+            loss_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(loss, loss_param, data->Y, dO, N, T, dV, nullptr);
+            NB200_CUDA_TRY(cudaGetLastError());
+        }
+        if (errors != nullptr && !error_is_value)
+        {
+            loss_error_kernel<<<blocks, 256, 0, ctx->stream>>>(error_kind, data->Y, dO, N, T, dE);
+            NB200_CUDA_TRY(cudaGetLastError());
+        }
+        if (errors != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMemcpyAsync(errors, error_is_value ? dV : dE, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (values != nullptr)
+        {
+            NB200_CUDA_TRY(cudaMemcpyAsync(values, dV, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    };
+    const int status = N > 0 ? run() : NB200_OK;
+    cudaFree(dW);
+    cudaFree(db);
+    cudaFree(dO);
+    cudaFree(dE);
+    cudaFree(dV);
+    return status;
+}
+
 int nb200_synth_linear_inputs(const int64_t samples, const int64_t inputs, const uint64_t seed, const int64_t modulo,
                               double* X, double* wopt, double* bopt)
 {

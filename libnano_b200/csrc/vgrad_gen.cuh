@@ -312,5 +312,45 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(const int kind, const do
     }
 }
 
+// elementwise loss_t::error over (N, T) (include/nano/loss/flatten.h:62-67 -> include/nano/loss/error.h:11-70); one
+// thread per sample. error_kind: 0 absdiff, 1 sclass, 2 mclass (include/nb200.h: nb200_error)
+__global__ void __launch_bounds__(256) loss_error_kernel(const int error_kind, const double* __restrict__ targets,
+                                                         const double* __restrict__ outputs, const int64_t N,
+                                                         const int64_t T, double* __restrict__ errors)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N)
+    {
+        return;
+    }
+    const double* t     = targets + i * T;
+    const double* o     = outputs + i * T;
+    double        error = 0.0;
+    if (error_kind == 0)
+    {
+        for (int64_t k = 0; k < T; ++k)
+        {
+            error += fabs(__dsub_rn(t[k], o[k]));
+        }
+    }
+    else if (error_kind == 1 && T > 1)
+    {
+        int64_t idx = 0;  // Eigen's maxCoeff keeps the first maximum
+        for (int64_t k = 1; k < T; ++k)
+        {
+            idx = (o[k] > o[idx]) ? k : idx;
+        }
+        error = (t[idx] > 0.0) ? 0.0 : 1.0;
+    }
+    else
+    {
+        for (int64_t k = 0; k < T; ++k)
+        {
+            error += (__dmul_rn(t[k], o[k]) < 2.220446049250313e-16) ? 1.0 : 0.0;
+        }
+    }
+    errors[i] = error;
+}
+
 #endif // __CUDACC__
 } // namespace nb200

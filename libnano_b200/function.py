@@ -148,6 +148,16 @@ class Dataset:
         _lib.check(_lib.lib().nb200_predict(self.ctx.handle, self.handle, _ptr(W), _ptr(b), _ptr(out)))
         return out
 
+    def evaluate(self, loss: Loss, W, b):
+        """linear::evaluate (src/linear/util.cpp:30-49): [2, N] = per-sample (errors, loss values) of the predictions
+        X W^T + b against the pinned targets; the outputs never leave HBM."""
+        W = np.ascontiguousarray(W, dtype=np.float64).reshape(self.targets, self.inputs)
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(self.targets)
+        out = np.empty((2, self.samples), dtype=np.float64)
+        _lib.check(_lib.lib().nb200_evaluate(self.ctx.handle, self.handle, loss.kind, loss.param, loss.error_kind,
+                                             _ptr(W), _ptr(b), _ptr(out[0]), _ptr(out[1])))
+        return out
+
     def close(self):
         if getattr(self, "handle", None):
             _lib.lib().nb200_dataset_release(self.handle)

@@ -1,0 +1,247 @@
+"""Mirror of nano::linear_t::fit (src/linear.cpp:30-48,79-116) over the GPU objective — SURVEY §8f row N1: the caller
+either side of the hot path. One fit = pin the selected samples in HBM, scale them there (flatten_iterator_t::scaling),
+minimise linear::function_t with a solver that drives the CUDA vgrad, upscale (W, b) back to the original units
+(nano::upscale) and evaluate the per-sample (error, loss) on the device (linear::evaluate). Around it: the
+hyper-parameter tuning of ml::tune (src/machine/tune.cpp:8-58) — k-fold splits (src/splitter/kfold.cpp), the coarse
+grid + local search of the tuner (src/tuner.cpp:17-42, src/tuner/local.cpp, src/tuner/util.cpp:60-118), warm starts
+from the closest earlier trial (src/machine/result.cpp:82-100) — and the final refit on all samples.
+
+The four registered models (src/linear.cpp:124-139) differ in which regularisers they tune (src/linear/{ordinary,
+lasso,ridge,elastic_net}.cpp). What is NOT mirrored: the surrogate tuner, serialization, the file loggers."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from .function import Dataset, LinearFunction, critical
+from .loss import ERROR_ABSDIFF, Loss
+
+# linear::make_param_space (src/linear/util.cpp:75-86)
+PARAM_GRID = tuple(float(f"{m}e{e}") for e in range(-8, 7) for m in (1, 3)) + (1e7,)
+# make_param_spaces of the registered ids
+MODELS = {"ordinary": (), "lasso": ("l1reg",), "ridge": ("l2reg",), "elastic_net": ("l1reg", "l2reg")}
+
+
+def kfold_split(samples, folds: int = 5, seed: int = 42):
+    """kfold_splitter_t::split (src/splitter/kfold.cpp:11-45): shuffle, cut into `folds` validation chunks (the last
+    one takes the remainder), sort both parts. The shuffle is numpy's, not libstdc++'s std::shuffle(mt19937_64)."""
+    samples = np.array(samples, dtype=np.int64)
+    critical(folds >= 2 and samples.size >= folds, "splitter: at least two folds and one sample per fold are needed")
+    shuffled = np.random.default_rng(seed).permutation(samples)
+    chunk = samples.size // folds
+    splits = []
+    for fold in range(folds):
+        begin = fold * chunk
+        end = begin + chunk if fold + 1 < folds else samples.size
+        valid = np.sort(shuffled[begin:end])
+        train = np.sort(np.concatenate([shuffled[:begin], shuffled[end:]]))
+        splits.append((train, valid))
+    return splits
+
+
+def local_search(min_igrid, max_igrid, src_igrid, radius: int):
+    """src/tuner/util.cpp:60-83: the 3^n neighbours at +-radius around src (itself included), inside the grid."""
+    igrids = []
+    for offsets in itertools.product((-1, 0, 1), repeat=len(src_igrid)):
+        igrid = tuple(s + o * radius for s, o in zip(src_igrid, offsets))
+        if all(lo <= i <= hi for lo, i, hi in zip(min_igrid, igrid, max_igrid)):
+            igrids.append(igrid)
+    return igrids
+
+
+def tune(spaces, callback, max_evals: int = 100):
+    """tuner_t::optimize with the local-search tuner (src/tuner.cpp:17-42, src/tuner/local.cpp:16-31):
+    `callback(params[trials, n_params]) -> values[trials]`; returns the steps [(igrid, params, value)] sorted by value."""
+    critical(len(spaces) > 0, "tuner: at least one parameter space is needed!")
+    min_igrid = tuple(0 for _ in spaces)
+    max_igrid = tuple(len(space) - 1 for space in spaces)
+    avg_igrid = tuple(len(space) // 2 for space in spaces)
+    steps = []
+
+    def evaluate(igrids):                                      # src/tuner/util.cpp:85-118
+        known = {step[0] for step in steps}
+        igrids = [igrid for igrid in igrids if igrid not in known]
+        if not igrids:
+            return False
+        params = np.array([[spaces[p][i] for p, i in enumerate(igrid)] for igrid in igrids], dtype=np.float64)
+        values = np.asarray(callback(params), dtype=np.float64)
+        for igrid, param, value in zip(igrids, params, values):
+            critical(np.isfinite(value), "tuner: invalid value (", value, ") detected for parameters (", param, ")!")
+            steps.append((igrid, param, float(value)))
+        steps.sort(key=lambda step: step[2])                   # stable, like std::sort on the value only
+        return True
+
+    evaluate([avg_igrid])
+    radius = 2
+    while steps and len(steps) < max_evals // 2:               # coarse grid around the running optimum
+        if not evaluate(local_search(min_igrid, max_igrid, steps[0][0], radius)):
+            break
+        radius *= 2
+    while steps and len(steps) < max_evals:                    # local search, radius 1
+        if not evaluate(local_search(min_igrid, max_igrid, steps[0][0], 1)):
+            break
+    return steps
+
+
+class _DeviceBackend:
+    """The product path: datasets pinned and scaled in HBM, the CUDA objective, device-side evaluation."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def pin(self, X, Y):
+        return Dataset.pin(self.ctx, X, Y)
+
+    @staticmethod
+    def function(data, loss, l1reg, l2reg):
+        return LinearFunction(data, loss, l1reg, l2reg)
+
+
+def default_solver(function, x0):
+    """The reference's tests fit smooth objectives with lbfgs and non-smooth ones with rqb
+    (test/test_linear_ridge.cpp:24): device-resident L-BFGS, host-driven RQB."""
+    from . import solver
+
+    if function.smooth():
+        return solver.lbfgs(function, x0, epsilon=1e-8, max_evals=1000)
+    return solver.rqb(function, x0, epsilon=1e-8, max_evals=2000)
+
+
+class FitResult:
+    """ml::result_t in small: per trial the parameters, the per-fold mean (error, loss) on both splits, the optimum
+    and the statistics of the final refit."""
+
+    def __init__(self, param_names, folds):
+        self.param_names = tuple(param_names)
+        self.folds = folds
+        self.params = np.zeros((0, len(self.param_names)))
+        self.train = np.zeros((0, folds, 2))                   # [trial, fold, (error, loss)] means
+        self.valid = np.zeros((0, folds, 2))
+        self.extras = []                                       # [trial][fold] -> solver solution (warm starts)
+        self.refit = None
+
+    def trials(self) -> int:
+        return self.params.shape[0]
+
+    def add(self, params):
+        params = np.asarray(params, dtype=np.float64).reshape(-1, len(self.param_names))
+        count = params.shape[0]
+        self.params = np.concatenate([self.params, params])
+        self.train = np.concatenate([self.train, np.full((count, self.folds, 2), np.nan)])
+        self.valid = np.concatenate([self.valid, np.full((count, self.folds, 2), np.nan)])
+        self.extras.extend([[None] * self.folds for _ in range(count)])
+
+    def closest_trial(self, params, max_trials: int) -> int:  # src/machine/result.cpp:82-100
+        best, best_distance = 0, np.finfo(float).max
+        for trial in range(max_trials):
+            distance = float(np.linalg.norm(self.params[trial] - params))
+            if distance < best_distance:
+                best, best_distance = trial, distance
+        return best
+
+    def value(self, trial: int) -> float:                      # mean over folds of the mean validation error
+        return float(np.mean(self.valid[trial, :, 0]))
+
+    def optimum_trial(self) -> int:                            # src/machine/result.cpp:64-80
+        return int(np.argmin([self.value(trial) for trial in range(self.trials())]))
+
+    def optimum_params(self) -> dict:
+        if not self.param_names:
+            return {}
+        return dict(zip(self.param_names, self.params[self.optimum_trial()]))
+
+
+class LinearModel:
+    """nano::linear_t: `fit` tunes the model's regularisation parameters by cross-validation and refits on all the
+    samples; `predict` and `evaluate` run on the device as well. `kind`: ordinary | lasso | ridge | elastic_net."""
+
+    def __init__(self, kind: str = "ordinary", scaling: str = "standard"):
+        critical(kind in MODELS, "linear: unknown model id <", kind, ">")
+        critical(scaling in Dataset.SCALINGS, "linear: unhandled scaling type")
+        self.kind, self.scaling = kind, scaling
+        self._weights = self._bias = None
+
+    def weights(self):
+        return self._weights
+
+    def bias(self):
+        return self._bias
+
+    def make_param_spaces(self):
+        return [PARAM_GRID for _ in MODELS[self.kind]]
+
+    def _regularisers(self, params):
+        values = dict(zip(MODELS[self.kind], params))
+        return float(values.get("l1reg", 0.0)), float(values.get("l2reg", 0.0))
+
+    def _prepare(self, backend, loss, X, Y):
+        """The scaled copy of the samples the objective reads (flatten_iterator_t::scaling + cache_flatten): pinned
+        and scaled in HBM once, shared by every trial on these samples."""
+        data = backend.pin(X, Y)
+        # class targets are never scaled (their statistics are disabled); regression targets follow the inputs
+        return data.scale(self.scaling, self.scaling if loss.error_kind == ERROR_ABSDIFF else "none")
+
+    def _fit_once(self, backend, loss, solver, data, params, x0=None):
+        """::fit (src/linear.cpp:30-48) on a prepared dataset -> (W, b in original units, the solver's result)."""
+        l1reg, l2reg = self._regularisers(params)
+        function = backend.function(data, loss, l1reg, l2reg)
+        start = np.zeros(function.size()) if x0 is None else np.asarray(x0, dtype=np.float64)
+        state = solver(function, start)
+        W, b = data.upscale(function.weights(state["x"]), function.bias(state["x"]))
+        return W, b, state
+
+    def fit(self, ctx, X, Y, loss, samples=None, solver=None, folds: int = 5, seed: int = 42,
+            tuner_max_evals: int = 100, _backend=None) -> FitResult:
+        """linear_t::fit (src/linear.cpp:79-116). X[N, D], Y[N, T] host arrays; `loss`: Loss or its id; `solver`:
+        callable (function, x0) -> dict with "x" (default_solver); returns the FitResult, keeps (weights, bias)."""
+        backend = _backend or _DeviceBackend(ctx)
+        loss = Loss(loss) if isinstance(loss, str) else loss
+        solver = solver or default_solver
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
+        samples = np.arange(X.shape[0]) if samples is None else np.asarray(samples, dtype=np.int64)
+        spaces = self.make_param_spaces()
+        result = FitResult(MODELS[self.kind], folds if spaces else 0)
+
+        if spaces:
+            splits = kfold_split(samples, folds, seed)
+            # per fold, pinned once for all the trials: the scaled training samples (what the objective reads) and
+            # both splits unscaled (the upscaled model is evaluated on them)
+            scaled_sets = [self._prepare(backend, loss, X[train], Y[train]) for train, _ in splits]
+            train_sets = [backend.pin(X[train], Y[train]) for train, _ in splits]
+            valid_sets = [backend.pin(X[valid], Y[valid]) for _, valid in splits]
+
+            def callback(new_params):                          # ml::tune's tuner_callback (tune.cpp:19-46)
+                old_trials = result.trials()
+                result.add(new_params)
+                for trial, params in enumerate(new_params):
+                    closest = result.closest_trial(params, old_trials) if old_trials > 0 else None
+                    for fold in range(len(splits)):
+                        # warm start from the closest earlier trial of this fold (tune.cpp:31-37; its solution in the
+                        # scaled space, where the reference passes the upscaled weights, src/linear.cpp:16-28)
+                        x0 = result.extras[closest][fold] if closest is not None else None
+                        W, b, state = self._fit_once(backend, loss, solver, scaled_sets[fold], params, x0)
+                        result.extras[old_trials + trial][fold] = state["x"]
+                        result.train[old_trials + trial, fold] = train_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                        result.valid[old_trials + trial, fold] = valid_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                return [result.value(trial) for trial in range(old_trials, result.trials())]
+
+            tune(spaces, callback, tuner_max_evals)
+            params = result.params[result.optimum_trial()]
+        else:
+            params = np.zeros(0)
+
+        # refit with the optimum hyper-parameters on all the given samples (linear.cpp:99-112)
+        W, b, state = self._fit_once(backend, loss, solver, self._prepare(backend, loss, X[samples], Y[samples]), params)
+        values = backend.pin(X[samples], Y[samples]).evaluate(loss, W, b)
+        self._weights, self._bias = W, b
+        result.refit = {"state": state, "errors": values[0], "values": values[1], "params": params}
+        return result
+
+    def predict(self, ctx, X, _backend=None):
+        """linear_t::do_predict (src/linear.cpp:118-128): outputs[N, T] = X W^T + b on the device."""
+        critical(self._weights is not None, "linear: the model is not fitted")
+        backend = _backend or _DeviceBackend(ctx)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        return backend.pin(X, np.zeros((X.shape[0], self._bias.size))).predict(self._weights, self._bias)

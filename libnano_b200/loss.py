@@ -13,6 +13,9 @@ KIND_MSE, KIND_MAE, KIND_CAUCHY, KIND_HINGE, KIND_SQUARED_HINGE, KIND_CLASSNLL =
 KIND_SAVAGE, KIND_TANGENT, KIND_LOGISTIC, KIND_EXPONENTIAL, KIND_PINBALL = 6, 7, 8, 9, 10
 KIND_SYNTH_CAUCHY, KIND_SYNTH_LOGISTIC = 11, 12
 
+# error measures (include/nb200.h: nb200_error; include/nano/loss/error.h)
+ERROR_ABSDIFF, ERROR_SCLASS, ERROR_MCLASS = 0, 1, 2
+
 # base name -> (kind, convex, smooth): the `static constexpr` flags of include/nano/loss/*.h
 _BASE = {
     "mse": (KIND_MSE, True, True),
@@ -46,6 +49,8 @@ class Loss:
         base = loss_id[2:] if loss_id[:2] in ("s-", "m-") else loss_id
         self._id = loss_id
         self.kind, self._convex, self._smooth = _BASE[base]
+        # the terror policy of flatten_loss_t (include/nano/loss/flatten.h:103-122): s- / m- prefix, else regression
+        self.error_kind = {"s-": ERROR_SCLASS, "m-": ERROR_MCLASS}.get(loss_id[:2], ERROR_ABSDIFF)
         self._params = {"loss::pinball::alpha": 0.5} if base == "pinball" else {}
 
     @staticmethod
@@ -97,6 +102,17 @@ class Loss:
         _lib.check(_lib.lib().nb200_loss_value(ctx.handle, self.kind, self.param, _ptr(targets), _ptr(outputs), N, T,
                                                _ptr(values)))
         return values
+
+    def error(self, ctx, targets, outputs):
+        """loss_t::error (src/loss.cpp:50-55): L1 distance (regression), 0-1 error of the arg-max label (s-),
+        number of mis-predicted labels (m-); pinball reports its value (src/loss/pinball.cpp:20-23)."""
+        if self.kind == KIND_PINBALL:
+            return self.value(ctx, targets, outputs)
+        targets, outputs, N, T = self._check(targets, outputs)
+        errors = np.empty(N, dtype=np.float64)
+        _lib.check(_lib.lib().nb200_loss_error(ctx.handle, self.error_kind, _ptr(targets), _ptr(outputs), N, T,
+                                               _ptr(errors)))
+        return errors
 
     def vgrad(self, ctx, targets, outputs):
         targets, outputs, N, T = self._check(targets, outputs)

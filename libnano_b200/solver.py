@@ -220,10 +220,14 @@ def _simplex_qp(K, h, max_iters: int = 200):
             if np.all(np.isfinite(Hinv)):
                 break
             Hinv = None
-        critical(Hinv is not None, "solver: the bundle's quadratic program is singular (degenerate metric)")
-        z2 = Hinv @ ones
+        z2 = Hinv @ ones if Hinv is not None else ones
         z2_sum = float(z2.sum())
-        critical(z2_sum > 0.0, "solver: the bundle's quadratic program is not convex (indefinite metric)")
+        if Hinv is None or not z2_sum > 0.0:
+            # K + S/A is positive definite in exact arithmetic; close to the solution its condition number exceeds
+            # what fp64 inverts. Near-complementary iterates are accepted as they are, anything else is a metric
+            # that is not positive definite
+            critical(mu <= 1e-10, "solver: the bundle's quadratic program is not convex (indefinite metric)")
+            break
 
         def solve(rc):
             # (K + S/A) da + 1 dnu = -rd - rc / a,  1.da = -rp   with rc = the complementarity residual a o s - target
@@ -374,9 +378,10 @@ def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: in
         rank-one formula (W += e e' / e.v) instead of being factorised per solve;
       * inactive planes are dropped only when the bundle is full, and the aggregate plane is the true aggregate
         (_Bundle._append);
-      * the metric starts at I / tau0 (reference_init=True restores quasi.cpp:33's tau0 I), the scaled-identity
-        update keeps positive candidates only and moves at most a decade per step (quasi_update);
-      * the convexity tests of the curve search get the parity bar's 1e-12 relative slack (csearch.cpp:99)."""
+      * the metric starts at I / tau0 (reference_init=True restores quasi.cpp:33's tau0 I); the SR1 update also
+        requires positive curvature e.v, the scaled-identity update keeps positive candidates only and moves at most
+        a decade per step (quasi_update);
+      * the convexity tests of the curve search get a rounding-level slack (csearch.cpp:99)."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     n = function.size()
     critical(x0.ndim == 1 and x0.size == n, "solver: incompatible initial point (", x0.size, " dimensions), expecting ",
@@ -445,13 +450,19 @@ def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: in
         v = gn1 - gn
         Me = M @ e
         denom = float(e @ (Me + v))
-        if abs(denom) >= 1e-8 * float(np.linalg.norm(e)) * float(np.linalg.norm(Me + v)):
+        ev = float(e @ v)
+        # quasi.cpp:100-107 applies the update when |e.(Me + v)| is not tiny; M stays positive definite only if the
+        # curvature e.v is positive as well (it is >= 0 for a convex f, up to rounding), so that is required too -
+        # the safeguard the reference leaves as a TODO (quasi.cpp:97-98)
+        # ... and, f being piecewise linear for the losses this solver is for (hinge, mae), e.v is often ~0 inside
+        # one linear piece: the update would flatten M along e and blow up its inverse, so the curvature left along e
+        # must stay above 1e-6 of the initial one
+        eMe = float(e @ Me)
+        curvature_left = eMe * ev / ((eMe + ev) * float(e @ e)) if ev > 0.0 and eMe > 0.0 else 0.0
+        if (abs(denom) >= 1e-8 * float(np.linalg.norm(e)) * float(np.linalg.norm(Me + v))
+                and curvature_left >= 1e-6 * miu):
             M -= np.outer(Me, Me) / denom
-            ev = float(e @ v)                                 # Sherman-Morrison: (M - Me Me'/c)^-1 = W + e e' / (c - e.Me)
-            if abs(ev) > 1e-300 * max(1.0, abs(denom)):
-                W += np.outer(e, e) / ev
-            else:
-                W[...] = np.linalg.pinv(M)
+            W += np.outer(e, e) / ev                          # Sherman-Morrison: (M - Me Me'/c)^-1 = W + e e' / (c - e.Me)
 
     bundle = _Bundle(x, gx, fx, max_size)
     y, gy = x.copy(), np.empty(n)
@@ -481,8 +492,9 @@ def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: in
                 status = "converged"
                 break
             # delta and error are non-negative for a convex f in exact arithmetic; f itself is only pinned to 1e-12
-            # relative (the parity bar), so the reference's `< 0` tests (csearch.cpp:99) get that much slack
-            slack = 1e-12 * (1.0 + abs(cfx))
+            # relative (the parity bar) and the proximal point to the accuracy of the quadratic program, so the
+            # reference's `< 0` tests (csearch.cpp:99) get that much slack (a tenth of the stopping tolerance at most)
+            slack = max(1e-12 * (1.0 + abs(cfx)), 0.1 * tol)
             if not np.isfinite(fy) or delta < -slack or error < -slack:
                 status = "failed"
                 break

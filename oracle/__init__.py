@@ -77,6 +77,7 @@ def lib():
         L = ctypes.CDLL(_LIB_PATH)
         L.oracle_loss_value.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp, _i64, _i64, _dp]
         L.oracle_loss_vgrad.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp, _i64, _i64, _dp]
+        L.oracle_loss_error.argtypes = [ctypes.c_int, _dp, _dp, _i64, _i64, _dp]
         L.oracle_predict.argtypes = [_dp, _dp, _dp, _i64, _i64, _i64, _dp]
         L.oracle_sum_reduce.argtypes = [_dp, _i64, _i64, _i64]
         for name in ("oracle_linear_vgrad", "oracle_linear_vgrad_fast"):
@@ -141,6 +142,36 @@ def loss_vgrad(loss_id: str, targets, outputs, param: float = 0.5):
     vgrads = np.empty_like(targets)
     lib().oracle_loss_vgrad(loss_kind(loss_id), param, _ptr(targets), _ptr(outputs), N, T, _ptr(vgrads))
     return vgrads
+
+
+ERROR_ABSDIFF, ERROR_SCLASS, ERROR_MCLASS = 0, 1, 2
+
+
+def error_kind(loss_id: str) -> int:
+    """The terror policy behind a loss id (include/nano/loss/flatten.h:103-122): s- / m- prefix, else regression."""
+    return ERROR_SCLASS if loss_id.startswith("s-") else ERROR_MCLASS if loss_id.startswith("m-") else ERROR_ABSDIFF
+
+
+def loss_error(loss_id: str, targets, outputs, param: float = 0.5):
+    """loss_t::error (src/loss.cpp:50-55): per-sample error; pinball's is its value (src/loss/pinball.cpp:20-23)."""
+    if loss_id == "pinball":
+        return loss_value(loss_id, targets, outputs, param)
+    targets = _f64(targets)
+    outputs = _f64(outputs)
+    if targets.shape != outputs.shape:
+        raise RuntimeError("critical check failed: loss: incompatible dimension-wise outputs and targets")
+    N = targets.shape[0]
+    T = int(np.prod(targets.shape[1:])) if targets.ndim > 1 else 1
+    errors = np.empty(N, dtype=np.float64)
+    lib().oracle_loss_error(error_kind(loss_id), _ptr(targets), _ptr(outputs), N, T, _ptr(errors))
+    return errors
+
+
+def evaluate(X, Y, loss_id: str, W, b, param: float = 0.5):
+    """linear::evaluate (src/linear/util.cpp:30-49): [2, N] = per-sample (errors, loss values) of the predictions."""
+    outputs = predict(X, W, b)
+    Y = _f64(Y).reshape(outputs.shape)
+    return np.stack([loss_error(loss_id, Y, outputs, param), loss_value(loss_id, Y, outputs, param)])
 
 
 def predict(X, W, b):

@@ -521,6 +521,45 @@ void oracle_loss_vgrad(const int kind, const double param, const double* targets
     }
 }
 
+void oracle_loss_error(const int error_kind, const double* targets, const double* outputs, const int64_t N,
+                       const int64_t T, double* errors)
+{
+    constexpr double epsilon = std::numeric_limits<double>::epsilon();
+    for (int64_t i = 0; i < N; ++i)
+    {
+        const double* t = targets + i * T;
+        const double* o = outputs + i * T;
+        double        error = 0.0;
+        if (error_kind == 0)
+        {
+            // absdiff_t (error.h:11-22): (target - output).abs().sum()
+            for (int64_t k = 0; k < T; ++k)
+            {
+                error += std::fabs(t[k] - o[k]);
+            }
+        }
+        else if (error_kind == 1 && T > 1)
+        {
+            // sclass_t, multi-class (error.h:55-61): the first maximum of the outputs must be a positive target
+            int64_t idx = 0;
+            for (int64_t k = 1; k < T; ++k)
+            {
+                idx = (o[k] > o[idx]) ? k : idx;
+            }
+            error = (t[idx] > 0.0) ? 0.0 : 1.0;
+        }
+        else
+        {
+            // mclass_t (error.h:28-40) and binary sclass_t (error.h:63-67): count of target * output < epsilon
+            for (int64_t k = 0; k < T; ++k)
+            {
+                error += (t[k] * o[k] < epsilon) ? 1.0 : 0.0;
+            }
+        }
+        errors[i] = error;
+    }
+}
+
 void oracle_predict(const double* X, const double* W, const double* b, const int64_t N, const int64_t D,
                     const int64_t T, double* outputs)
 {

@@ -58,6 +58,13 @@ void oracle_loss_value(int kind, double param, const double* targets, const doub
 void oracle_loss_vgrad(int kind, double param, const double* targets, const double* outputs, int64_t N, int64_t T,
                        double* vgrads);
 
+/* loss_t::error over (N, T) (include/nano/loss/flatten.h:62-67 -> include/nano/loss/error.h:11-70).
+ * error_kind: 0 absdiff (regression ids: L1 distance), 1 sclass (s- ids: 0-1 error of the arg-max label, or of the sign
+ * when T == 1), 2 mclass (m- ids: number of labels with target * output < epsilon). pinball's error is its value
+ * (src/loss/pinball.cpp:20-23). */
+void oracle_loss_error(int error_kind, const double* targets, const double* outputs, int64_t N, int64_t T,
+                       double* errors);
+
 /* linear::predict (src/linear/util.cpp:6-21): outputs[N,T] = X[N,D] * W[T,D]^T + b[T] */
 void oracle_predict(const double* X, const double* W, const double* b, int64_t N, int64_t D, int64_t T,
                     double* outputs);

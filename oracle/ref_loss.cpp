@@ -3,6 +3,8 @@
 // kind follows oracle/__init__.py LOSS_KINDS: 0 mse 1 mae 2 cauchy 3 hinge 4 squared-hinge 5 classnll 6 savage 7 tangent
 // 8 logistic 9 exponential (pinball lives in src/loss/pinball.cpp behind tensor maps: its golden vectors are the
 // reference's test/test_loss.cpp:271-307).
+#include <nano/loss/error.h> // over ref_shim/nano/tensor.h
+
 #include <nano/loss/cauchy.h>
 #include <nano/loss/classnll.h>
 #include <nano/loss/exponential.h>
@@ -105,6 +107,26 @@ int ref_loss_vgrad(const int kind, const double* targets, const double* outputs,
     }
     return 0;
 }
+}
+
+// loss_t::error per sample through the reference's own error functors (include/nano/loss/error.h:11-70);
+// error_kind: 0 absdiff (regression), 1 sclass (s- ids), 2 mclass (m- ids)
+extern "C" int ref_loss_error(const int error_kind, const double* targets, const double* outputs, const int64_t N,
+                              const int64_t T, double* errors)
+{
+    using namespace nano::loss::detail;
+    for (int64_t i = 0; i < N; ++i)
+    {
+        const array_t t(targets + i * T, T), o(outputs + i * T, T);
+        switch (error_kind)
+        {
+        case 0: errors[i] = absdiff_t::error(t, o); break;
+        case 1: errors[i] = sclass_t::error(t, o); break;
+        case 2: errors[i] = mclass_t::error(t, o); break;
+        default: return 1;
+        }
+    }
+    return 0;
 }
 
 // objective (B) losses, kind: 0 mse 1 mae 2 cauchy 3 hinge 4 logistic (oracle/__init__.py SYNTH_LOSSES).

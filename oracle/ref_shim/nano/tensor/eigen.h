@@ -99,6 +99,23 @@ public:
         return (*this)(best);
     }
 
+    // the slice include/nano/loss/error.h uses: `.array()` of an array, `(a < scalar).count()`
+    const array_t& array() const { return *this; }
+    struct mask_t
+    {
+        tensor_size_t m_count{0};
+        tensor_size_t count() const { return m_count; }
+    };
+    mask_t operator<(const scalar_t other) const
+    {
+        mask_t mask;
+        for (const auto v : m_data)
+        {
+            mask.m_count += (v < other) ? 1 : 0;
+        }
+        return mask;
+    }
+
     // (Eigen: array -> vector -> diagonal matrix; only named by Hessian members that are never called)
     const array_t& matrix() const { return *this; }
     const array_t& asDiagonal() const { return *this; }

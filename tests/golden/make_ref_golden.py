@@ -86,6 +86,38 @@ def main():
                       "targets": [float(v).hex() for v in targets.ravel()], "fx": float(fx.value).hex(),
                       "gx": [float(v).hex() for v in gx.ravel()]})
 
+    # loss_t::error through the reference's error functors (include/nano/loss/error.h); its own stream, so the cases
+    # above do not depend on this section
+    lib.ref_loss_error.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int64, ctypes.c_int64, dp]
+    erng = np.random.default_rng(20261021)
+    errors = []
+    for name, kind in (("absdiff", 0), ("sclass", 1), ("mclass", 2)):
+        for T in (1, 3, 13):
+            N = 32
+            outputs = erng.normal(0.0, 1.0, (N, T))
+            if name == "absdiff":
+                targets = erng.normal(0.0, 1.0, (N, T))
+                outputs[0] = targets[0]
+            else:
+                targets = np.where(erng.uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+                if name == "sclass" and T > 1:
+                    targets = -np.ones((N, T))
+                    targets[np.arange(N), erng.integers(0, T, N)] = 1.0
+                outputs[0] = 0.0                                  # edges == 0 < epsilon; arg-max tie -> first label
+                outputs[1] = targets[1] * 2.0 ** -52              # edges == epsilon exactly: not an error
+                outputs[2] = targets[2] * 2.0 ** -53              # just below
+                outputs[3] = outputs[3, 0]                        # all outputs equal (tie)
+                outputs[4] = targets[4]
+                outputs[5] = -targets[5]
+            targets = np.ascontiguousarray(targets)
+            outputs = np.ascontiguousarray(outputs)
+            values = np.empty(N)
+            assert lib.ref_loss_error(kind, targets.ctypes.data_as(dp), outputs.ctypes.data_as(dp), N, T,
+                                      values.ctypes.data_as(dp)) == 0
+            errors.append({"error": name, "T": T, "N": N, "targets": [float(v).hex() for v in targets.ravel()],
+                           "outputs": [float(v).hex() for v in outputs.ravel()],
+                           "errors": [float(v).hex() for v in values]})
+
     # the random stream of linear_model_t (seed 42 as in BASELINE config 1, and another seed)
     lib.ref_rng_draws.argtypes = [ctypes.c_uint64, ctypes.c_int64, dp]
     draws = {}
@@ -94,14 +126,14 @@ def main():
         assert lib.ref_rng_draws(seed, out.size, out.ctypes.data_as(dp)) == 0
         draws[str(seed)] = [float(v).hex() for v in out]
 
-    payload = {"rng_draws": draws, "synth": synth, "source": "reference loss code compiled in place: include/nano/loss/*.h (cases) and "
+    payload = {"rng_draws": draws, "synth": synth, "errors": errors, "source": "reference loss code compiled in place: include/nano/loss/*.h (cases) and "
                          "src/function/mlearn/loss.cpp (synth); oracle/ref_loss.cpp over oracle/ref_shim/ (stand-in for "
                          "the Eigen array / matrix vocabulary, sequential sums)",
                "generator": "tests/golden/make_ref_golden.py", "cases": cases}
     path = os.path.join(HERE, "ref_loss_golden.json")
     with open(path, "w") as handle:
         json.dump(payload, handle)
-    print(path, len(cases), "cases +", len(synth), "synth cases", os.path.getsize(path), "bytes")
+    print(path, len(cases), "cases +", len(synth), "synth cases +", len(errors), "error cases", os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,247 @@
+"""linear_t::fit mirrored over the GPU objective (libnano_b200/linear.py). Mirrors the reference's model
+tests (test/test_linear_ordinary.cpp, test_linear_ridge.cpp, test_linear_lasso.cpp: fit on a synthetic linear
+datasource with some irrelevant features, then the weights and bias are recovered and the predictions match the
+targets). CPU tests run the same orchestration over an oracle-backed backend (test infrastructure) and the host-only
+pieces (splitter, tuner); GPU tests run the product path."""
+import numpy as np
+import pytest
+
+from libnano_b200 import linear as nb_linear
+from libnano_b200 import solver as nb_solver
+from test_host_solvers import OracleFunction
+
+
+def linear_datasource(seed, N, D, T=1, relevant_modulo=2, noise=0.0, classification=False):
+    """test/fixture/datasource/linear.h in small: targets = W x + b with only every `relevant_modulo`-th feature used"""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, (N, D)) * rng.uniform(0.5, 20.0, D) + rng.uniform(-3, 3, D)    # badly scaled on purpose
+    W = rng.uniform(-1, 1, (T, D))
+    W[:, np.arange(D) % relevant_modulo != 0] = 0.0
+    b = rng.uniform(-1, 1, T)
+    Y = X @ W.T + b + noise * rng.normal(size=(N, T))
+    if classification:
+        Y = np.where(Y - np.median(Y, axis=0) < 0, -1.0, 1.0)
+    return X, Y, W, b
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# an oracle-backed backend with the interface of linear._DeviceBackend
+# ----------------------------------------------------------------------------------------------------------------
+class OracleDataset:
+    def __init__(self, oracle, X, Y):
+        self.oracle, self.X, self.Y = oracle, np.array(X, dtype=np.float64), np.array(Y, dtype=np.float64)
+        self.istats = self.tstats = None
+        self.iscaling = self.tscaling = "none"
+
+    def scale(self, inputs="standard", targets="none"):
+        self.istats, self.tstats = self.oracle.scalar_stats(self.X), self.oracle.scalar_stats(self.Y)
+        self.iscaling, self.tscaling = inputs, targets
+        self.X = self.oracle.scale(self.X, self.istats, inputs)
+        self.Y = self.oracle.scale(self.Y, self.tstats, targets)
+        return self
+
+    def upscale(self, W, b):
+        if self.istats is None:
+            return np.array(W), np.array(b)
+        return self.oracle.upscale(self.istats, self.iscaling, self.tstats, self.tscaling, W, b)
+
+    def evaluate(self, loss, W, b):
+        return self.oracle.evaluate(self.X, self.Y, loss.type_id(), W, b)
+
+    def predict(self, W, b):
+        return self.oracle.predict(self.X, W, b)
+
+
+class OracleLinearFunction(OracleFunction):
+    def weights(self, x):
+        D, T = self._X.shape[1], self._Y.shape[1]
+        return np.asarray(x)[: D * T].reshape(T, D)
+
+    def bias(self, x):
+        D, T = self._X.shape[1], self._Y.shape[1]
+        return np.asarray(x)[D * T:]
+
+
+class OracleBackend:
+    def __init__(self, oracle):
+        self.oracle = oracle
+
+    def pin(self, X, Y):
+        return OracleDataset(self.oracle, X, Y)
+
+    def function(self, data, loss, l1reg, l2reg):
+        return OracleLinearFunction(self.oracle, data.X, data.Y, loss.type_id(), l1=l1reg, l2=l2reg,
+                                    smooth=loss.smooth() and l1reg <= 0.0)
+
+
+def cpu_solver(oracle):
+    def solve(function, x0):
+        if function.smooth():
+            result = oracle.lbfgs(lambda x, gx=None: function.do_eval(np.asarray(x), gx), x0, epsilon=1e-10,
+                                  max_evals=5000)
+            assert result["status"] == "gradient_test"
+            return result
+        return nb_solver.rqb(function, x0, epsilon=1e-9, max_evals=4000)
+
+    return solve
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host-only pieces
+# ----------------------------------------------------------------------------------------------------------------
+def test_param_space_is_the_reference_grid():
+    grid = nb_linear.PARAM_GRID       # src/linear/util.cpp:75-86
+    assert len(grid) == 31 and grid[0] == 1e-8 and grid[1] == 3e-8 and grid[15] == 3e-1 and grid[-1] == 1e7
+    assert all(a < b for a, b in zip(grid, grid[1:]))
+
+
+@pytest.mark.parametrize("count,folds", [(10, 2), (11, 3), (100, 5), (5, 5)])
+def test_kfold_split_partitions_the_samples(count, folds):
+    samples = np.arange(100, 100 + count)
+    splits = nb_linear.kfold_split(samples, folds, seed=7)
+    assert len(splits) == folds
+    seen = []
+    for fold, (train, valid) in enumerate(splits):
+        assert np.array_equal(np.sort(np.concatenate([train, valid])), samples)      # a partition, both parts sorted
+        assert np.all(np.diff(train) > 0) and np.all(np.diff(valid) > 0)
+        assert valid.size == (count // folds if fold + 1 < folds else count - (folds - 1) * (count // folds))
+        seen.append(valid)
+    assert np.array_equal(np.sort(np.concatenate(seen)), samples)                    # every sample validates once
+    again = nb_linear.kfold_split(samples, folds, seed=7)
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(splits, again))
+    with pytest.raises(RuntimeError):
+        nb_linear.kfold_split(samples, count + 1)
+
+
+def test_local_search_neighbourhood():
+    # src/tuner/util.cpp:60-83
+    assert nb_linear.local_search((0,), (30,), (15,), 2) == [(13,), (15,), (17,)]
+    assert nb_linear.local_search((0,), (30,), (0,), 1) == [(0,), (1,)]
+    assert len(nb_linear.local_search((0, 0), (30, 30), (15, 15), 4)) == 9
+    assert len(nb_linear.local_search((0, 0), (30, 30), (30, 0), 1)) == 4
+
+
+@pytest.mark.parametrize("optimum", [(0,), (30,), (11,), (22,)])
+def test_tuner_finds_the_grid_optimum_of_a_convex_response(optimum):
+    grid = nb_linear.PARAM_GRID
+    calls = []
+
+    def callback(params):
+        calls.extend(tuple(p) for p in params)
+        return [abs(np.log10(p[0]) - np.log10(grid[optimum[0]])) for p in params]
+
+    steps = nb_linear.tune([grid], callback)
+    assert steps[0][0] == optimum and steps[0][2] == 0.0
+    assert len(calls) == len(set(calls)) == len(steps) <= 31                 # no grid point is evaluated twice
+    assert calls[0] == (grid[15],)                                           # starts from the middle of the grid
+    assert [s[2] for s in steps] == sorted(s[2] for s in steps)
+
+
+def test_tuner_two_parameters_and_budget():
+    grid = nb_linear.PARAM_GRID
+    target = (grid[9], grid[20])
+    steps = nb_linear.tune([grid, grid], lambda params: [abs(np.log10(p[0] / target[0])) + abs(np.log10(p[1] / target[1]))
+                                                         for p in params])
+    assert steps[0][0] == (9, 20)
+    capped = nb_linear.tune([grid, grid], lambda params: [float(p[0] + p[1]) for p in params], max_evals=12)
+    assert len(capped) <= 12 + 9
+    with pytest.raises(RuntimeError, match="invalid value"):
+        nb_linear.tune([grid], lambda params: [np.nan for _ in params])
+    with pytest.raises(RuntimeError, match="at least one parameter space"):
+        nb_linear.tune([], lambda params: [])
+
+
+def test_fit_result_bookkeeping():
+    result = nb_linear.FitResult(("l1reg", "l2reg"), 2)
+    result.add([[1.0, 1.0], [10.0, 1.0]])
+    result.valid[0, :, 0], result.valid[1, :, 0] = (0.5, 0.3), (0.1, 0.2)
+    result.add([[9.0, 2.0]])
+    result.valid[2, :, 0] = (0.4, 0.4)
+    assert result.trials() == 3 and result.closest_trial(np.array([9.0, 2.0]), 2) == 1    # result.cpp:82-100
+    assert result.optimum_trial() == 1 and result.optimum_params() == {"l1reg": 10.0, "l2reg": 1.0}
+    with pytest.raises(RuntimeError, match="unknown model id"):
+        nb_linear.LinearModel("bayesian")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the orchestration over the oracle backend (CPU)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scaling", ["none", "mean", "minmax", "standard"])
+def test_ordinary_fit_recovers_the_generating_model(oracle, scaling):
+    # test/test_linear_ordinary.cpp: mse + lbfgs, weights and bias to 1e-6 whatever the scaling
+    X, Y, W, b = linear_datasource(1, 120, 6, T=2)
+    model = nb_linear.LinearModel("ordinary", scaling)
+    result = model.fit(None, X, Y, "mse", solver=cpu_solver(oracle), _backend=OracleBackend(oracle))
+    assert result.trials() == 0 and result.optimum_params() == {}
+    assert np.max(np.abs(model.weights() - W)) < 1e-6 and np.max(np.abs(model.bias() - b)) < 1e-6
+    assert np.max(result.refit["errors"]) < 1e-5 and result.refit["state"]["status"] == "gradient_test"
+    outputs = model.predict(None, X, _backend=OracleBackend(oracle))
+    assert np.max(np.abs(outputs - Y)) < 1e-5
+
+
+def test_ridge_fit_tunes_l2reg_and_recovers_the_model(oracle):
+    # test/test_linear_ridge.cpp: the tuner settles on a negligible l2reg for noise-free targets
+    X, Y, W, b = linear_datasource(2, 100, 5)
+    model = nb_linear.LinearModel("ridge", "standard")
+    result = model.fit(None, X, Y, "mse", solver=cpu_solver(oracle), folds=2, _backend=OracleBackend(oracle))
+    assert result.param_names == ("l2reg",) and 3 <= result.trials() <= 31
+    assert result.optimum_params()["l2reg"] <= 1e-4
+    assert np.all(np.isfinite(result.valid)) and np.all(np.isfinite(result.train))
+    assert np.max(np.abs(model.weights() - W)) < 1e-3 and np.max(np.abs(model.bias() - b)) < 1e-2
+    # a heavier regulariser validates worse than the optimum
+    heavy = int(np.argmax(result.params[:, 0]))
+    assert result.value(heavy) > result.value(result.optimum_trial())
+
+
+def test_lasso_fit_with_a_nonsmooth_loss(oracle):
+    # test/test_linear_lasso.cpp with mae: RQB drives the non-smooth objective; irrelevant features stay out
+    X, Y, W, b = linear_datasource(3, 80, 4)
+    model = nb_linear.LinearModel("lasso", "standard")
+    result = model.fit(None, X, Y, "mae", solver=cpu_solver(oracle), folds=2, tuner_max_evals=8,
+                       _backend=OracleBackend(oracle))
+    assert result.param_names == ("l1reg",) and result.trials() >= 3
+    assert np.max(np.abs(model.weights() - W)) < 1e-2 and abs(model.bias()[0] - b[0]) < 5e-2
+    assert np.mean(result.refit["errors"]) < 1e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU: the product path
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("scaling", ["none", "standard"])
+def test_gpu_ordinary_fit_recovers_the_generating_model(ctx, scaling):
+    X, Y, W, b = linear_datasource(1, 2000, 24, T=2)
+    model = nb_linear.LinearModel("ordinary", scaling)
+    result = model.fit(ctx, X, Y, "mse", solver=lambda f, x0: nb_solver.lbfgs(f, x0, epsilon=1e-10, max_evals=5000))
+    assert result.refit["state"]["status"] == "gradient_test"
+    assert np.max(np.abs(model.weights() - W)) < 1e-6 and np.max(np.abs(model.bias() - b)) < 1e-6
+    assert np.max(np.abs(model.predict(ctx, X) - Y)) < 1e-5 and np.max(result.refit["errors"]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_ridge_fit_matches_the_oracle_backed_fit(ctx, oracle):
+    # same orchestration, same splits: the product path and the oracle backend pick the same l2reg and agree on the
+    # validation statistics and the model
+    X, Y, W, b = linear_datasource(2, 400, 8, noise=0.05)
+    gpu, cpu = nb_linear.LinearModel("ridge"), nb_linear.LinearModel("ridge")
+    r_gpu = gpu.fit(ctx, X, Y, "mse", folds=2, solver=lambda f, x0: nb_solver.lbfgs(f, x0, epsilon=1e-10, max_evals=5000))
+    r_cpu = cpu.fit(None, X, Y, "mse", folds=2, solver=cpu_solver(oracle), _backend=OracleBackend(oracle))
+    assert r_gpu.trials() == r_cpu.trials() and np.array_equal(r_gpu.params, r_cpu.params)
+    assert r_gpu.optimum_params() == r_cpu.optimum_params()
+    assert np.max(np.abs(r_gpu.valid - r_cpu.valid) / (1 + np.abs(r_cpu.valid))) < 1e-6
+    assert np.max(np.abs(gpu.weights() - cpu.weights())) < 1e-6 and np.max(np.abs(gpu.bias() - cpu.bias())) < 1e-6
+    assert np.max(np.abs(gpu.weights() - W)) < 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_elastic_net_classification_with_the_default_solvers(ctx):
+    # s-hinge + elastic net is non-smooth: default_solver picks the host-driven RQB over the CUDA vgrad; the tuner
+    # minimises the validation 0-1 error (device-side linear::evaluate)
+    X, Y, W, b = linear_datasource(4, 600, 6, classification=True)
+    model = nb_linear.LinearModel("elastic_net", "standard")
+    result = model.fit(ctx, X, Y, "s-hinge", folds=2, tuner_max_evals=6)
+    assert result.param_names == ("l1reg", "l2reg") and result.trials() >= 1
+    assert np.all((result.valid[:, :, 0] >= 0.0) & (result.valid[:, :, 0] <= 1.0))
+    assert np.mean(result.refit["errors"]) < 0.1                              # 0-1 error of the refit model
+    predictions = np.sign(model.predict(ctx, X))
+    assert np.mean(predictions != Y) == np.mean(result.refit["errors"])
