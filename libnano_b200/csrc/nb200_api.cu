@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <random>
 #include <vector>
@@ -34,6 +35,13 @@ struct nb200_ctx
     int          sm_count{0};
     int          smem_optin{0};
     int          l2_bytes{0};
+    // grow-only scratch of nb200_evaluate (called once per trial and fold by linear_t::fit): a device arena for
+    // (W, b, outputs, errors, values) and a pinned host buffer the two result vectors land in
+    std::mutex   scratch_lock;
+    char*        arena{nullptr};
+    size_t       arena_bytes{0};
+    char*        staging{nullptr};
+    size_t       staging_bytes{0};
 };
 
 struct nb200_data
@@ -1147,6 +1155,8 @@ void nb200_ctx_release(nb200_ctx* ctx)
     {
         cudaSetDevice(ctx->device);
         cudaStreamDestroy(ctx->stream);
+        cudaFree(ctx->arena);
+        cudaFreeHost(ctx->staging);
         delete ctx;
     }
 }
@@ -2258,6 +2268,27 @@ int nb200_loss_error(nb200_ctx* ctx, const int error_kind, const double* targets
     return status;
 }
 
+static int ctx_reserve(nb200_ctx* ctx, const size_t device_bytes, const size_t host_bytes)
+{
+    if (device_bytes > ctx->arena_bytes)
+    {
+        cudaFree(ctx->arena);
+        ctx->arena       = nullptr;
+        ctx->arena_bytes = 0;
+        NB200_CUDA_TRY(cudaMalloc(&ctx->arena, device_bytes));
+        ctx->arena_bytes = device_bytes;
+    }
+    if (host_bytes > ctx->staging_bytes)
+    {
+        cudaFreeHost(ctx->staging);
+        ctx->staging       = nullptr;
+        ctx->staging_bytes = 0;
+        NB200_CUDA_TRY(cudaMallocHost(&ctx->staging, host_bytes));
+        ctx->staging_bytes = host_bytes;
+    }
+    return NB200_OK;
+}
+
 int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, const int loss, const double loss_param,
                    const int error_kind, const double* W, const double* b, double* errors, double* values)
 {
@@ -2266,52 +2297,63 @@ int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, const int loss, const
     NB200_REQUIRE(ctx->device == data->device, "evaluate: context and dataset live on different devices");
     NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "evaluate: unknown loss");
     NB200_REQUIRE(error_kind >= 0 && error_kind < NB200_ERROR_COUNT, "evaluate: unknown error kind");
-    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t N = data->N, D = data->D, T = data->T;
-    const size_t  rows = static_cast<size_t>(N) * sizeof(double);
-    double *      dW = nullptr, *db = nullptr, *dO = nullptr, *dE = nullptr, *dV = nullptr;
-    const auto    run = [&]() -> int
+    if (N == 0)
     {
-        NB200_CUDA_TRY(cudaMalloc(&dW, static_cast<size_t>(T) * D * sizeof(double)));
-        NB200_CUDA_TRY(cudaMalloc(&db, static_cast<size_t>(T) * sizeof(double)));
-        NB200_CUDA_TRY(cudaMalloc(&dO, rows * T));
-        NB200_CUDA_TRY(cudaMalloc(&dE, rows));
-        NB200_CUDA_TRY(cudaMalloc(&dV, rows));
-        NB200_CUDA_TRY(cudaMemcpyAsync(dW, W, static_cast<size_t>(T) * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        NB200_CUDA_TRY(cudaMemcpyAsync(db, b, static_cast<size_t>(T) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        predict_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(data->X, dW, db, N, D, T, dO);
-        NB200_CUDA_TRY(cudaGetLastError());
-        const unsigned blocks = static_cast<unsigned>((N + 255) / 256);
-        // pinball's error is its value (src/loss/pinball.cpp:20-23)
-        const bool error_is_value = loss == NB200_LOSS_PINBALL;
-        if (values != nullptr || error_is_value)
-        {
-            loss_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(loss, loss_param, data->Y, dO, N, T, dV, nullptr);
-            NB200_CUDA_TRY(cudaGetLastError());
-        }
-        if (errors != nullptr && !error_is_value)
-        {
-            loss_error_kernel<<<blocks, 256, 0, ctx->stream>>>(error_kind, data->Y, dO, N, T, dE);
-            NB200_CUDA_TRY(cudaGetLastError());
-        }
-        if (errors != nullptr)
-        {
-            NB200_CUDA_TRY(cudaMemcpyAsync(errors, error_is_value ? dV : dE, rows, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        if (values != nullptr)
-        {
-            NB200_CUDA_TRY(cudaMemcpyAsync(values, dV, rows, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return NB200_OK;
-    };
-    const int status = N > 0 ? run() : NB200_OK;
-    cudaFree(dW);
-    cudaFree(db);
-    cudaFree(dO);
-    cudaFree(dE);
-    cudaFree(dV);
-    return status;
+    }
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    const std::lock_guard<std::mutex> guard(ctx->scratch_lock);
+
+    // arena layout (256-byte aligned slices): W [T, D] | b [T] | outputs [N, T] | errors [N] | values [N]
+    const auto   aligned = [](const size_t bytes) { return (bytes + 255) / 256 * 256; };
+    const size_t rows = static_cast<size_t>(N) * sizeof(double);
+    const size_t w_bytes = aligned(static_cast<size_t>(T) * D * sizeof(double));
+    const size_t b_bytes = aligned(static_cast<size_t>(T) * sizeof(double));
+    const size_t o_bytes = aligned(rows * T);
+    const size_t r_bytes = aligned(rows);
+    const int    status = ctx_reserve(ctx, w_bytes + b_bytes + o_bytes + 2 * r_bytes, 2 * r_bytes);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    auto* dW = reinterpret_cast<double*>(ctx->arena);
+    auto* db = reinterpret_cast<double*>(ctx->arena + w_bytes);
+    auto* dO = reinterpret_cast<double*>(ctx->arena + w_bytes + b_bytes);
+    auto* dE = reinterpret_cast<double*>(ctx->arena + w_bytes + b_bytes + o_bytes);
+    auto* dV = reinterpret_cast<double*>(ctx->arena + w_bytes + b_bytes + o_bytes + r_bytes);
+    auto* hE = reinterpret_cast<double*>(ctx->staging);
+    auto* hV = reinterpret_cast<double*>(ctx->staging + r_bytes);
+
+    NB200_CUDA_TRY(cudaMemcpyAsync(dW, W, static_cast<size_t>(T) * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NB200_CUDA_TRY(cudaMemcpyAsync(db, b, static_cast<size_t>(T) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    predict_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(data->X, dW, db, N, D, T, dO);
+    NB200_CUDA_TRY(cudaGetLastError());
+    const unsigned blocks = static_cast<unsigned>((N + 255) / 256);
+    // pinball's error is its value (src/loss/pinball.cpp:20-23)
+    const bool error_is_value = loss == NB200_LOSS_PINBALL;
+    if (values != nullptr || error_is_value)
+    {
+        loss_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(loss, loss_param, data->Y, dO, N, T, dV, nullptr);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaMemcpyAsync(hV, dV, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (errors != nullptr && !error_is_value)
+    {
+        loss_error_kernel<<<blocks, 256, 0, ctx->stream>>>(error_kind, data->Y, dO, N, T, dE);
+        NB200_CUDA_TRY(cudaGetLastError());
+        NB200_CUDA_TRY(cudaMemcpyAsync(hE, dE, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    NB200_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (errors != nullptr)
+    {
+        std::memcpy(errors, error_is_value ? hV : hE, rows);
+    }
+    if (values != nullptr)
+    {
+        std::memcpy(values, hV, rows);
+    }
+    return NB200_OK;
 }
 
 int nb200_synth_linear_inputs(const int64_t samples, const int64_t inputs, const uint64_t seed, const int64_t modulo,

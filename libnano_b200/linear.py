@@ -23,6 +23,19 @@ PARAM_GRID = tuple(float(f"{m}e{e}") for e in range(-8, 7) for m in (1, 3)) + (1
 MODELS = {"ordinary": (), "lasso": ("l1reg",), "ridge": ("l2reg",), "elastic_net": ("l1reg", "l2reg")}
 
 
+def feature_importance(weights):
+    """linear::feature_importance (src/linear/util.cpp:51-63) for scalar features (one column each): the weight
+    magnitude per input column cumulated over the targets."""
+    return np.abs(np.atleast_2d(np.asarray(weights, dtype=np.float64))).sum(axis=0)
+
+
+def sparsity_ratio(importance, threshold: float = 1e-6) -> float:
+    """linear::sparsity_ratio (src/linear/util.cpp:65-73): the fraction of the features below the threshold."""
+    importance = np.asarray(importance, dtype=np.float64)
+    critical(threshold > 0.0 and importance.size > 0 and importance.min() >= 0.0, "linear: invalid feature importance")
+    return float(np.count_nonzero(importance < threshold)) / float(importance.size)
+
+
 def kfold_split(samples, folds: int = 5, seed: int = 42):
     """kfold_splitter_t::split (src/splitter/kfold.cpp:11-45): shuffle, cut into `folds` validation chunks (the last
     one takes the remainder), sort both parts. The shuffle is numpy's, not libstdc++'s std::shuffle(mt19937_64)."""
@@ -238,6 +251,15 @@ class LinearModel:
         self._weights, self._bias = W, b
         result.refit = {"state": state, "errors": values[0], "values": values[1], "params": params}
         return result
+
+    def evaluate(self, ctx, X, Y, loss, _backend=None):
+        """learner_t::evaluate (src/learner.cpp:79-93): [2, N] = per-sample (errors, loss values) of the fitted model."""
+        critical(self._weights is not None, "linear: the model is not fitted")
+        backend = _backend or _DeviceBackend(ctx)
+        loss = Loss(loss) if isinstance(loss, str) else loss
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
+        return backend.pin(X, Y).evaluate(loss, self._weights, self._bias)
 
     def predict(self, ctx, X, _backend=None):
         """linear_t::do_predict (src/linear.cpp:118-128): outputs[N, T] = X W^T + b on the device."""

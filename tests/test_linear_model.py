@@ -151,6 +151,16 @@ def test_tuner_two_parameters_and_budget():
         nb_linear.tune([], lambda params: [])
 
 
+def test_feature_importance_and_sparsity_ratio():
+    # src/linear/util.cpp:51-73 (test/test_linear_util.cpp)
+    W = np.array([[1.0, -2.0, 0.0, 1e-9], [0.5, 0.0, 0.0, -1e-9]])
+    importance = nb_linear.feature_importance(W)
+    assert np.allclose(importance, [1.5, 2.0, 0.0, 2e-9], rtol=0, atol=1e-18)
+    assert nb_linear.sparsity_ratio(importance) == 0.5 and nb_linear.sparsity_ratio(importance, 1e-12) == 0.25
+    with pytest.raises(RuntimeError):
+        nb_linear.sparsity_ratio(np.array([-1.0]))
+
+
 def test_fit_result_bookkeeping():
     result = nb_linear.FitResult(("l1reg", "l2reg"), 2)
     result.add([[1.0, 1.0], [10.0, 1.0]])
@@ -177,6 +187,10 @@ def test_ordinary_fit_recovers_the_generating_model(oracle, scaling):
     assert np.max(result.refit["errors"]) < 1e-5 and result.refit["state"]["status"] == "gradient_test"
     outputs = model.predict(None, X, _backend=OracleBackend(oracle))
     assert np.max(np.abs(outputs - Y)) < 1e-5
+    values = model.evaluate(None, X, Y, "mse", _backend=OracleBackend(oracle))
+    assert np.array_equal(values, np.stack([result.refit["errors"], result.refit["values"]]))
+    importance = nb_linear.feature_importance(model.weights())
+    assert nb_linear.sparsity_ratio(importance, 1e-5) == 0.5          # every second feature is irrelevant
 
 
 def test_ridge_fit_tunes_l2reg_and_recovers_the_model(oracle):
