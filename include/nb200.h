@@ -298,6 +298,12 @@ NB200_API int nb200_loss_error(nb200_ctx* ctx, int error_kind, const double* tar
 NB200_API int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, int loss, double loss_param, int error_kind,
                              const double* W, const double* b, double* errors, double* values);
 
+/* Host-side algebra of the proximal bundle drivers (no device needed): alpha[m] = argmin a.K.a / 2 - h.a over the unit
+ * simplex, K[m,m] symmetric positive semi-definite. This is the dual of the quadratic program libnano's bundle solvers
+ * build in n + 1 variables (src/solver/bundle/bundle.cpp:109-168): one variable per cutting plane. Inactive planes get
+ * an exact zero. NB200_ERR_INVALID if K is not positive semi-definite (or an argument is null / non-finite). */
+NB200_API int nb200_simplex_qp(const double* K, const double* h, int64_t m, double* alpha);
+
 /* Host-side data of the builtin synthetic test functions: the random part of the linear_model_t constructor
  * (src/function/mlearn/linear.cpp:15-33): rng = std::mt19937_64(seed), u ~ uniform_real_distribution(0, 1);
  * X[samples, inputs] row-major, then wopt[inputs], then bopt = u - 0.5; wopt is divided by its sum and the columns

@@ -77,6 +77,7 @@ SIGNATURES = {
                                         c_double_p]),
     "nb200_evaluate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                       c_double_p, c_double_p, c_double_p, c_double_p]),
+    "nb200_simplex_qp": (ctypes.c_int, [c_double_p, c_double_p, c_i64, c_double_p]),
     "nb200_synth_linear_inputs": (ctypes.c_int, [c_i64, c_i64, ctypes.c_uint64, c_i64, c_double_p, c_double_p,
                                                  c_double_p]),
     "nb200_loss_vgrad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, c_double_p, c_double_p, c_i64,
