@@ -23,10 +23,19 @@ PARAM_GRID = tuple(float(f"{m}e{e}") for e in range(-8, 7) for m in (1, 3)) + (1
 MODELS = {"ordinary": (), "lasso": ("l1reg",), "ridge": ("l2reg",), "elastic_net": ("l1reg", "l2reg")}
 
 
-def feature_importance(weights):
-    """linear::feature_importance (src/linear/util.cpp:51-63) for scalar features (one column each): the weight
-    magnitude per input column cumulated over the targets."""
-    return np.abs(np.atleast_2d(np.asarray(weights, dtype=np.float64))).sum(axis=0)
+def feature_importance(weights, column2feature=None):
+    """linear::feature_importance (src/linear/util.cpp:51-63): the weight magnitude per feature, cumulated over the
+    targets and over the flatten columns of the feature (`column2feature[column]`, dataset_t::column2feature; one
+    column per feature when omitted)."""
+    per_column = np.abs(np.atleast_2d(np.asarray(weights, dtype=np.float64))).sum(axis=0)
+    if column2feature is None:
+        return per_column
+    column2feature = np.asarray(column2feature, dtype=np.int64)
+    critical(column2feature.size == per_column.size and column2feature.min() >= 0,
+             "linear: one feature index per flatten column is needed")
+    importance = np.zeros(int(column2feature.max()) + 1)
+    np.add.at(importance, column2feature, per_column)
+    return importance
 
 
 def sparsity_ratio(importance, threshold: float = 1e-6) -> float:

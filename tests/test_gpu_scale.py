@@ -1,6 +1,5 @@
 """GPU tests at scale and for the sharded path: synthetic HBM-resident datasets, two-phase (partial / finish)
 evaluation, logical shards on one device, and size-independent properties at the BASELINE sizes."""
-import ctypes
 
 import numpy as np
 import pytest

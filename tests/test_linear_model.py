@@ -161,6 +161,41 @@ def test_feature_importance_and_sparsity_ratio():
         nb_linear.sparsity_ratio(np.array([-1.0]))
 
 
+def test_reference_known_answers_of_the_host_pieces():
+    # test/test_linear_util.cpp:82-110 (13 flatten columns of 4 features) and test/test_tuner.cpp:224-272
+    columns = [0, 1, 1, 1, 1, 1, 2, 3, 3, 3, 3, 3, 3]
+    assert np.array_equal(nb_linear.feature_importance([[1, 0, -1, 0, 0, 1, -2, -3, 0, 0, 1, 1, 1]], columns),
+                          [1, 2, 2, 6])
+    assert np.array_equal(nb_linear.feature_importance([[0, 0, 0, 0, 0, 1, -2, -3, 0, 0, 0, 0, 0]], columns),
+                          [0, 1, 2, 3])
+    importance = np.array([0.0, 1e-9, 1e-3, 1e-1, 1e-7, 1e-7, 1e-1, 1e+1])
+    for threshold, expected in ((1e-10, 1 / 8), (1e-8, 2 / 8), (1e-6, 4 / 8), (1e-2, 5 / 8)):
+        assert nb_linear.sparsity_ratio(importance, threshold) == expected
+    low, high, middle = (0, 0), (9, 6), (5, 3)
+    assert nb_linear.local_search(low, high, low, 1) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    assert nb_linear.local_search(low, high, high, 2) == [(7, 4), (7, 6), (9, 4), (9, 6)]
+    assert nb_linear.local_search(low, high, middle, 1) == [(4, 2), (4, 3), (4, 4), (5, 2), (5, 3), (5, 4), (6, 2),
+                                                            (6, 3), (6, 4)]
+
+
+@pytest.mark.parametrize("seed", [42, 11, 122])
+def test_kfold_reference_case(seed):
+    # test/test_splitter.cpp:60-88: 25 samples, 5 folds -> 20 / 5, disjoint validation parts that cover the samples
+    splits = nb_linear.kfold_split(np.arange(25), 5, seed)
+    assert [(train.size, valid.size) for train, valid in splits] == [(20, 5)] * 5
+    assert np.array_equal(np.sort(np.concatenate([valid for _, valid in splits])), np.arange(25))
+    for train, valid in splits:
+        assert not set(train) & set(valid)
+
+
+def test_evaluate_is_zero_for_the_generating_model(oracle):
+    # test/test_linear_util.cpp:63-80: mse errors and values vanish (1e-12) at the datasource's own weights and bias
+    rng = np.random.default_rng(9)
+    X, W, b = rng.uniform(-1, 1, (20, 13)), rng.uniform(-1, 1, (3, 13)), rng.uniform(-1, 1, 3)
+    values = oracle.evaluate(X, X @ W.T + b, "mse", W, b)
+    assert values.shape == (2, 20) and np.max(np.abs(values)) < 1e-12
+
+
 def test_fit_result_bookkeeping():
     result = nb_linear.FitResult(("l1reg", "l2reg"), 2)
     result.add([[1.0, 1.0], [10.0, 1.0]])
@@ -221,6 +256,17 @@ def test_lasso_fit_with_a_nonsmooth_loss(oracle):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU: the product path
 # ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_evaluate_is_zero_for_the_generating_model(ctx):
+    # test/test_linear_util.cpp:63-80 on the device
+    import libnano_b200 as nb
+
+    rng = np.random.default_rng(9)
+    X, W, b = rng.uniform(-1, 1, (20, 13)), rng.uniform(-1, 1, (3, 13)), rng.uniform(-1, 1, 3)
+    values = nb.Dataset.pin(ctx, X, X @ W.T + b).evaluate(nb.Loss("mse"), W, b)
+    assert values.shape == (2, 20) and np.max(np.abs(values)) < 1e-12      # |outputs| <= 14: rounding is ~1e-15
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scaling", ["none", "standard"])
 def test_gpu_ordinary_fit_recovers_the_generating_model(ctx, scaling):
