@@ -7,7 +7,7 @@ grid + local search of the tuner (src/tuner.cpp:17-42, src/tuner/local.cpp, src/
 from the closest earlier trial (src/machine/result.cpp:82-100) — and the final refit on all samples.
 
 The four registered models (src/linear.cpp:124-139) differ in which regularisers they tune (src/linear/{ordinary,
-lasso,ridge,elastic_net}.cpp). What is NOT mirrored: the surrogate tuner, serialization, the file loggers."""
+lasso,ridge,elastic_net}.cpp). What is NOT mirrored: serialization, the file loggers, the random splitter."""
 from __future__ import annotations
 
 import itertools
@@ -72,10 +72,87 @@ def local_search(min_igrid, max_igrid, src_igrid, radius: int):
     return igrids
 
 
-def tune(spaces, callback, max_evals: int = 100):
-    """tuner_t::optimize with the local-search tuner (src/tuner.cpp:17-42, src/tuner/local.cpp:16-31):
-    `callback(params[trials, n_params]) -> values[trials]`; returns the steps [(igrid, params, value)] sorted by value."""
+class ParamSpace(tuple):
+    """param_space_t (src/tuner/space.cpp): a sorted grid of distinct values searched on a linear or a log10 scale. A
+    plain tuple of grid values is a log10 space (what linear::make_param_space builds)."""
+
+    def __new__(cls, values, scale: str = "log10"):
+        values = tuple(float(v) for v in values)
+        critical(len(values) >= 2, "parameter space: at least two grid values must be given!")
+        critical(all(a < b for a, b in zip(values, values[1:])), "parameter space: the grid values must be sorted and "
+                 "distinct!")
+        critical(scale in ("linear", "log10"), "parameter space: unknown scale")
+        critical(scale != "log10" or values[0] >= np.finfo(float).eps,
+                 "parameter space: the grid values must be strictly positive if using the logarithmic scale!")
+        self = super().__new__(cls, values)
+        self.scale = scale
+        return self
+
+    def to_surrogate(self, value: float) -> float:
+        critical(self[0] <= value <= self[-1], "parameter space: cannot map value (", value,
+                 ") outside the parameter grid range [", self[0], ",", self[-1], "]!")
+        return (value - self[0]) / (self[-1] - self[0]) if self.scale == "linear" else float(np.log10(value))
+
+    def closest_grid_point_from_surrogate(self, value: float) -> int:
+        return int(np.argmin([abs(value - self.to_surrogate(v)) for v in self]))      # the first of equal distances
+
+
+def quadratic_surrogate_features(p):
+    """quadratic_surrogate_fit_t (src/tuner/surrogate.cpp:8-41): [1 | p_i | p_i p_j (i <= j)] per sample."""
+    p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+    size = p.shape[1]
+    columns = [np.ones(p.shape[0])] + [p[:, i] for i in range(size)]
+    columns += [p[:, i] * p[:, j] for i in range(size) for j in range(i, size)]
+    return np.stack(columns, axis=1)
+
+
+def quadratic_surrogate_model(q):
+    """quadratic_surrogate_t (src/tuner/surrogate.cpp:73-100): q -> (Q, c, d) with value x.Q.x / 2 + c.x + d."""
+    q = np.asarray(q, dtype=np.float64)
+    size = int(np.sqrt(2 * q.size)) - 1
+    critical(size > 0 and q.size == (size + 1) * (size + 2) // 2, "tuner: invalid surrogate model")
+    Q = np.zeros((size, size))
+    k = size + 1
+    for i in range(size):
+        for j in range(i, size):
+            Q[i, j] = Q[j, i] = q[k]
+            k += 1
+    Q[np.diag_indices(size)] *= 2.0
+    return Q, q[1:size + 1].copy(), float(q[0])
+
+
+def _surrogate_candidate(spaces, steps):
+    """One iteration of surrogate_tuner_t::do_optimize (src/tuner/surrogate.cpp:139-186): fit the quadratic to every
+    evaluated step (least squares = the mse fit the reference runs L-BFGS on, minimum norm while under-determined),
+    minimise it, return the closest grid point. A surrogate that is not convex has no minimiser (the reference's
+    L-BFGS then stops wherever its budget ends): the grid point with the smallest surrogate value is taken instead."""
+    p = np.array([[space.to_surrogate(v) for space, v in zip(spaces, step[1])] for step in steps])
+    y = np.array([step[2] for step in steps])
+    q = np.linalg.lstsq(quadratic_surrogate_features(p), y, rcond=None)[0]
+    critical(np.all(np.isfinite(q)), "tuner: failed to fit the surrogate model!")
+    Q, c, _ = quadratic_surrogate_model(q)
+    try:
+        np.linalg.cholesky(Q)
+        optimum = np.linalg.solve(Q, -c)
+        return tuple(space.closest_grid_point_from_surrogate(x) for space, x in zip(spaces, optimum))
+    except np.linalg.LinAlgError:
+        grids = [np.array([space.to_surrogate(v) for v in space]) for space in spaces]
+        best, best_value = None, np.inf
+        for igrid in itertools.product(*[range(len(space)) for space in spaces]):
+            x = np.array([grid[i] for grid, i in zip(grids, igrid)])
+            value = float(x @ (0.5 * Q @ x + c))
+            if value < best_value:
+                best, best_value = igrid, value
+        return best
+
+
+def tune(spaces, callback, max_evals: int = 100, tuner: str = "local-search"):
+    """tuner_t::optimize (src/tuner.cpp:17-42) with the local-search tuner (src/tuner/local.cpp:16-31) or the
+    quadratic-surrogate tuner (src/tuner/surrogate.cpp:125-186): `callback(params[trials, n_params]) -> values[trials]`;
+    returns the steps [(igrid, params, value)] sorted by value."""
     critical(len(spaces) > 0, "tuner: at least one parameter space is needed!")
+    critical(tuner in ("local-search", "surrogate"), "tuner: unknown id <", tuner, ">")
+    spaces = [space if isinstance(space, ParamSpace) else ParamSpace(space) for space in spaces]
     min_igrid = tuple(0 for _ in spaces)
     max_igrid = tuple(len(space) - 1 for space in spaces)
     avg_igrid = tuple(len(space) // 2 for space in spaces)
@@ -100,8 +177,9 @@ def tune(spaces, callback, max_evals: int = 100):
         if not evaluate(local_search(min_igrid, max_igrid, steps[0][0], radius)):
             break
         radius *= 2
-    while steps and len(steps) < max_evals:                    # local search, radius 1
-        if not evaluate(local_search(min_igrid, max_igrid, steps[0][0], 1)):
+    while steps and len(steps) < max_evals:                    # around the optimum / the surrogate's minimiser, radius 1
+        centre = steps[0][0] if tuner == "local-search" else _surrogate_candidate(spaces, steps)
+        if not evaluate(local_search(min_igrid, max_igrid, centre, 1)):
             break
     return steps
 
@@ -214,9 +292,10 @@ class LinearModel:
         return W, b, state
 
     def fit(self, ctx, X, Y, loss, samples=None, solver=None, folds: int = 5, seed: int = 42,
-            tuner_max_evals: int = 100, _backend=None) -> FitResult:
+            tuner_max_evals: int = 100, tuner: str = "local-search", _backend=None) -> FitResult:
         """linear_t::fit (src/linear.cpp:79-116). X[N, D], Y[N, T] host arrays; `loss`: Loss or its id; `solver`:
-        callable (function, x0) -> dict with "x" (default_solver); returns the FitResult, keeps (weights, bias)."""
+        callable (function, x0) -> dict with "x" (default_solver); `tuner`: "local-search" or "surrogate" (the reference's
+        default, src/machine/params.cpp:11); returns the FitResult, keeps (weights, bias)."""
         backend = _backend or _DeviceBackend(ctx)
         loss = Loss(loss) if isinstance(loss, str) else loss
         solver = solver or default_solver
@@ -249,7 +328,7 @@ class LinearModel:
                         result.valid[old_trials + trial, fold] = valid_sets[fold].evaluate(loss, W, b).mean(axis=1)
                 return [result.value(trial) for trial in range(old_trials, result.trials())]
 
-            tune(spaces, callback, tuner_max_evals)
+            tune(spaces, callback, tuner_max_evals, tuner)
             params = result.params[result.optimum_trial()]
         else:
             params = np.zeros(0)

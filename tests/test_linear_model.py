@@ -196,6 +196,90 @@ def test_evaluate_is_zero_for_the_generating_model(oracle):
     assert values.shape == (2, 20) and np.max(np.abs(values)) < 1e-12
 
 
+# test/test_tuner.cpp:13-26: param1 on a linear scale, param2 on a log10 scale
+TUNER_SPACES = (nb_linear.ParamSpace((0.0, 0.1, 0.2, 0.3, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0), "linear"),
+                nb_linear.ParamSpace((1e-3, 1e-2, 1e-1, 1e+0, 1e+1, 1e+2, 1e+3), "log10"))
+
+
+def evaluate_ll(x, y, x0, y0):      # test/test_tuner.cpp:28-31
+    return (x - x0) ** 2 + (y - y0) ** 2 + 0.5
+
+
+def evaluate_10(x, y, x0, y0):      # test/test_tuner.cpp:33-36
+    return (x - x0) ** 2 + (np.log10(y) - np.log10(y0) - (1.0 + x) / (1.0 + x0) + 1.0) ** 2 + 0.5
+
+
+@pytest.mark.parametrize("tuner,evaluator", [("local-search", evaluate_ll), ("surrogate", evaluate_10)])
+def test_tuners_find_every_grid_optimum(tuner, evaluator):
+    # check_optimize (test/test_tuner.cpp:38-80): wherever the optimum sits on the 10 x 7 grid, the tuner ends on it,
+    # its steps are sorted and no grid point is evaluated twice
+    for ix0, x0 in enumerate(TUNER_SPACES[0]):
+        for iy0, y0 in enumerate(TUNER_SPACES[1]):
+            steps = nb_linear.tune(TUNER_SPACES, lambda params: [evaluator(p[0], p[1], x0, y0) for p in params],
+                                   tuner=tuner)
+            assert [s[2] for s in steps] == sorted(s[2] for s in steps)
+            assert len({s[0] for s in steps}) == len(steps)
+            assert steps[0][0] == (ix0, iy0) and tuple(steps[0][1]) == (x0, y0) and steps[0][2] == 0.5
+
+
+@pytest.mark.parametrize("tuner", ["local-search", "surrogate"])
+def test_tuners_fail_like_the_reference(tuner):
+    # test/test_tuner.cpp:384-410
+    with pytest.raises(RuntimeError, match="at least one parameter space"):
+        nb_linear.tune([], lambda params: [], tuner=tuner)
+    with pytest.raises(RuntimeError, match="invalid value"):
+        nb_linear.tune(TUNER_SPACES, lambda params: [np.nan] * len(params), tuner=tuner)
+    with pytest.raises(RuntimeError, match="unknown id"):
+        nb_linear.tune(TUNER_SPACES, lambda params: [0.0] * len(params), tuner="bayesian")
+
+
+def test_param_space_contract():
+    # test/test_tuner.cpp:125-214
+    for values, scale in (((), "log10"), ((1.0,), "log10"), ((1.0, 1.0), "linear"), ((2.0, 1.0), "linear"),
+                          ((0.0, 1.0), "log10"), ((-1.0, 1.0), "log10")):
+        with pytest.raises(RuntimeError):
+            nb_linear.ParamSpace(values, scale)
+    log_space, linear_space = TUNER_SPACES[1], TUNER_SPACES[0]
+    assert log_space.to_surrogate(1e-3) == -3.0 and log_space.to_surrogate(1e+2) == 2.0
+    assert linear_space.to_surrogate(0.5) == 0.5 and linear_space.to_surrogate(1.0) == 1.0
+    with pytest.raises(RuntimeError, match="outside the parameter grid range"):
+        log_space.to_surrogate(1e+4)
+    assert [log_space.closest_grid_point_from_surrogate(v) for v in (-9.0, -2.6, -2.4, 0.1, 2.9, 7.0)] == [0, 0, 1, 3, 6, 6]
+    assert [linear_space.closest_grid_point_from_surrogate(v) for v in (-1.0, 0.04, 0.41, 0.95, 3.0)] == [0, 0, 4, 8, 9]
+
+
+@pytest.mark.parametrize("p,q", [((1.0,), (1.0, -2.0, 1.0)), ((1.0, -2.0), (5.0, -2.0, 4.0, 1.0, 0.0, 1.0)),
+                                 ((0.1, 1.0), (1.0, 0.0, -2.0, 1.0, -0.2, 1.01))])
+def test_quadratic_surrogate_known_minimisers(p, q):
+    # test/test_tuner.cpp:313-335: the surrogate with coefficients q has its minimum, 0, at p
+    Q, c, d = nb_linear.quadratic_surrogate_model(q)
+    optimum = np.linalg.solve(Q, -c)
+    assert np.allclose(optimum, p, rtol=0, atol=1e-12)
+    assert abs(optimum @ (0.5 * Q @ optimum + c) + d) < 1e-12
+    assert abs(float((nb_linear.quadratic_surrogate_features([p]) @ np.asarray(q))[0])) < 1e-12    # same model
+
+
+def test_quadratic_surrogate_fit_recovers_the_coefficients():
+    # test/test_tuner.cpp:337-368
+    q1 = np.array([1.0, 0.5, -1.0])
+    p1 = np.arange(-3.0, 4.0).reshape(7, 1)
+    y1 = q1[0] + q1[1] * p1[:, 0] + q1[2] * p1[:, 0] ** 2
+    assert np.allclose(np.linalg.lstsq(nb_linear.quadratic_surrogate_features(p1), y1, rcond=None)[0], q1, atol=1e-12)
+    q2 = np.array([1.0, 0.5, 1.5, 2.0, -1.0, -1.0])
+    p2 = np.array([[a, b] for a in range(-2, 3) for b in range(-2, 3)], dtype=np.float64)
+    y2 = q2[0] + q2[1] * p2[:, 0] + q2[2] * p2[:, 1] + q2[3] * p2[:, 0] ** 2 + q2[4] * p2[:, 0] * p2[:, 1] \
+        + q2[5] * p2[:, 1] ** 2
+    assert np.allclose(np.linalg.lstsq(nb_linear.quadratic_surrogate_features(p2), y2, rcond=None)[0], q2, atol=1e-12)
+
+
+def test_ridge_fit_with_the_surrogate_tuner(oracle):
+    X, Y, W, b = linear_datasource(2, 100, 5)
+    model = nb_linear.LinearModel("ridge", "standard")
+    result = model.fit(None, X, Y, "mse", solver=cpu_solver(oracle), folds=2, tuner="surrogate",
+                       _backend=OracleBackend(oracle))
+    assert result.optimum_params()["l2reg"] <= 1e-4 and np.max(np.abs(model.weights() - W)) < 1e-3
+
+
 def test_fit_result_bookkeeping():
     result = nb_linear.FitResult(("l1reg", "l2reg"), 2)
     result.add([[1.0, 1.0], [10.0, 1.0]])
