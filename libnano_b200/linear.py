@@ -7,7 +7,7 @@ grid + local search of the tuner (src/tuner.cpp:17-42, src/tuner/local.cpp, src/
 from the closest earlier trial (src/machine/result.cpp:82-100) — and the final refit on all samples.
 
 The four registered models (src/linear.cpp:124-139) differ in which regularisers they tune (src/linear/{ordinary,
-lasso,ridge,elastic_net}.cpp). What is NOT mirrored: serialization, the file loggers, the random splitter."""
+lasso,ridge,elastic_net}.cpp). What is NOT mirrored: serialization and the file loggers."""
 from __future__ import annotations
 
 import itertools
@@ -60,6 +60,23 @@ def kfold_split(samples, folds: int = 5, seed: int = 42):
         train = np.sort(np.concatenate([shuffled[:begin], shuffled[end:]]))
         splits.append((train, valid))
     return splits
+
+
+def random_split(samples, folds: int = 5, seed: int = 42, train_per: int = 80):
+    """random_splitter_t::split (src/splitter/random.cpp:13-46): `folds` independent shuffles, the first train_per
+    percent train, the rest validate; both parts sorted. (numpy's shuffle, as in kfold_split.)"""
+    samples = np.array(samples, dtype=np.int64)
+    critical(10 <= train_per <= 90, "splitter: train_per out of [10, 90]")
+    train_size = (train_per * samples.size + 50) // 100          # idiv: rounds to nearest (numeric.h)
+    rng = np.random.default_rng(seed)
+    splits = []
+    for _ in range(folds):
+        samples = rng.permutation(samples)
+        splits.append((np.sort(samples[:train_size]), np.sort(samples[train_size:])))
+    return splits
+
+
+SPLITTERS = {"k-fold": kfold_split, "random": random_split}
 
 
 def local_search(min_igrid, max_igrid, src_igrid, radius: int):
@@ -292,7 +309,8 @@ class LinearModel:
         return W, b, state
 
     def fit(self, ctx, X, Y, loss, samples=None, solver=None, folds: int = 5, seed: int = 42,
-            tuner_max_evals: int = 100, tuner: str = "local-search", _backend=None) -> FitResult:
+            tuner_max_evals: int = 100, tuner: str = "local-search", splitter: str = "k-fold",
+            _backend=None) -> FitResult:
         """linear_t::fit (src/linear.cpp:79-116). X[N, D], Y[N, T] host arrays; `loss`: Loss or its id; `solver`:
         callable (function, x0) -> dict with "x" (default_solver); `tuner`: "local-search" or "surrogate" (the reference's
         default, src/machine/params.cpp:11); returns the FitResult, keeps (weights, bias)."""
@@ -306,7 +324,8 @@ class LinearModel:
         result = FitResult(MODELS[self.kind], folds if spaces else 0)
 
         if spaces:
-            splits = kfold_split(samples, folds, seed)
+            critical(splitter in SPLITTERS, "splitter: unknown id <", splitter, ">")
+            splits = SPLITTERS[splitter](samples, folds, seed)
             # per fold, pinned once for all the trials: the scaled training samples (what the objective reads) and
             # both splits unscaled (the upscaled model is evaluated on them)
             scaled_sets = [self._prepare(backend, loss, X[train], Y[train]) for train, _ in splits]

@@ -188,6 +188,25 @@ def test_kfold_reference_case(seed):
         assert not set(train) & set(valid)
 
 
+@pytest.mark.parametrize("seed", [42, 11, 122])
+def test_random_split_reference_case(seed):
+    # test/test_splitter.cpp:90-108: 30 samples, 5 folds, 80 % -> 24 / 6, each fold a partition
+    splits = nb_linear.random_split(np.arange(30), 5, seed)
+    assert [(train.size, valid.size) for train, valid in splits] == [(24, 6)] * 5
+    for train, valid in splits:
+        assert np.array_equal(np.sort(np.concatenate([train, valid])), np.arange(30))
+        assert np.all(np.diff(train) > 0) and np.all(np.diff(valid) > 0)
+
+
+@pytest.mark.parametrize("splitter", ["k-fold", "random"])
+def test_splitters_are_consistent(splitter):
+    # test/test_splitter.cpp:110-140: same seed, same splits; another seed, other splits
+    split = nb_linear.SPLITTERS[splitter]
+    a, b, c = split(np.arange(21), 5, 42), split(np.arange(21), 5, 42), split(np.arange(21), 5, 11)
+    assert all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(a, b))
+    assert any(not np.array_equal(x[1], y[1]) for x, y in zip(a, c))
+
+
 def test_evaluate_is_zero_for_the_generating_model(oracle):
     # test/test_linear_util.cpp:63-80: mse errors and values vanish (1e-12) at the datasource's own weights and bias
     rng = np.random.default_rng(9)
