@@ -25,6 +25,8 @@ def main():
     parser.add_argument("--outer-folds", type=int, default=2)
     parser.add_argument("--folds", type=int, default=2)
     parser.add_argument("--tuner-max-evals", type=int, default=100)
+    parser.add_argument("--tuner", default="local-search", choices=["local-search", "surrogate"])
+    parser.add_argument("--splitter", default="k-fold", choices=["k-fold", "random"])
     parser.add_argument("--noise", type=float, default=0.1)
     args = parser.parse_args()
 
@@ -56,10 +58,11 @@ def main():
           flush=True)
     data.close()
 
-    for fold, (train, valid) in enumerate(linear.kfold_split(np.arange(N), args.outer_folds, seed=42)):
+    for fold, (train, valid) in enumerate(linear.SPLITTERS[args.splitter](np.arange(N), args.outer_folds, seed=42)):
         model = nb.LinearModel(args.linear, "standard")
         t0 = time.perf_counter()
-        result = model.fit(ctx, X, Y, loss, samples=train, folds=args.folds, tuner_max_evals=args.tuner_max_evals)
+        result = model.fit(ctx, X, Y, loss, samples=train, folds=args.folds, tuner_max_evals=args.tuner_max_evals,
+                           tuner=args.tuner, splitter=args.splitter)
         fit_seconds = time.perf_counter() - t0
         test = model.evaluate(ctx, X[valid], Y[valid], loss)
         optimum = result.optimum_trial() if result.trials() else None
@@ -70,7 +73,7 @@ def main():
             "train_error": None if optimum is None else float(np.mean(result.train[optimum, :, 0])),
             "valid_error": None if optimum is None else result.value(optimum),
             "refit_error": float(np.mean(result.refit["errors"])), "test_error": float(np.mean(test[0])),
-            "trials": result.trials(), "inner_folds": args.folds, "fit_seconds": round(fit_seconds, 3),
+            "trials": result.trials(), "inner_folds": args.folds, "tuner": args.tuner, "splitter": args.splitter, "fit_seconds": round(fit_seconds, 3),
             "refit_status": result.refit["state"]["status"], "refit_fcalls": result.refit["state"]["fcalls"],
             "max_weight_error": float(np.max(np.abs(model.weights() - W))) if loss.error_kind == 0 else None,
             "sparsity_ratio_1e-2": linear.sparsity_ratio(importance, 1e-2),
