@@ -204,8 +204,8 @@ def _simplex_qp(K, h):
 
 class _Bundle:
     """The bundle of cutting planes of libnano's proximal bundle solvers (bundle_t, src/solver/bundle/bundle.cpp):
-    rows (g_j, h_j) with h_j = f_j + g_j.(x - x_j) relative to the stability centre x, kept small by dropping the
-    planes with zero multipliers and, at capacity, the two smallest ones in favour of the aggregate plane."""
+    rows (g_j, h_j) with h_j = f_j + g_j.(x - x_j) relative to the stability centre x; a full bundle first drops the
+    planes with zero multipliers, then the two smallest ones in favour of the aggregate plane."""
 
     def __init__(self, x, gx, fx, max_size):
         n = x.size

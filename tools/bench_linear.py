@@ -54,7 +54,7 @@ def main():
     seconds = (time.perf_counter() - t0) / repeats
     print(json.dumps({"evaluate": f"{N} x {D}", "ms_per_call": round(1e3 * seconds, 3),
                       "gbs_of_X": round(8e-9 * N * D / seconds, 1),
-                      "note": "wall clock of nb200_evaluate: W, b up, three kernels, 2 N doubles back to pageable memory"}),
+                      "note": "wall clock of nb200_evaluate: W, b up, three kernels, 2 N doubles back through the pinned staging buffer"}),
           flush=True)
     data.close()
 
