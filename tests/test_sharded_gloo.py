@@ -88,3 +88,54 @@ def test_sharded_function_over_gloo(oracle, world, N, D, T, loss_id):
         p.join(timeout=120)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert list(out) == [1] * world
+
+
+def _solver_worker(rank, world, port, N, D, solver_id, out):
+    """The host-driven non-smooth drivers over a sharded objective: every rank runs the same host algebra on the same
+    all-reduced (f, g), so the ranks stay in lock-step without any further exchange."""
+    import oracle
+    from libnano_b200 import solver as nb_solver
+    from libnano_b200.sharded import ShardedFunction, shard_rows
+    from test_host_solvers import OracleFunction, informative_problem
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, Y = informative_problem(4, N, D, True)
+        l1, l2 = 1e-2, 1e-2
+        row0, rows = shard_rows(N, world, rank)
+        shard = OracleShard(oracle, X[row0:row0 + rows], Y[row0:row0 + rows], "s-hinge", l1, l2)
+        function = ShardedFunction(shard, N, convex=True, smooth=False, strong_convexity=l2 / D)
+        x0 = np.zeros(D + 1)
+        if solver_id == "rqb":
+            result = nb_solver.rqb(function, x0, epsilon=1e-8, max_evals=4000)
+            whole = nb_solver.rqb(OracleFunction(oracle, X, Y, "s-hinge", l1=l1, l2=l2), x0, epsilon=1e-8, max_evals=4000)
+            ok = result["status"] == "specific_test" and abs(result["fx"] - whole["fx"]) <= 1e-7 * (1 + abs(whole["fx"]))
+        else:
+            result = nb_solver.osga(function, x0, epsilon=1e-6, max_evals=600)
+            ok = result["fx"] < function(x0) and result["iterations"] > 10
+        # lock-step: identical iterates and call counts on every rank
+        packed = np.concatenate([result["x"], [result["fx"], result["fcalls"], result["iterations"]]])
+        gathered = [torch.zeros(packed.size, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(packed))
+        ok = ok and all(torch.equal(gathered[0], g) for g in gathered)
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("solver_id", ["rqb", "osga"])
+def test_host_driven_solvers_stay_in_lock_step_over_gloo(oracle, solver_id):
+    # BASELINE config 5 sharded: hinge + elastic net over 2 ranks, the drivers replicated on every rank
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_solver_worker, args=(r, world, port, 600, 8, solver_id, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert list(out) == [1] * world
