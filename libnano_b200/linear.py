@@ -310,10 +310,12 @@ class LinearModel:
 
     def fit(self, ctx, X, Y, loss, samples=None, solver=None, folds: int = 5, seed: int = 42,
             tuner_max_evals: int = 100, tuner: str = "local-search", splitter: str = "k-fold",
-            _backend=None) -> FitResult:
+            batch_trials: bool = False, _backend=None) -> FitResult:
         """linear_t::fit (src/linear.cpp:79-116). X[N, D], Y[N, T] host arrays; `loss`: Loss or its id; `solver`:
         callable (function, x0) -> dict with "x" (default_solver); `tuner`: "local-search" or "surrogate" (the reference's
-        default, src/machine/params.cpp:11); returns the FitResult, keeps (weights, bias)."""
+        default, src/machine/params.cpp:11); `batch_trials`: solve the trials the tuner asks for together on each fold
+        with solver.lbfgs_batch - ONE pass over X per round for all of them (nb200_vgrad_batch) - when the objective
+        is smooth (l1reg = 0, smooth loss, one target); returns the FitResult, keeps (weights, bias)."""
         backend = _backend or _DeviceBackend(ctx)
         loss = Loss(loss) if isinstance(loss, str) else loss
         solver = solver or default_solver
@@ -332,9 +334,35 @@ class LinearModel:
             train_sets = [backend.pin(X[train], Y[train]) for train, _ in splits]
             valid_sets = [backend.pin(X[valid], Y[valid]) for _, valid in splits]
 
+            def store(trial, fold, W, b, x):
+                result.extras[trial][fold] = x
+                result.train[trial, fold] = train_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                result.valid[trial, fold] = valid_sets[fold].evaluate(loss, W, b).mean(axis=1)
+
+            def batched_callback(new_params, old_trials):
+                """All the new trials of a fold advance together: one pass over X per round (solver.lbfgs_batch)."""
+                from . import solver as nb_solver
+
+                regularisers = [self._regularisers(params) for params in new_params]
+                for fold, data in enumerate(scaled_sets):
+                    function = backend.function(data, loss, 0.0, 0.0)
+                    x0s = np.zeros((len(new_params), function.size()))
+                    for trial, params in enumerate(new_params):
+                        if old_trials > 0:
+                            x0s[trial] = result.extras[result.closest_trial(params, old_trials)][fold]
+                    states = nb_solver.lbfgs_batch(function, x0s, 0.0, [l2 for _, l2 in regularisers], epsilon=1e-8)
+                    for trial, state in enumerate(states):
+                        W, b = data.upscale(function.weights(state["x"]), function.bias(state["x"]))
+                        store(old_trials + trial, fold, W, b, state["x"])
+
             def callback(new_params):                          # ml::tune's tuner_callback (tune.cpp:19-46)
                 old_trials = result.trials()
                 result.add(new_params)
+                batchable = (batch_trials and loss.smooth() and Y.shape[1] == 1
+                             and all(self._regularisers(params)[0] == 0.0 for params in new_params))
+                if batchable:
+                    batched_callback(new_params, old_trials)
+                    return [result.value(trial) for trial in range(old_trials, result.trials())]
                 for trial, params in enumerate(new_params):
                     closest = result.closest_trial(params, old_trials) if old_trials > 0 else None
                     for fold in range(len(splits)):
@@ -342,9 +370,7 @@ class LinearModel:
                         # scaled space, where the reference passes the upscaled weights, src/linear.cpp:16-28)
                         x0 = result.extras[closest][fold] if closest is not None else None
                         W, b, state = self._fit_once(backend, loss, solver, scaled_sets[fold], params, x0)
-                        result.extras[old_trials + trial][fold] = state["x"]
-                        result.train[old_trials + trial, fold] = train_sets[fold].evaluate(loss, W, b).mean(axis=1)
-                        result.valid[old_trials + trial, fold] = valid_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                        store(old_trials + trial, fold, W, b, state["x"])
                 return [result.value(trial) for trial in range(old_trials, result.trials())]
 
             tune(spaces, callback, tuner_max_evals, tuner)

@@ -459,3 +459,113 @@ def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: in
 
     return {"x": x, "fx": fx, "status": result_status, "fcalls": function.fcalls(), "gcalls": function.gcalls(),
             "iterations": iterations}
+
+
+def lbfgs_batch(function, x0s, l1s, l2s, epsilon: float = 1e-8, max_rounds: int = 1000, history: int = 20,
+                c1: float = 1e-4, c2: float = 0.9):
+    """K L-BFGS solves that share one pass over X per evaluation round (the tuner's trials on one fold,
+    src/machine/tune.cpp:25-42, differ only in their regularisation values).
+
+    Every round evaluates the current trial point of all the unfinished models with ONE `function.vgrad_batch`
+    (nb200_vgrad_batch: the K weight vectors become the rows of one many-target problem), then each model advances its
+    own two-loop recursion (src/solver/lbfgs.cpp:49-84) and its own line search on the host: bracketing / bisection to
+    the weak Wolfe conditions (c1, c2), or CG-DESCENT's approximate ones at rounding level, from a unit step (1 / |g|
+    for the first iteration). Smooth objectives only
+    (l1 = 0). Stops per model on libnano's gradient test |g|_inf / max(1, |f|) < epsilon (src/solver/state.cpp:138-141).
+    Returns a list of dicts like lbfgs(): x, fx, gradient_test, status, fcalls, iterations; plus "rounds" = the number
+    of passes over X the whole batch took."""
+    xs = np.array(x0s, dtype=np.float64, ndmin=2)
+    K, n = xs.shape
+    critical(n == function.size(), "solver: incompatible initial points (", n, " dimensions), expecting ",
+             function.size(), " dimensions!")
+    l1s = np.broadcast_to(np.asarray(l1s, dtype=np.float64), (K,)).copy()
+    l2s = np.broadcast_to(np.asarray(l2s, dtype=np.float64), (K,)).copy()
+    critical(bool(np.all(l1s == 0.0)), "solver: lbfgs_batch is for smooth objectives (l1 = 0)")
+
+    def gradient_test(f, g):
+        return float(np.max(np.abs(g))) / max(1.0, abs(f))
+
+    fs, gs = function.vgrad_batch(xs, l1s, l2s)
+    rounds = 1
+    models = []
+    for k in range(K):
+        model = {"x": xs[k].copy(), "f": float(fs[k]), "g": gs[k].copy(), "S": [], "Y": [], "status": None,
+                 "fcalls": 1, "iterations": 0}
+        if not (np.isfinite(model["f"]) and np.all(np.isfinite(model["g"]))):
+            model["status"] = "failed"
+        elif gradient_test(model["f"], model["g"]) < epsilon:
+            model["status"] = "gradient_test"
+        models.append(model)
+
+    def new_direction(model):
+        # two-loop recursion over the (s, y) pairs, newest last
+        q = model["g"].copy()
+        alphas = []
+        for s, y in zip(reversed(model["S"]), reversed(model["Y"])):
+            alpha = float(s @ q) / float(s @ y)
+            alphas.append(alpha)
+            q -= alpha * y
+        if model["S"]:
+            s, y = model["S"][-1], model["Y"][-1]
+            q *= float(s @ y) / float(y @ y)
+        for (s, y), alpha in zip(zip(model["S"], model["Y"]), reversed(alphas)):
+            beta = float(y @ q) / float(s @ y)
+            q += (alpha - beta) * s
+        d = -q
+        dg = float(d @ model["g"])
+        if not dg < 0.0:                                      # not a descent direction: restart from steepest descent
+            model["S"], model["Y"] = [], []
+            d = -model["g"]
+            dg = float(d @ model["g"])
+        model["d"], model["dg"] = d, dg
+        model["t"] = 1.0 if model["S"] else 1.0 / max(float(np.linalg.norm(model["g"])), 1e-300)
+        model["lo"], model["hi"] = 0.0, np.inf
+
+    for model in models:
+        if model["status"] is None:
+            new_direction(model)
+
+    while rounds < max_rounds:
+        active = [k for k, model in enumerate(models) if model["status"] is None]
+        if not active:
+            break
+        trial = np.stack([models[k]["x"] + models[k]["t"] * models[k]["d"] for k in active])
+        fs, gs = function.vgrad_batch(trial, l1s[active], l2s[active])
+        rounds += 1
+        for row, k in enumerate(active):
+            model = models[k]
+            model["fcalls"] += 1
+            f, g, t = float(fs[row]), gs[row], model["t"]
+            finite = np.isfinite(f) and bool(np.all(np.isfinite(g)))
+            gd = float(g @ model["d"]) if finite else np.nan
+            armijo = finite and f <= model["f"] + c1 * t * model["dg"]
+            # the approximate Wolfe conditions of CG-DESCENT (src/lsearchk/cgdescent.cpp, epsilon 1e-6): once the
+            # decrease of f drowns in its rounding, the slope alone decides
+            approximate = (finite and f <= model["f"] + 1e-6 * abs(model["f"])
+                           and (2.0 * c1 - 1.0) * model["dg"] >= gd >= c2 * model["dg"])
+            if not approximate and not (armijo and gd >= c2 * model["dg"]):
+                if armijo:
+                    model["lo"] = t                                          # curvature fails: grow
+                else:
+                    model["hi"] = t                                          # Armijo fails: shrink
+                model["t"] = 0.5 * (model["lo"] + model["hi"]) if np.isfinite(model["hi"]) else 2.0 * model["lo"]
+                collapsed = np.isfinite(model["hi"]) and model["hi"] - model["lo"] <= 1e-16 * max(1.0, model["hi"])
+                if collapsed or model["t"] > 1e300:
+                    model["status"] = "failed"                               # no Wolfe point in the bracket
+                continue
+            s_k, y_k = trial[row] - model["x"], g - model["g"]               # a Wolfe point: accept the step
+            if float(s_k @ y_k) > 1e-16 * float(np.linalg.norm(s_k)) * float(np.linalg.norm(y_k)):
+                model["S"].append(s_k)
+                model["Y"].append(y_k)
+                if len(model["S"]) > history:
+                    model["S"].pop(0)
+                    model["Y"].pop(0)
+            model["x"], model["f"], model["g"] = trial[row].copy(), f, g.copy()
+            model["iterations"] += 1
+            if gradient_test(f, g) < epsilon:
+                model["status"] = "gradient_test"
+            else:
+                new_direction(model)
+    return [{"x": model["x"], "fx": model["f"], "gradient_test": gradient_test(model["f"], model["g"]),
+             "status": model["status"] or "max_iters", "fcalls": model["fcalls"], "gcalls": model["fcalls"],
+             "iterations": model["iterations"], "rounds": rounds} for model in models]

@@ -62,6 +62,15 @@ class OracleLinearFunction(OracleFunction):
         return np.asarray(x)[D * T:]
 
 
+    def vgrad_batch(self, xs, l1s, l2s, want_grad=True):
+        # the product evaluates the K models in one pass over X (nb200_vgrad_batch); the double one by one
+        type(self).batch_calls = getattr(type(self), "batch_calls", 0) + 1
+        fs, gs = np.empty(len(xs)), np.empty_like(xs)
+        for k, x in enumerate(xs):
+            fs[k], gs[k] = self._oracle.linear_vgrad(self._X, self._Y, self._loss_id, x, float(l1s[k]), float(l2s[k]))
+        return fs, (gs if want_grad else None)
+
+
 class OracleBackend:
     def __init__(self, oracle):
         self.oracle = oracle
@@ -343,6 +352,31 @@ def test_ridge_fit_tunes_l2reg_and_recovers_the_model(oracle):
     # a heavier regulariser validates worse than the optimum
     heavy = int(np.argmax(result.params[:, 0]))
     assert result.value(heavy) > result.value(result.optimum_trial())
+
+
+def test_ridge_fit_with_batched_trials_matches_the_sequential_fit(oracle):
+    # N3 inside the tuner: the trials of each fold advance together (solver.lbfgs_batch over vgrad_batch)
+    X, Y, W, b = linear_datasource(2, 200, 6, noise=0.05)
+    sequential, batched = nb_linear.LinearModel("ridge"), nb_linear.LinearModel("ridge")
+    r_seq = sequential.fit(None, X, Y, "mse", solver=cpu_solver(oracle), folds=2, _backend=OracleBackend(oracle))
+    OracleLinearFunction.batch_calls = 0
+    r_bat = batched.fit(None, X, Y, "mse", solver=cpu_solver(oracle), folds=2, batch_trials=True,
+                        _backend=OracleBackend(oracle))
+    assert OracleLinearFunction.batch_calls > 0
+    # same trials up to ties between validation errors that differ by less than the solvers' precision (1e-8)
+    common = min(r_bat.trials(), r_seq.trials())
+    assert common >= 5 and np.array_equal(r_bat.params[:5], r_seq.params[:5])
+    for trial in range(r_bat.trials()):
+        match = np.flatnonzero(r_seq.params[:, 0] == r_bat.params[trial, 0])
+        if match.size:
+            assert np.max(np.abs(r_bat.valid[trial] - r_seq.valid[match[0]])) < 1e-6
+    assert abs(r_bat.value(r_bat.optimum_trial()) - r_seq.value(r_seq.optimum_trial())) < 1e-7
+    assert np.max(np.abs(batched.weights() - sequential.weights())) < 1e-5
+    # a non-smooth objective falls back to one solve per trial
+    OracleLinearFunction.batch_calls = 0
+    nb_linear.LinearModel("lasso").fit(None, X, Y, "mse", solver=cpu_solver(oracle), folds=2, tuner_max_evals=4,
+                                       batch_trials=True, _backend=OracleBackend(oracle))
+    assert OracleLinearFunction.batch_calls == 0
 
 
 def test_lasso_fit_with_a_nonsmooth_loss(oracle):

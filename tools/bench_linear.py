@@ -27,6 +27,8 @@ def main():
     parser.add_argument("--tuner-max-evals", type=int, default=100)
     parser.add_argument("--tuner", default="local-search", choices=["local-search", "surrogate"])
     parser.add_argument("--splitter", default="k-fold", choices=["k-fold", "random"])
+    parser.add_argument("--batch-trials", action="store_true",
+                        help="smooth objectives: the trials of a fold advance together, one pass over X per round")
     parser.add_argument("--noise", type=float, default=0.1)
     args = parser.parse_args()
 
@@ -62,7 +64,7 @@ def main():
         model = nb.LinearModel(args.linear, "standard")
         t0 = time.perf_counter()
         result = model.fit(ctx, X, Y, loss, samples=train, folds=args.folds, tuner_max_evals=args.tuner_max_evals,
-                           tuner=args.tuner, splitter=args.splitter)
+                           tuner=args.tuner, splitter=args.splitter, batch_trials=args.batch_trials)
         fit_seconds = time.perf_counter() - t0
         test = model.evaluate(ctx, X[valid], Y[valid], loss)
         optimum = result.optimum_trial() if result.trials() else None
@@ -73,7 +75,7 @@ def main():
             "train_error": None if optimum is None else float(np.mean(result.train[optimum, :, 0])),
             "valid_error": None if optimum is None else result.value(optimum),
             "refit_error": float(np.mean(result.refit["errors"])), "test_error": float(np.mean(test[0])),
-            "trials": result.trials(), "inner_folds": args.folds, "tuner": args.tuner, "splitter": args.splitter, "fit_seconds": round(fit_seconds, 3),
+            "trials": result.trials(), "inner_folds": args.folds, "tuner": args.tuner, "splitter": args.splitter, "batch_trials": args.batch_trials, "fit_seconds": round(fit_seconds, 3),
             "refit_status": result.refit["state"]["status"], "refit_fcalls": result.refit["state"]["fcalls"],
             "max_weight_error": float(np.max(np.abs(model.weights() - W))) if loss.error_kind == 0 else None,
             "sparsity_ratio_1e-2": linear.sparsity_ratio(importance, 1e-2),
