@@ -192,8 +192,23 @@ inline loss_traits_t loss_traits(const std::string& id)
     raise("loss: unknown id <" + id + ">");
 }
 
+// the terror policy behind a loss id (include/nano/loss/flatten.h:103-122): "s-" / "m-" prefix, else regression
+inline int error_kind(const std::string& id)
+{
+    return id.rfind("s-", 0) == 0 ? NB200_ERROR_SCLASS : id.rfind("m-", 0) == 0 ? NB200_ERROR_MCLASS : NB200_ERROR_ABSDIFF;
+}
+
 namespace linear
 {
+// linear::evaluate (src/linear/util.cpp:30-49) over a pinned dataset: per-sample errors and loss values of the
+// predictions X W^T + b; the outputs stay in HBM. `errors` / `values` hold samples() doubles each.
+inline void evaluate(const context_t& ctx, const dataset_t& dataset, const std::string& loss_id, const scalar_t* weights,
+                     const scalar_t* bias, scalar_t* errors, scalar_t* values, const scalar_t loss_param = 0.5)
+{
+    check(nb200_evaluate(ctx.handle(), dataset.handle(), loss_traits(loss_id).m_kind, loss_param, error_kind(loss_id),
+                         weights, bias, errors, values));
+}
+
 // nano::linear::function_t on the GPU: x = [W (T x D row-major) | b (T)]
 class function_t final : public ::nano_b200::function_t
 {
