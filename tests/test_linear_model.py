@@ -379,6 +379,22 @@ def test_ridge_fit_with_batched_trials_matches_the_sequential_fit(oracle):
     assert OracleLinearFunction.batch_calls == 0
 
 
+@pytest.mark.parametrize("kind,loss_id", [("lasso", "mse"), ("lasso", "mae"), ("elastic_net", "mae")])
+def test_regularised_fits_pass_the_reference_checks(oracle, kind, loss_id):
+    # test/test_linear_lasso.cpp / test_linear_elastic_net.cpp (disabled upstream "until an efficient optimizer ... is
+    # available"): weights and bias recovered to 1e-6, relevant features important (> 1e-1), irrelevant ones out (< 1e-6)
+    X, Y, W, b = linear_datasource(3, 100, 4)
+    model = nb_linear.LinearModel(kind, "standard")
+    kwargs = {"tuner_max_evals": 12} if kind == "elastic_net" else {}
+    result = model.fit(None, X, Y, loss_id, solver=cpu_solver(oracle), folds=2, _backend=OracleBackend(oracle), **kwargs)
+    assert result.refit["state"]["status"] in ("specific_test", "gradient_test")
+    assert np.max(np.abs(model.weights() - W)) < 1e-6 and np.max(np.abs(model.bias() - b)) < 1e-6
+    importance = nb_linear.feature_importance(model.weights())
+    relevant = np.abs(W[0]) > 0
+    assert np.all(importance[relevant] > 1e-1) and np.all(importance[~relevant] < 1e-6)
+    assert nb_linear.sparsity_ratio(importance) == 0.5                      # check_importance (fixture/linear.h:134-158)
+
+
 def test_lasso_fit_with_a_nonsmooth_loss(oracle):
     # test/test_linear_lasso.cpp with mae: RQB drives the non-smooth objective; irrelevant features stay out
     X, Y, W, b = linear_datasource(3, 80, 4)
