@@ -65,6 +65,13 @@ class context_t
 {
 public:
     explicit context_t(const int device = 0) { check(nb200_init(device, &m_handle)); }
+    // a device GROUP (nb200_init_multi): datasets pinned on it are split over the devices in contiguous row blocks and
+    // objectives on them evaluate on every device from this one process (the thread pool's role in libnano)
+    explicit context_t(const std::vector<int>& devices)
+    {
+        check(nb200_init_multi(static_cast<int>(devices.size()), devices.data(), &m_handle));
+    }
+    int devices() const { return nb200_ctx_devices(m_handle); }
     ~context_t() { nb200_ctx_release(m_handle); }
     context_t(const context_t&)            = delete;
     context_t& operator=(const context_t&) = delete;

@@ -15,6 +15,9 @@
 
 #include "../nb200.h"
 
+#include <algorithm>
+#include <vector>
+
 namespace nano::cuda
 {
 inline int loss_kind(const loss_t& loss)
@@ -49,8 +52,10 @@ inline int loss_kind(const loss_t& loss)
 class linear_function_t final : public ::nano::function_t
 {
 public:
+    /// \param devices the GPUs to shard the samples over (empty: every visible device, i.e. the whole box, like
+    ///        libnano's pool uses every core); the rows are split in contiguous blocks, one per device.
     linear_function_t(const flatten_iterator_t& iterator, const loss_t& loss, scalar_t l1reg, scalar_t l2reg,
-                      int device = 0)
+                      std::vector<int> devices = {})
         : ::nano::function_t("linear", (iterator.dataset().columns() + 1) * ::nano::size(iterator.dataset().target_dims()))
         , m_isize(iterator.dataset().columns())
         , m_tsize(::nano::size(iterator.dataset().target_dims()))
@@ -66,8 +71,17 @@ public:
                 targets.slice(range).reshape(range.size() * m_tsize) = target.reshape(range.size() * m_tsize);
             });
 
+        if (devices.empty())
+        {
+            for (int device = 0; device < nb200_device_count(); ++device)
+            {
+                devices.push_back(device);
+            }
+        }
+        // (never more devices than samples: every device needs at least one row)
+        devices.resize(std::min(devices.size(), static_cast<size_t>(std::max<tensor_size_t>(samples, 1))));
         nb200_ctx* ctx = nullptr;
-        check(nb200_init(device, &ctx));
+        check(nb200_init_multi(static_cast<int>(devices.size()), devices.data(), &ctx));
         m_ctx.reset(ctx, nb200_ctx_release);
 
         nb200_data* data = nullptr;

@@ -110,6 +110,21 @@ NB200_API int nb200_device_count(void);
 /* Bind a context to CUDA device `device` (creates a non-blocking stream). Fails loudly (NB200_ERR_CUDA) when
  * there is no usable GPU: there is no CPU fallback. */
 NB200_API int nb200_init(int device, nb200_ctx** out_ctx);
+
+/* A device GROUP: one process, several GPUs. libnano is one process that shards do_eval over the
+ * worker threads of its pool (src/linear/function.cpp:53-57) and fits one model per process (src/linear.cpp:30-48);
+ * a group context gives that process every GPU of the box. Datasets pinned (or generated) on it are split in
+ * contiguous balanced row blocks over `devices` (the first N % ndev devices hold one row more), objectives created
+ * on them evaluate on every device from the calling host thread, and every entry point that takes an nb200_obj /
+ * nb200_data / nb200_ctx accepts the group handle (exceptions: the cross-process protocol nb200_vgrad_partial /
+ * finish / peer_* / sharded, nb200_objective_set_stream and nb200_vgrad_batch return NB200_ERR_UNSUPPORTED).
+ * Single-target objectives on distinct devices with a peer path publish their reduced sums straight into the first
+ * device's mailbox (NVLink) from inside the launch; everything else gathers the per-device sums by peer copies. The
+ * fold runs in device order: results are bit-identical to the one-process-per-GPU path on the same partition.
+ * x / gx / fx of nb200_vgrad_device live on devices[0]. */
+NB200_API int nb200_init_multi(int ndev, const int* devices, nb200_ctx** out_ctx);
+/* devices of a context: 1 for nb200_init, ndev for nb200_init_multi */
+NB200_API int nb200_ctx_devices(const nb200_ctx* ctx);
 NB200_API void nb200_ctx_release(nb200_ctx* ctx);
 
 /* ---- dataset: replaces flatten_iterator_t::cache_flatten/cache_targets ---------------------------------------- */
@@ -200,6 +215,18 @@ NB200_API int nb200_vgrad_sharded(nb200_obj* obj, const double* x, int64_t n, in
 NB200_API int nb200_vgrad_sharded_device(nb200_obj* obj, const double* x_dev, int64_t n, int64_t n_global,
                                          double* gx_dev, double* fx_dev);
 
+/* How a connected objective meets its peers: 0 = the launch publishes its sums into the peers' mailboxes and leaves,
+ * the STREAM waits for the peers' ready words (cuStreamWaitValue64: no SM is held, so evaluations of different
+ * objectives can be enqueued in any order on different ranks without cross-waiting) and a finish kernel folds the
+ * slots; 1 = the launch itself waits for the peers (one kernel; used when the driver offers no stream wait, or with
+ * NB200_PEER_WAIT=1); -1 = not connected. Both kinds raise both signals, so ranks in different modes interoperate. */
+NB200_API int nb200_objective_peer_mode(const nb200_obj* obj);
+
+/* The per-device objectives behind a group objective (1 and the objective itself for a plain one): borrowed handles
+ * for per-device introspection (nb200_objective_describe / pass_stats / last_pass_ms / launches). */
+NB200_API int        nb200_objective_parts(const nb200_obj* obj);
+NB200_API nb200_obj* nb200_objective_part(nb200_obj* obj, int index);
+
 /* cudaStream_t of the objective, as an opaque pointer (so that callers can order collectives after phase 1);
  * set_stream re-points the objective at a caller-owned stream (a NULL handle is the legacy default stream), e.g. the
  * stream the caller's NCCL all-reduce is enqueued on, so that phase 1 -> all-reduce -> phase 2 need no host
@@ -216,6 +243,20 @@ NB200_API int64_t nb200_objective_launches(const nb200_obj* obj);
 NB200_API int    nb200_objective_enable_timing(nb200_obj* obj, int enabled);
 NB200_API double nb200_objective_last_pass_ms(nb200_obj* obj);
 NB200_API int    nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count, int reset);
+
+/* The passes since the last reset one by one (milliseconds, at most `capacity` of them; *count = how many there are):
+ * the distribution behind pass_stats, e.g. to tell a straggling device from a slow collective. A group objective
+ * reports its first device; the others through nb200_objective_part. */
+NB200_API int nb200_objective_pass_samples(nb200_obj* obj, double* pass_ms, int64_t capacity, int64_t* count);
+
+/* The roofline denominators of THIS board, measured in the run that quotes them (a few milliseconds each):
+ * the issue rate of the fp64 tensor pipe (mma.sync m8n8k4 f64 — tcgen05 has no fp64 kind), of the fp64 FMA pipe, and
+ * a read-only HBM stream through 1-D bulk copies (the single-target pass only reads; the usual copy figure counts
+ * read + write). */
+#define NB200_PEAK_DMMA_TFLOPS 0
+#define NB200_PEAK_DFMA_TFLOPS 1
+#define NB200_PEAK_HBM_READ_GBS 2
+NB200_API int nb200_probe_peak(nb200_ctx* ctx, int kind, double* value);
 
 /* Host-side wall clock of nb200_vgrad since the last reset, microseconds summed over `calls` calls: staging x
  * (+ enqueueing its H2D copy), enqueueing the evaluation, waiting for the stream and handing (g, f) over. */

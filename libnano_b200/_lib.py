@@ -17,6 +17,8 @@ SIGNATURES = {
     "nb200_version": (ctypes.c_char_p, []),
     "nb200_device_count": (ctypes.c_int, []),
     "nb200_init": (ctypes.c_int, [ctypes.c_int, c_void_pp]),
+    "nb200_init_multi": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), c_void_pp]),
+    "nb200_ctx_devices": (ctypes.c_int, [ctypes.c_void_p]),
     "nb200_ctx_release": (None, [ctypes.c_void_p]),
     "nb200_dataset_pin": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_i64, c_i64, c_i64, c_void_pp]),
     "nb200_dataset_synth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, c_i64, c_i64, c_i64, c_i64,
@@ -52,12 +54,17 @@ SIGNATURES = {
     "nb200_vgrad_sharded": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, c_i64, c_double_p, c_double_p]),
     "nb200_vgrad_sharded_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i64, c_i64, ctypes.c_void_p,
                                                   ctypes.c_void_p]),
+    "nb200_objective_peer_mode": (ctypes.c_int, [ctypes.c_void_p]),
+    "nb200_objective_parts": (ctypes.c_int, [ctypes.c_void_p]),
+    "nb200_objective_part": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nb200_objective_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_launches": (c_i64, [ctypes.c_void_p]),
     "nb200_objective_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "nb200_objective_last_pass_ms": (ctypes.c_double, [ctypes.c_void_p]),
     "nb200_objective_pass_stats": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(c_i64), ctypes.c_int]),
+    "nb200_objective_pass_samples": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.POINTER(c_i64)]),
+    "nb200_probe_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p]),
     "nb200_objective_host_profile": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p,
                                                     ctypes.POINTER(c_i64), ctypes.c_int]),
     "nb200_objective_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -326,9 +326,12 @@ struct solver_method_t
 class device_lbfgs_t
 {
 public:
+    // obj: the objective whose stream carries the solver state (the first part of a device group); group: the group
+    // objective when the evaluation spans several devices of this process (group.cuh), null otherwise
     device_lbfgs_t(nb200_obj* obj, const int64_t n_global, nb200_allreduce_fn allreduce, void* allreduce_user,
-                   const solver_method_t method = solver_method_t{})
+                   const solver_method_t method = solver_method_t{}, nb200_obj* group = nullptr)
         : m_obj(obj)
+        , m_group(group)
         , m_n(obj->n)
         , m_n_global(n_global)
         , m_allreduce(allreduce)
@@ -491,7 +494,11 @@ public:
         const double*         x_best = current_is_valid ? m_x : m_x0;
         const solver_point_t& best   = current_is_valid ? c : p;
         NB200_CUDA_TRY(cudaMemcpyAsync(x_host, x_best, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        NB200_CUDA_TRY(cudaStreamSynchronize(stream));
+        rc = obj_sync(m_obj);
+        if (rc != NB200_OK)
+        {
+            return rc;
+        }
         collect_timing(m_obj);
         *fx            = best.f;
         *gradient_test = best.gmax / std::max(1.0, std::fabs(best.f));
@@ -511,8 +518,7 @@ private:
         int status;
         if (m_allreduce == nullptr)
         {
-            // one launch; with connected peers the cross-rank all-reduce happens inside it (vgrad_t1.cuh)
-            status = enqueue_eval(m_obj, m_x, true, true, m_n_global, m_g, m_f, m_obj->peer_world > 1);
+            status = solver_enqueue_eval(m_obj, m_group, m_x, m_n_global, m_g, m_f);
         }
         else
         {
@@ -541,7 +547,16 @@ private:
         solver_probe_kernel<<<1, kSolverThreads, 0, m_obj->stream>>>(m_n, m_x, m_g, m_d, m_f, m_probe_dev);
         NB200_CUDA_TRY(cudaGetLastError());
         m_obj->launches += 1;
-        NB200_CUDA_TRY(cudaStreamSynchronize(m_obj->stream));
+        int status = obj_sync(m_obj);
+        if (status == NB200_OK)
+        {
+            // a fused evaluation that gave up on a peer summed stale mail: stop instead of iterating on a wrong (f, g)
+            status = peer_check(m_obj);
+        }
+        if (status != NB200_OK)
+        {
+            return status;
+        }
         collect_timing(m_obj);
         point.f     = m_probe[0];
         point.dg    = m_probe[1];
@@ -766,6 +781,7 @@ private:
     }
 
     nb200_obj*         m_obj;
+    nb200_obj*         m_group;
     int64_t            m_n;
     int64_t            m_n_global;
     nb200_allreduce_fn m_allreduce;

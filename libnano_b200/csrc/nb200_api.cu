@@ -22,6 +22,7 @@
 #include "vgrad_gen.cuh"
 #include "kernel_tables.cuh"
 #include "batch.cuh"
+#include "probe.cuh"
 
 using namespace nb200;
 
@@ -42,6 +43,9 @@ struct nb200_ctx
     size_t       arena_bytes{0};
     char*        staging{nullptr};
     size_t       staging_bytes{0};
+    // a device group (nb200_init_multi): one context per device, owned by this one; datasets pinned on it are split
+    // in contiguous row blocks over the parts and objectives on them evaluate on every device
+    std::vector<nb200_ctx*> parts;
 };
 
 struct nb200_data
@@ -56,6 +60,9 @@ struct nb200_data
     int64_t          N{0}, D{0}, T{0};
     nb200::column_stats_t inputs_stats;  // filled by nb200_dataset_scale
     nb200::column_stats_t targets_stats;
+    // a dataset on a device group: rows [row0[r], row0[r + 1]) live on parts[r] (X, Y above stay null)
+    std::vector<nb200_data*> parts;
+    std::vector<int64_t>     row0;
 };
 
 namespace
@@ -434,8 +441,25 @@ struct nb200_obj
     unsigned char*      peer_base[kT1MaxPeers] = {nullptr}; // every rank's mailbox as seen from this device
     int*                h_peer_error{nullptr};             // mapped host flag raised by the kernel on a peer timeout
     int*                d_peer_error{nullptr};
+    // how an evaluation meets its peers (vgrad_t1.cuh): 0 = the launch publishes and leaves, the STREAM waits for the
+    // peers' ready words and peer-finish folds the slots (no SM is held while waiting: evaluations of different
+    // objectives can never cross-wait); 1 = the launch itself spins on the peers' flags (one kernel, holds the GPU)
+    int                 peer_wait{0};
+    bool                peer_direct{false};                // peers live in this process (plain pointers, nothing to close)
+    int                 peer_grid{0};                      // grid the mailbox was sized for
+    unsigned long long  publish_epoch{0};                  // publish-only launches issued on d_grid_counter[1]
+    bool                peer_pending{false};               // a stream wait on the peers may be outstanding
+    unsigned long long* h_release{nullptr};                // pinned: the value a timed-out wait is released with
+    cudaStream_t        release_stream{nullptr};
 
     batch_state batch; // nb200_vgrad_batch
+
+    // an objective on a device group: one objective per device (owned), evaluated together; parts[0] talks to the host
+    std::vector<nb200_obj*>  parts;
+    bool                     group_fused{false};   // the parts publish into each other's mailboxes (distinct devices)
+    bool                     peer_passive{false};  // a part other than the first: publishes, never folds
+    double*                  group_gather{nullptr}; // two-phase groups: [parts][1 + T + T*D] on the first device
+    std::vector<cudaEvent_t> group_events;          // [parts]: x is ready (slot 0) / part r's sums are ready
 
     // state of a two-phase evaluation
     bool    partial_has_grad{false};
@@ -453,10 +477,54 @@ struct nb200_obj
     double      last_pass_ms{-1.0};
     double      pass_ms_total{0.0};
     int64_t     pass_count{0};
+    std::vector<float> pass_samples; // the passes since the last reset, one by one (bounded)
 };
 
 namespace
 {
+// cuStreamWaitValue64 through the runtime's driver entry-point query (libnb200.so does not link libcuda): the stream
+// waits until the 64-bit word at `address` is >= `value` — no SM is held while it waits
+using stream_wait_value_fn = int (*)(cudaStream_t stream, unsigned long long address, unsigned long long value,
+                                     unsigned int flags);
+stream_wait_value_fn stream_wait_value()
+{
+    static const stream_wait_value_fn fn = []() -> stream_wait_value_fn
+    {
+        void*                           entry = nullptr;
+        cudaDriverEntryPointQueryResult found = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &entry, cudaEnableDefault, &found) != cudaSuccess ||
+            found != cudaDriverEntryPointSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<stream_wait_value_fn>(entry);
+    }();
+    return fn;
+}
+
+// forget the peers: unmap their mailboxes, free this rank's (a new plan may change the grid the mailbox is sized for,
+// and flags of an earlier connection must never be mistaken for fresh mail)
+void drop_peers(nb200_obj* obj)
+{
+    for (int r = 0; r < kT1MaxPeers; ++r)
+    {
+        if (obj->peer_base[r] != nullptr && obj->peer_base[r] != obj->peer_local && !obj->peer_direct)
+        {
+            cudaIpcCloseMemHandle(obj->peer_base[r]);
+        }
+        obj->peer_base[r] = nullptr;
+    }
+    cudaFree(obj->peer_local);
+    obj->peer_local    = nullptr;
+    obj->peer_world    = 1;
+    obj->peer_rank     = 0;
+    obj->peer_epoch    = 0;
+    obj->publish_epoch = 0;
+    obj->peer_direct   = false;
+    obj->peer_grid     = 0;
+}
+
 void free_obj(nb200_obj* obj)
 {
     if (obj == nullptr)
@@ -473,15 +541,22 @@ void free_obj(nb200_obj* obj)
     cudaFree(obj->d_dL);
     cudaFree(obj->d_Wp);
     cudaFree(obj->d_grid_counter);
-    for (int r = 0; r < kT1MaxPeers; ++r)
+    for (nb200_obj* part : obj->parts)
     {
-        if (obj->peer_base[r] != nullptr && obj->peer_base[r] != obj->peer_local)
-        {
-            cudaIpcCloseMemHandle(obj->peer_base[r]);
-        }
+        free_obj(part);
     }
-    cudaFree(obj->peer_local);
+    for (cudaEvent_t event : obj->group_events)
+    {
+        cudaEventDestroy(event);
+    }
+    cudaFree(obj->group_gather);
+    drop_peers(obj);
     cudaFreeHost(obj->h_peer_error);
+    cudaFreeHost(obj->h_release);
+    if (obj->release_stream != nullptr)
+    {
+        cudaStreamDestroy(obj->release_stream);
+    }
     obj->batch.release();
     cudaFreeHost(obj->h_x);
     cudaFreeHost(obj->h_out);
@@ -516,9 +591,9 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     cudaFree(obj->d_Wp);
     obj->d_partials = obj->d_partials_gw = obj->d_dL = obj->d_Wp = nullptr;
     obj->use_t1 = false;
-    NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter, 0, sizeof(unsigned long long)));
+    NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter, 0, 2 * sizeof(unsigned long long)));
     obj->grid_epoch = 0;
-    obj->peer_world = 1; // a new plan may change the grid: peers must reconnect
+    drop_peers(obj); // a new plan may change the grid: peers must export and connect again
 
     const bool force_generic = forced_variant == -2 || env_int("NB200_FORCE_GENERIC", 0) != 0;
     if (T == 1 && !force_generic && D <= (1 << 20))
@@ -706,7 +781,7 @@ int make_objective(nb200_data* data, const int loss, const double loss_param, co
             NB200_CUDA_TRY(cudaEventCreate(&obj->ev0[i]));
             NB200_CUDA_TRY(cudaEventCreate(&obj->ev1[i]));
         }
-        NB200_CUDA_TRY(cudaMalloc(&obj->d_grid_counter, sizeof(unsigned long long)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_grid_counter, 2 * sizeof(unsigned long long))); // [grid barrier | published]
         NB200_CUDA_TRY(cudaMalloc(&obj->d_x, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_out, (n + 2) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_reduced, static_cast<size_t>(1 + data->T + data->T * data->D) * sizeof(double)));
@@ -741,6 +816,10 @@ void collect_timing(nb200_obj* obj)
             obj->last_pass_ms = ms;
             obj->pass_ms_total += ms;
             obj->pass_count += 1;
+            if (obj->pass_samples.size() < 65536)
+            {
+                obj->pass_samples.push_back(ms);
+            }
         }
     }
     obj->pass_pending = 0;
@@ -770,10 +849,19 @@ int timing_end(nb200_obj* obj)
     return NB200_OK;
 }
 
-int enqueue_finish(nb200_obj* obj, const double* x_dev, const int64_t n_global, double* gx_dev, double* fx_dev)
+// peers: fold the `peer_world` reduced vectors the ranks published into this rank's mailbox (rank order) on the way
+int enqueue_finish(nb200_obj* obj, const double* x_dev, const int64_t n_global, double* gx_dev, double* fx_dev,
+                   const double* mail = nullptr)
 {
     finish_params p{};
     p.reduced  = obj->d_reduced;
+    if (mail != nullptr)
+    {
+        p.mail        = mail;
+        p.world       = obj->peer_world;
+        p.col_stride  = obj->peer_col_stride;
+        p.reduced_out = obj->d_reduced;
+    }
     p.x        = x_dev;
     p.gx       = gx_dev;
     p.fx       = fx_dev;
@@ -812,7 +900,9 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
     if (obj->use_t1)
     {
         const t1_variant& var = kT1Variants[obj->t1.variant];
-        obj->grid_epoch += 1;
+        // the counters only advance when the launch succeeded (a failed launch must not leave the next one waiting
+        // for arrivals that never happen)
+        const unsigned long long grid_epoch = obj->grid_epoch + 1;
 
         t1_params p{};
         p.X              = data->X;
@@ -832,7 +922,7 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.loss_param     = obj->loss_param;
         p.l2_resident    = (static_cast<int64_t>(N) * (D + 1) * 8 <= (static_cast<int64_t>(data->l2_bytes) * 3) / 4) ? 1 : 0;
         p.grid_counter   = obj->d_grid_counter;
-        p.grid_target    = obj->grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
+        p.grid_target    = grid_epoch * static_cast<unsigned long long>(obj->t1.grid);
         p.reduced        = obj->d_reduced;
         p.fuse_finish    = finish ? 1 : 0;
         p.flavour        = obj->flavour;
@@ -842,19 +932,29 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         p.l1             = obj->l1;
         p.l2             = obj->l2;
         p.world          = 1;
+        p.peer_wait      = 1;
+        const bool   publish_only = peers && obj->peer_wait == 0;
+        const size_t mail_bytes   = static_cast<size_t>(2) * obj->peer_world * obj->peer_col_stride * sizeof(double);
         if (peers)
         {
-            obj->peer_epoch += 1;
+            NB200_REQUIRE(finish, "peers: a fused evaluation always runs to (f, g)");
             p.world      = obj->peer_world;
             p.rank       = obj->peer_rank;
             p.col_stride = obj->peer_col_stride;
-            p.epoch      = obj->peer_epoch;
+            p.epoch      = obj->peer_epoch + 1;
             p.peer_error = obj->d_peer_error;
-            const size_t mail_bytes = static_cast<size_t>(2) * obj->peer_world * obj->peer_col_stride * sizeof(double);
+            p.peer_wait  = obj->peer_wait;
             for (int r = 0; r < obj->peer_world; ++r)
             {
                 p.peer_mail[r] = reinterpret_cast<double*>(obj->peer_base[r]);
                 p.peer_flag[r] = reinterpret_cast<unsigned long long*>(obj->peer_base[r] + mail_bytes);
+            }
+            p.publish_counter = obj->d_grid_counter + 1;
+            p.publish_target  = (obj->publish_epoch + 1) * static_cast<unsigned long long>(obj->t1.grid);
+            if (publish_only)
+            {
+                p.fuse_finish = 0;
+                p.gx_out      = nullptr;
             }
         }
 
@@ -863,8 +963,40 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         const void* kernel = reinterpret_cast<const void*>(want_grad ? var.grad : var.value);
         NB200_CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(obj->t1.grid), dim3((var.NCW + kT1ProducerWarps) * 32),
                                                    args, static_cast<size_t>(obj->t1.smem_bytes), obj->stream));
+        obj->grid_epoch = grid_epoch;
         obj->launches += 1;
-        return timing_end(obj);
+        if (peers)
+        {
+            obj->peer_epoch += 1;
+            obj->publish_epoch += 1;
+        }
+        status = timing_end(obj);
+        if (status != NB200_OK || !publish_only || obj->peer_passive)
+        {
+            return status; // (a passive part of a device group only publishes: the first part folds and finishes)
+        }
+
+        // the stream (not an SM) waits until every peer's ready word for this evaluation is in my mailbox, then the
+        // finish kernel folds the world's slots in rank order
+        const unsigned long long parity = obj->peer_epoch & 1ULL;
+        const auto* flags = reinterpret_cast<const unsigned long long*>(obj->peer_local + mail_bytes);
+        const unsigned long long* ready = flags + 2ULL * obj->peer_world * obj->t1.grid + parity * obj->peer_world;
+        for (int q = 0; q < obj->peer_world; ++q)
+        {
+            if (q == obj->peer_rank)
+            {
+                continue; // my own slices are ordered by the stream
+            }
+            const int rc = stream_wait_value()(obj->stream, reinterpret_cast<unsigned long long>(ready + q),
+                                               obj->peer_epoch, 0u /*CU_STREAM_WAIT_VALUE_GEQ*/);
+            if (rc != 0)
+            {
+                return fail(NB200_ERR_CUDA, "peers: cuStreamWaitValue64 failed with driver error " + std::to_string(rc));
+            }
+        }
+        obj->peer_pending = true;
+        const double* mail = reinterpret_cast<const double*>(obj->peer_local) + parity * obj->peer_world * obj->peer_col_stride;
+        return enqueue_finish(obj, x_dev, n_global, want_grad ? gx_out : nullptr, fx_out, mail);
     }
 
     if (obj->use_fd)
@@ -1054,6 +1186,64 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
     return finish ? enqueue_finish(obj, x_dev, n_global, gx_out, fx_out) : NB200_OK;
 }
 
+// Wait for the objective's stream. With a stream wait on the peers outstanding the host polls under a time limit
+// (NB200_PEER_TIMEOUT_MS, default 30 s): a peer that never publishes would otherwise park the stream for ever. On
+// expiry the wait is released by writing the awaited epoch into this rank's own ready words, and the evaluation is
+// reported as failed — like the in-kernel wait's device-side time limit.
+int obj_sync(nb200_obj* obj)
+{
+    if (obj->peer_pending && obj->peer_world > 1 && obj->peer_wait == 0)
+    {
+        static const int limit_ms = std::max(1, env_int("NB200_PEER_TIMEOUT_MS", 30000));
+        const auto       start    = std::chrono::steady_clock::now();
+        for (int spins = 0;; ++spins)
+        {
+            const cudaError_t state = cudaStreamQuery(obj->stream);
+            if (state == cudaSuccess)
+            {
+                break;
+            }
+            if (state != cudaErrorNotReady)
+            {
+                NB200_CUDA_TRY(state);
+            }
+            if ((spins & 1023) == 1023 &&
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start).count() > limit_ms)
+            {
+                const size_t mail_bytes = static_cast<size_t>(2) * obj->peer_world * obj->peer_col_stride * sizeof(double);
+                auto* flags = reinterpret_cast<unsigned long long*>(obj->peer_local + mail_bytes);
+                unsigned long long* ready = flags + 2ULL * obj->peer_world * obj->t1.grid;
+                for (int i = 0; i < 2 * obj->peer_world; ++i)
+                {
+                    obj->h_release[i] = obj->peer_epoch;
+                }
+                NB200_CUDA_TRY(cudaMemcpyAsync(ready, obj->h_release, 2 * obj->peer_world * sizeof(unsigned long long),
+                                               cudaMemcpyHostToDevice, obj->release_stream));
+                NB200_CUDA_TRY(cudaStreamSynchronize(obj->release_stream));
+                NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+                *obj->h_peer_error = 1;
+                break;
+            }
+        }
+        obj->peer_pending = false;
+        return NB200_OK;
+    }
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    obj->peer_pending = false;
+    return NB200_OK;
+}
+
+// after a synchronisation: did an evaluation give up on a peer? (its sums are then stale: never hand them out)
+int peer_check(nb200_obj* obj)
+{
+    if (obj->h_peer_error != nullptr && *obj->h_peer_error != 0)
+    {
+        *obj->h_peer_error = 0;
+        return fail(NB200_ERR_CUDA, "peers: a rank did not reach the all-reduce within the time limit");
+    }
+    return NB200_OK;
+}
+
 int upload_x(nb200_obj* obj, const double* x, const int64_t n)
 {
     NB200_REQUIRE(n == obj->n, "function: invalid input size, expecting (" + std::to_string(obj->n) + ",), got (" +
@@ -1075,7 +1265,15 @@ double* result_base(nb200_obj* obj)
 int collect_result(nb200_obj* obj, double* gx, double* fx)
 {
     const size_t n = static_cast<size_t>(obj->n);
-    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    int          status = obj_sync(obj);
+    if (status == NB200_OK)
+    {
+        status = peer_check(obj);
+    }
+    if (status != NB200_OK)
+    {
+        return status;
+    }
     collect_timing(obj);
     if (gx != nullptr)
     {
@@ -1086,6 +1284,143 @@ int collect_result(nb200_obj* obj, double* gx, double* fx)
 }
 } // namespace
 
+#include "group.cuh"
+
+namespace
+{
+int peer_allocate(nb200_obj* obj, int world);
+int peer_choose_mode(nb200_obj* obj, int world);
+
+// Wire the parts of a group objective: fused over peer memory when every part runs the single-target kernel on its own
+// device with the same grid and every pair of devices has a peer path (NB200_GROUP_FUSED=0 keeps the two-phase path);
+// otherwise the sums travel by peer copies. Called again after a change of plan.
+int group_connect(nb200_obj* group)
+{
+    const int world = static_cast<int>(group->parts.size());
+    group->group_fused = false;
+    for (nb200_obj* part : group->parts)
+    {
+        drop_peers(part);
+        part->peer_passive = false;
+    }
+    bool fused = world >= 2 && env_int("NB200_GROUP_FUSED", 1) != 0;
+    for (int i = 0; i < world && fused; ++i)
+    {
+        const nb200_obj* a = group->parts[static_cast<size_t>(i)];
+        fused = a->use_t1 && a->t1.grid == group->parts[0]->t1.grid;
+        for (int j = 0; j < world && fused; ++j)
+        {
+            const nb200_obj* b = group->parts[static_cast<size_t>(j)];
+            int can = 0;
+            fused = i == j || (a->device != b->device &&
+                               cudaDeviceCanAccessPeer(&can, a->device, b->device) == cudaSuccess && can != 0);
+        }
+    }
+    cudaGetLastError();
+    if (!fused)
+    {
+        return NB200_OK;
+    }
+    for (nb200_obj* part : group->parts)
+    {
+        NB200_CUDA_TRY(cudaSetDevice(part->device));
+        const int status = peer_allocate(part, world);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+    }
+    NB200_CUDA_TRY(cudaSetDevice(group->parts[0]->device));
+    int status = peer_choose_mode(group->parts[0], world);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
+    for (int r = 0; r < world; ++r)
+    {
+        nb200_obj* part = group->parts[static_cast<size_t>(r)];
+        for (int q = 0; q < world; ++q)
+        {
+            part->peer_base[q] = group->parts[static_cast<size_t>(q)]->peer_local; // same process: plain pointers
+        }
+        part->peer_direct  = true;
+        part->peer_world   = world;
+        part->peer_rank    = r;
+        part->peer_epoch   = 0;
+        part->peer_wait    = group->parts[0]->peer_wait;
+        part->peer_passive = r > 0;
+    }
+    group->group_fused = true;
+    return NB200_OK;
+}
+
+int make_group_objective(nb200_data* data, const int loss, const double loss_param, const int flavour, const double l1,
+                         const double l2, const double* fixed_bias, const int variant, nb200_obj** out_obj)
+{
+    NB200_REQUIRE(out_obj != nullptr, "objective: null argument");
+    auto* group = new (std::nothrow) nb200_obj{};
+    NB200_REQUIRE(group != nullptr, "objective: out of host memory");
+    nb200_dataset_retain(data);
+    group->data       = data;
+    group->device     = data->device;
+    group->loss       = loss;
+    group->loss_param = loss_param;
+    group->flavour    = flavour;
+    group->l1         = l1;
+    group->l2         = l2;
+    const auto build = [&]() -> int
+    {
+        for (nb200_data* part_data : data->parts)
+        {
+            nb200_obj* part   = nullptr;
+            const int  status = make_objective(part_data, loss, loss_param, flavour, l1, l2, fixed_bias, variant, &part);
+            if (status != NB200_OK)
+            {
+                return status;
+            }
+            group->parts.push_back(part);
+            cudaEvent_t event = nullptr;
+            NB200_CUDA_TRY(cudaSetDevice(part->device));
+            NB200_CUDA_TRY(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+            group->group_events.push_back(event);
+        }
+        group->n      = group->parts[0]->n;
+        group->stream = group->parts[0]->stream;
+        if (fixed_bias != nullptr)
+        {
+            group->fixed_bias.assign(fixed_bias, fixed_bias + data->T);
+        }
+        NB200_CUDA_TRY(cudaSetDevice(group->device));
+        NB200_CUDA_TRY(cudaMalloc(&group->group_gather, data->parts.size() *
+                                                            static_cast<size_t>(1 + data->T + data->T * data->D) *
+                                                            sizeof(double)));
+        return group_connect(group);
+    };
+    const int status = build();
+    if (status != NB200_OK)
+    {
+        const std::string message = g_last_error;
+        group->stream = nullptr;
+        free_obj(group);
+        g_last_error = message;
+        return status;
+    }
+    *out_obj = group;
+    return NB200_OK;
+}
+
+// entry points that only make sense for one device (the cross-process protocol, tuning knobs)
+#define NB200_NOT_ON_A_GROUP(obj, what)                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if ((obj) != nullptr && !(obj)->parts.empty())                                                                 \
+        {                                                                                                              \
+            return ::nb200::fail(3 /*NB200_ERR_UNSUPPORTED*/,                                                           \
+                                 std::string(what) + ": not available on a device group (it evaluates on all of its "  \
+                                                     "devices by itself)");                                            \
+        }                                                                                                              \
+    } while (0)
+} // namespace
 #include "lbfgs.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1149,8 +1484,64 @@ int nb200_init(const int device, nb200_ctx** out_ctx)
     return NB200_OK;
 }
 
+int nb200_init_multi(const int ndev, const int* devices, nb200_ctx** out_ctx)
+{
+    NB200_REQUIRE(out_ctx != nullptr && devices != nullptr, "init: null argument");
+    NB200_REQUIRE(ndev >= 1 && ndev <= kT1MaxPeers, "init: a device group holds 1 to 8 devices");
+    auto* group = new (std::nothrow) nb200_ctx{};
+    NB200_REQUIRE(group != nullptr, "init: out of host memory");
+    for (int i = 0; i < ndev; ++i)
+    {
+        nb200_ctx* part   = nullptr;
+        const int  status = nb200_init(devices[i], &part);
+        if (status != NB200_OK)
+        {
+            const std::string message = g_last_error;
+            nb200_ctx_release(group);
+            g_last_error = message;
+            return status;
+        }
+        group->parts.push_back(part);
+    }
+    group->device     = group->parts[0]->device;
+    group->sm_count   = group->parts[0]->sm_count;
+    group->smem_optin = group->parts[0]->smem_optin;
+    group->l2_bytes   = group->parts[0]->l2_bytes;
+    // peer access both ways between distinct devices (the fused evaluation stores into the peers' mailboxes and the
+    // two-phase one copies sums between devices); devices without a peer path still work through staged copies
+    for (int i = 0; i < ndev; ++i)
+    {
+        for (int j = 0; j < ndev; ++j)
+        {
+            int can = 0;
+            if (devices[i] != devices[j] && cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can != 0)
+            {
+                cudaSetDevice(devices[i]);
+                cudaDeviceEnablePeerAccess(devices[j], 0); // cudaErrorPeerAccessAlreadyEnabled is fine
+            }
+            cudaGetLastError();
+        }
+    }
+    *out_ctx = group;
+    return NB200_OK;
+}
+
+int nb200_ctx_devices(const nb200_ctx* ctx)
+{
+    return ctx == nullptr ? 0 : (ctx->parts.empty() ? 1 : static_cast<int>(ctx->parts.size()));
+}
+
 void nb200_ctx_release(nb200_ctx* ctx)
 {
+    if (ctx != nullptr && !ctx->parts.empty())
+    {
+        for (nb200_ctx* part : ctx->parts)
+        {
+            nb200_ctx_release(part);
+        }
+        delete ctx;
+        return;
+    }
     if (ctx != nullptr)
     {
         cudaSetDevice(ctx->device);
@@ -1204,10 +1595,52 @@ static int alloc_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const
     return NB200_OK;
 }
 
+// a dataset on a device group: `make(part context, part index, first row, rows, out)` builds each part
+extern "C++" template <typename tmake>
+int group_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const int64_t T, nb200_data** out_data,
+                         const tmake& make)
+{
+    NB200_REQUIRE(out_data != nullptr, "dataset: null argument");
+    const int world = static_cast<int>(ctx->parts.size());
+    NB200_REQUIRE(N >= world && D > 0 && T > 0, "dataset: every device of the group needs at least one sample");
+    auto* data = new (std::nothrow) nb200_data{};
+    NB200_REQUIRE(data != nullptr, "dataset: out of host memory");
+    data->device     = ctx->device;
+    data->sm_count   = ctx->sm_count;
+    data->smem_optin = ctx->smem_optin;
+    data->l2_bytes   = ctx->l2_bytes;
+    data->N          = N;
+    data->D          = D;
+    data->T          = T;
+    group_split_rows(N, world, data->row0);
+    for (int r = 0; r < world; ++r)
+    {
+        nb200_data* part   = nullptr;
+        const int   status = make(ctx->parts[static_cast<size_t>(r)], r, data->row0[static_cast<size_t>(r)],
+                                  data->row0[static_cast<size_t>(r) + 1] - data->row0[static_cast<size_t>(r)], &part);
+        if (status != NB200_OK)
+        {
+            const std::string message = g_last_error;
+            nb200_dataset_release(data);
+            g_last_error = message;
+            return status;
+        }
+        data->parts.push_back(part);
+    }
+    *out_data = data;
+    return NB200_OK;
+}
+
 int nb200_dataset_pin(nb200_ctx* ctx, const double* X, const double* Y, const int64_t N, const int64_t D,
                       const int64_t T, nb200_data** out_data)
 {
     NB200_REQUIRE(X != nullptr && Y != nullptr, "dataset: null inputs or targets");
+    if (ctx != nullptr && !ctx->parts.empty())
+    {
+        return group_dataset(ctx, N, D, T, out_data,
+                             [&](nb200_ctx* part, int, const int64_t row0, const int64_t rows, nb200_data** out)
+                             { return nb200_dataset_pin(part, X + row0 * D, Y + row0 * T, rows, D, T, out); });
+    }
     nb200_data* data   = nullptr;
     const int   status = alloc_dataset(ctx, N, D, T, &data);
     if (status != NB200_OK)
@@ -1235,6 +1668,13 @@ int nb200_dataset_synth(nb200_ctx* ctx, const uint64_t seed, const int synth_kin
     NB200_REQUIRE(synth_kind == NB200_SYNTH_MULTICLASS ? T >= 2 : T == 1,
                   "dataset: classification/regression are single-target, multiclass needs T >= 2");
     NB200_REQUIRE(row_offset >= 0, "dataset: negative row offset");
+    if (ctx != nullptr && !ctx->parts.empty())
+    {
+        return group_dataset(ctx, N, D, T, out_data,
+                             [&](nb200_ctx* part, int, const int64_t row0, const int64_t rows, nb200_data** out) {
+                                 return nb200_dataset_synth(part, seed, synth_kind, rows, D, T, row_offset + row0, noise, out);
+                             });
+    }
     nb200_data* data   = nullptr;
     int         status = alloc_dataset(ctx, N, D, T, &data);
     if (status != NB200_OK)
@@ -1278,6 +1718,24 @@ int nb200_dataset_read(const nb200_data* data, const int64_t row0, const int64_t
 {
     NB200_REQUIRE(data != nullptr, "dataset: null argument");
     NB200_REQUIRE(row0 >= 0 && rows >= 0 && row0 + rows <= data->N, "dataset: row range out of bounds");
+    if (!data->parts.empty())
+    {
+        for (size_t r = 0; r < data->parts.size(); ++r)
+        {
+            const int64_t lo = std::max(row0, data->row0[r]), hi = std::min(row0 + rows, data->row0[r + 1]);
+            if (lo < hi)
+            {
+                const int status = nb200_dataset_read(data->parts[r], lo - data->row0[r], hi - lo,
+                                                      X != nullptr ? X + (lo - row0) * data->D : nullptr,
+                                                      Y != nullptr ? Y + (lo - row0) * data->T : nullptr);
+                if (status != NB200_OK)
+                {
+                    return status;
+                }
+            }
+        }
+        return NB200_OK;
+    }
     NB200_CUDA_TRY(cudaSetDevice(data->device));
     if (X != nullptr && rows > 0)
     {
@@ -1319,6 +1777,10 @@ void nb200_dataset_release(nb200_data* data)
 {
     if (data != nullptr && data->refs.fetch_sub(1, std::memory_order_acq_rel) == 1)
     {
+        for (nb200_data* part : data->parts)
+        {
+            nb200_dataset_release(part);
+        }
         cudaSetDevice(data->device);
         cudaFree(data->X);
         cudaFree(data->Y);
@@ -1326,8 +1788,8 @@ void nb200_dataset_release(nb200_data* data)
     }
 }
 
-static int device_column_stats(nb200_data* data, const double* values, const int64_t C, const unsigned char* enable,
-                               column_stats_t& stats)
+// raw [5][C]: count, sum, sum of squares, min, max over the finite values of every column
+static int device_column_raw(nb200_data* data, const double* values, const int64_t C, std::vector<double>& raw)
 {
     const int64_t N      = data->N;
     const int     chunks = static_cast<int>((N + kStatsRowsPerBlock - 1) / kStatsRowsPerBlock);
@@ -1341,15 +1803,58 @@ static int device_column_stats(nb200_data* data, const double* values, const int
         NB200_CUDA_TRY(cudaGetLastError());
         column_stats_fold_kernel<<<static_cast<unsigned>((C + 255) / 256), 256>>>(partial, chunks, C, folded);
         NB200_CUDA_TRY(cudaGetLastError());
-        std::vector<double> raw(static_cast<size_t>(5 * C));
+        raw.assign(static_cast<size_t>(5 * C), 0.0);
         NB200_CUDA_TRY(cudaMemcpy(raw.data(), folded, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        finish_column_stats(raw, C, enable, stats);
         return NB200_OK;
     };
     const int status = run();
     cudaFree(partial);
     cudaFree(folded);
     return status;
+}
+
+static int device_column_stats(nb200_data* data, const double* values, const int64_t C, const unsigned char* enable,
+                               column_stats_t& stats)
+{
+    std::vector<double> raw;
+    const int           status = device_column_raw(data, values, C, raw);
+    if (status == NB200_OK)
+    {
+        finish_column_stats(raw, C, enable, stats);
+    }
+    return status;
+}
+
+// statistics over ALL rows of a dataset on a device group: per-device sums folded in device order
+static int group_column_stats(nb200_data* data, const bool inputs, const unsigned char* enable, column_stats_t& stats)
+{
+    const int64_t       C = inputs ? data->D : data->T;
+    std::vector<double> total(static_cast<size_t>(5 * C), 0.0), raw;
+    for (int64_t c = 0; c < C; ++c)
+    {
+        total[static_cast<size_t>(3 * C + c)] = INFINITY;
+        total[static_cast<size_t>(4 * C + c)] = -INFINITY;
+    }
+    for (nb200_data* part : data->parts)
+    {
+        NB200_CUDA_TRY(cudaSetDevice(part->device));
+        const int status = device_column_raw(part, inputs ? part->X : part->Y, C, raw);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        for (int64_t c = 0; c < C; ++c)
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                total[static_cast<size_t>(k * C + c)] += raw[static_cast<size_t>(k * C + c)];
+            }
+            total[static_cast<size_t>(3 * C + c)] = std::fmin(total[static_cast<size_t>(3 * C + c)], raw[static_cast<size_t>(3 * C + c)]);
+            total[static_cast<size_t>(4 * C + c)] = std::fmax(total[static_cast<size_t>(4 * C + c)], raw[static_cast<size_t>(4 * C + c)]);
+        }
+    }
+    finish_column_stats(total, C, enable, stats);
+    return NB200_OK;
 }
 
 static int device_column_scale(double* values, const int64_t N, const int64_t C, const column_stats_t& stats,
@@ -1389,6 +1894,34 @@ int nb200_dataset_scale(nb200_data* data, const int inputs_scaling, const int ta
     NB200_REQUIRE(inputs_scaling >= 0 && inputs_scaling <= 3 && targets_scaling >= 0 && targets_scaling <= 3,
                   "dataset: unhandled scaling type");
     NB200_REQUIRE(data->inputs_stats.empty(), "dataset: already scaled");
+    if (!data->parts.empty())
+    {
+        int status = group_column_stats(data, true, enable_inputs, data->inputs_stats);
+        if (status == NB200_OK)
+        {
+            status = group_column_stats(data, false, enable_targets, data->targets_stats);
+        }
+        for (size_t r = 0; r < data->parts.size() && status == NB200_OK; ++r)
+        {
+            nb200_data* part = data->parts[r];
+            NB200_CUDA_TRY(cudaSetDevice(part->device));
+            status = device_column_scale(part->X, part->N, part->D, data->inputs_stats, inputs_scaling, part->sm_count);
+            if (status == NB200_OK)
+            {
+                status = device_column_scale(part->Y, part->N, part->T, data->targets_stats, targets_scaling, part->sm_count);
+            }
+            part->inputs_stats          = data->inputs_stats;
+            part->targets_stats         = data->targets_stats;
+            part->inputs_stats.scaling  = inputs_scaling;
+            part->targets_stats.scaling = targets_scaling;
+        }
+        if (status == NB200_OK)
+        {
+            data->inputs_stats.scaling  = inputs_scaling;
+            data->targets_stats.scaling = targets_scaling;
+        }
+        return status;
+    }
     NB200_CUDA_TRY(cudaSetDevice(data->device));
     int status = device_column_stats(data, data->X, data->D, enable_inputs, data->inputs_stats);
     if (status == NB200_OK)
@@ -1462,12 +1995,29 @@ int nb200_upscale(const nb200_data* data, double* W, double* b)
 int nb200_objective_create(nb200_data* data, const int loss, const double loss_param, const int flavour,
                            const double l1, const double l2, const double* fixed_bias, nb200_obj** out_obj)
 {
+    if (data != nullptr && !data->parts.empty())
+    {
+        return make_group_objective(data, loss, loss_param, flavour, l1, l2, fixed_bias, -1, out_obj);
+    }
     return make_objective(data, loss, loss_param, flavour, l1, l2, fixed_bias, -1, out_obj);
 }
 
 int nb200_objective_clone(const nb200_obj* obj, nb200_obj** out_obj)
 {
     NB200_REQUIRE(obj != nullptr && out_obj != nullptr, "objective: null argument");
+    if (!obj->parts.empty())
+    {
+        const nb200_obj* first = obj->parts[0];
+        const int status = make_group_objective(
+            obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
+            obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
+            first->use_t1 ? first->t1.variant : (first->use_fd ? -5 : (first->use_ft ? -6 : (first->use_mt ? -4 : -2))), out_obj);
+        for (size_t r = 0; status == NB200_OK && r < obj->parts.size(); ++r)
+        {
+            (*out_obj)->parts[r]->timing = obj->parts[r]->timing;
+        }
+        return status;
+    }
     const int status = make_objective(obj->data, obj->loss, obj->loss_param, obj->flavour, obj->l1, obj->l2,
                                       obj->fixed_bias.empty() ? nullptr : obj->fixed_bias.data(),
                                       obj->use_t1 ? obj->t1.variant : (obj->use_fd ? -5 : (obj->use_ft ? -6 : (obj->use_mt ? -4 : -2))), out_obj);
@@ -1492,19 +2042,24 @@ int nb200_vgrad(nb200_obj* obj, const double* x, const int64_t n, double* gx, do
 {
     NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    // (a device group stages x and collects (g, f) through its first part; every part evaluates)
+    nb200_obj* const host = obj->parts.empty() ? obj : obj->parts[0];
     const auto t0     = std::chrono::steady_clock::now();
-    int        status = upload_x(obj, x, n);
+    int        status = upload_x(host, x, n);
     const auto t1     = std::chrono::steady_clock::now();
     if (status == NB200_OK)
     {
-        double* out = result_base(obj);
-        status      = enqueue_eval(obj, obj->d_x, gx != nullptr, true, obj->data->N, gx != nullptr ? out : nullptr,
-                                   out + obj->n);
+        double* out = result_base(host);
+        status      = obj->parts.empty()
+                          ? enqueue_eval(obj, obj->d_x, gx != nullptr, true, obj->data->N, gx != nullptr ? out : nullptr,
+                                         out + obj->n)
+                          : group_enqueue_eval(obj, host->d_x, gx != nullptr, obj->data->N, gx != nullptr ? out : nullptr,
+                                               out + obj->n);
     }
     const auto t2 = std::chrono::steady_clock::now();
     if (status == NB200_OK)
     {
-        status = collect_result(obj, gx, fx);
+        status = collect_result(host, gx, fx);
     }
     const auto t3 = std::chrono::steady_clock::now();
     obj->host_us[0] += std::chrono::duration<double, std::micro>(t1 - t0).count();
@@ -1537,21 +2092,42 @@ int nb200_vgrad_device(nb200_obj* obj, const double* x_dev, const int64_t n, dou
     NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
     NB200_REQUIRE(n == obj->n, "function: invalid input size");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    if (!obj->parts.empty())
+    {
+        return group_enqueue_eval(obj, x_dev, gx_dev != nullptr, obj->data->N, gx_dev, fx_dev); // x on the first device
+    }
     return enqueue_eval(obj, x_dev, gx_dev != nullptr, true, obj->data->N, gx_dev, fx_dev);
 }
 
 int nb200_objective_sync(nb200_obj* obj)
 {
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    if (!obj->parts.empty())
+    {
+        for (size_t r = obj->parts.size(); r-- > 0;)
+        {
+            const int status = nb200_objective_sync(obj->parts[r]);
+            if (status != NB200_OK)
+            {
+                return status;
+            }
+        }
+        return NB200_OK;
+    }
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    const int status = obj_sync(obj);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
     collect_timing(obj);
-    return NB200_OK;
+    return peer_check(obj); // nb200_vgrad_sharded_device is checked here
 }
 
 int nb200_vgrad_partial(nb200_obj* obj, const double* x, const int64_t n, const int want_grad,
                         double** out_partial_dev, int64_t* out_partial_len)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_partial");
     NB200_REQUIRE(obj != nullptr && x != nullptr && out_partial_dev != nullptr && out_partial_len != nullptr,
                   "function: null argument");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
@@ -1571,6 +2147,7 @@ int nb200_vgrad_partial(nb200_obj* obj, const double* x, const int64_t n, const 
 
 int nb200_vgrad_finish(nb200_obj* obj, const int64_t n_global, double* gx, double* fx)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_finish");
     NB200_REQUIRE(obj != nullptr && fx != nullptr, "function: null argument");
     NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
     NB200_REQUIRE(gx == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
@@ -1587,6 +2164,7 @@ int nb200_vgrad_finish(nb200_obj* obj, const int64_t n_global, double* gx, doubl
 int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, const int64_t n, const int want_grad,
                                double** out_partial_dev, int64_t* out_partial_len)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_partial_device");
     NB200_REQUIRE(obj != nullptr && x_dev != nullptr && out_partial_dev != nullptr && out_partial_len != nullptr,
                   "function: null argument");
     NB200_REQUIRE(n == obj->n, "function: invalid input size");
@@ -1604,6 +2182,7 @@ int nb200_vgrad_partial_device(nb200_obj* obj, const double* x_dev, const int64_
 int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, const int64_t n_global, double* gx_dev,
                               double* fx_dev)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_finish_device");
     NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
     NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
     NB200_REQUIRE(gx_dev == nullptr || obj->partial_has_grad, "function: the gradient was not requested in phase 1");
@@ -1611,23 +2190,77 @@ int nb200_vgrad_finish_device(nb200_obj* obj, const double* x_dev, const int64_t
     return enqueue_finish(obj, x_dev, n_global, gx_dev, fx_dev);
 }
 
-int nb200_objective_peer_export(nb200_obj* obj, const int world, void* handle_out, int64_t* grid_out)
+// this rank's mailbox: mail [2 (parity)][world][col_stride] doubles, per-CTA flags [2][world][grid] and the ready words
+// [2][world] of the publish-only mode (64-bit each), zeroed
+} // extern "C"
+namespace
 {
-    NB200_REQUIRE(obj != nullptr && handle_out != nullptr && grid_out != nullptr, "peers: null argument");
+int peer_allocate(nb200_obj* obj, const int world)
+{
     NB200_REQUIRE(world >= 2 && world <= kT1MaxPeers, "peers: the world size must be in [2, 8]");
     NB200_REQUIRE(obj->use_t1, "peers: the fused all-reduce exists for the single-target kernel only");
     NB200_REQUIRE(obj->peer_local == nullptr, "peers: already exported");
-    NB200_CUDA_TRY(cudaSetDevice(obj->device));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
     obj->peer_col_stride = static_cast<int>(round_up(obj->data->D + 2, 2));
-    const size_t bytes = (static_cast<size_t>(2) * world * obj->peer_col_stride +
-                          static_cast<size_t>(2) * world * obj->t1.grid) * sizeof(double);
+    obj->peer_grid       = obj->t1.grid;
+    const size_t bytes   = (static_cast<size_t>(2) * world * obj->peer_col_stride +
+                          static_cast<size_t>(2) * world * obj->t1.grid + static_cast<size_t>(2) * world) * sizeof(double);
     NB200_CUDA_TRY(cudaMalloc(&obj->peer_local, bytes));
     NB200_CUDA_TRY(cudaMemset(obj->peer_local, 0, bytes));
-    NB200_CUDA_TRY(cudaHostAlloc(&obj->h_peer_error, sizeof(int), cudaHostAllocMapped));
+    if (obj->h_peer_error == nullptr)
+    {
+        NB200_CUDA_TRY(cudaHostAlloc(&obj->h_peer_error, sizeof(int), cudaHostAllocMapped));
+        NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->d_peer_error, obj->h_peer_error, 0));
+        NB200_CUDA_TRY(cudaMallocHost(&obj->h_release, 2 * kT1MaxPeers * sizeof(unsigned long long)));
+        NB200_CUDA_TRY(cudaStreamCreateWithFlags(&obj->release_stream, cudaStreamNonBlocking));
+    }
     *obj->h_peer_error = 0;
-    NB200_CUDA_TRY(cudaHostGetDevicePointer(&obj->d_peer_error, obj->h_peer_error, 0));
+    // the publish counter restarts with the mailbox
+    NB200_CUDA_TRY(cudaMemset(obj->d_grid_counter + 1, 0, sizeof(unsigned long long)));
+    obj->publish_epoch = 0;
     NB200_CUDA_TRY(cudaDeviceSynchronize());
+    return NB200_OK;
+}
+
+// Publish-only evaluations need the stream to wait on a word in HBM (cuStreamWaitValue64). Probe it once on this
+// objective's own mailbox: a wait that is already satisfied must fall through. NB200_PEER_WAIT=1 forces the
+// in-kernel wait, =0 insists on the stream wait.
+int peer_choose_mode(nb200_obj* obj, const int world)
+{
+    const int forced = env_int("NB200_PEER_WAIT", -1);
+    obj->peer_wait   = 1;
+    if (forced == 1)
+    {
+        return NB200_OK;
+    }
+    bool usable = stream_wait_value() != nullptr;
+    if (usable)
+    {
+        const size_t mail_bytes = static_cast<size_t>(2) * world * obj->peer_col_stride * sizeof(double);
+        auto* flags = reinterpret_cast<unsigned long long*>(obj->peer_local + mail_bytes);
+        // (the word probed is a ready word of parity 0 that no peer has written yet: it holds 0)
+        usable = stream_wait_value()(obj->stream, reinterpret_cast<unsigned long long>(flags + 2ULL * world * obj->t1.grid),
+                                     0ULL, 0u) == 0 &&
+                 cudaStreamSynchronize(obj->stream) == cudaSuccess;
+        cudaGetLastError();
+    }
+    NB200_REQUIRE(usable || forced != 0, "peers: NB200_PEER_WAIT=0 but cuStreamWaitValue64 is not usable on this device");
+    obj->peer_wait = usable ? 0 : 1;
+    return NB200_OK;
+}
+} // namespace
+extern "C" {
+
+int nb200_objective_peer_export(nb200_obj* obj, const int world, void* handle_out, int64_t* grid_out)
+{
+    NB200_NOT_ON_A_GROUP(obj, "nb200_objective_peer_export");
+    NB200_REQUIRE(obj != nullptr && handle_out != nullptr && grid_out != nullptr, "peers: null argument");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+    const int status = peer_allocate(obj, world);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
     cudaIpcMemHandle_t handle;
     NB200_CUDA_TRY(cudaIpcGetMemHandle(&handle, obj->peer_local));
     std::memcpy(handle_out, &handle, sizeof(handle));
@@ -1637,8 +2270,11 @@ int nb200_objective_peer_export(nb200_obj* obj, const int world, void* handle_ou
 
 int nb200_objective_peer_connect(nb200_obj* obj, const int rank, const int world, const void* handles)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_objective_peer_connect");
     NB200_REQUIRE(obj != nullptr && handles != nullptr, "peers: null argument");
     NB200_REQUIRE(obj->peer_local != nullptr, "peers: export first");
+    NB200_REQUIRE(obj->peer_world == 1, "peers: already connected (a new plan drops the connection)");
+    NB200_REQUIRE(obj->use_t1 && obj->peer_grid == obj->t1.grid, "peers: the launch plan changed since the export");
     NB200_REQUIRE(world >= 2 && world <= kT1MaxPeers && rank >= 0 && rank < world, "peers: invalid rank / world");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     for (int r = 0; r < world; ++r)
@@ -1655,10 +2291,20 @@ int nb200_objective_peer_connect(nb200_obj* obj, const int rank, const int world
         NB200_CUDA_TRY(cudaIpcOpenMemHandle(&mapped, handle, cudaIpcMemLazyEnablePeerAccess));
         obj->peer_base[r] = static_cast<unsigned char*>(mapped);
     }
+    const int status = peer_choose_mode(obj, world);
+    if (status != NB200_OK)
+    {
+        return status;
+    }
     obj->peer_world = world;
     obj->peer_rank  = rank;
     obj->peer_epoch = 0;
     return NB200_OK;
+}
+
+int nb200_objective_peer_mode(const nb200_obj* obj)
+{
+    return (obj == nullptr || obj->peer_world <= 1) ? -1 : obj->peer_wait;
 }
 
 static int check_peers(nb200_obj* obj)
@@ -1669,6 +2315,7 @@ static int check_peers(nb200_obj* obj)
 
 int nb200_vgrad_sharded(nb200_obj* obj, const double* x, const int64_t n, const int64_t n_global, double* gx, double* fx)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_sharded");
     NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
     NB200_REQUIRE(n_global > 0, "function: the global sample count must be positive");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
@@ -1685,12 +2332,7 @@ int nb200_vgrad_sharded(nb200_obj* obj, const double* x, const int64_t n, const 
     }
     if (status == NB200_OK)
     {
-        status = collect_result(obj, gx, fx);
-    }
-    if (status == NB200_OK && *obj->h_peer_error != 0)
-    {
-        *obj->h_peer_error = 0;
-        return fail(NB200_ERR_CUDA, "peers: a rank did not reach the all-reduce within the time limit");
+        status = collect_result(obj, gx, fx); // also reports a peer that never showed up
     }
     return status;
 }
@@ -1698,6 +2340,7 @@ int nb200_vgrad_sharded(nb200_obj* obj, const double* x, const int64_t n, const 
 int nb200_vgrad_sharded_device(nb200_obj* obj, const double* x_dev, const int64_t n, const int64_t n_global,
                                double* gx_dev, double* fx_dev)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_sharded_device");
     NB200_REQUIRE(obj != nullptr && x_dev != nullptr && fx_dev != nullptr, "function: null argument");
     NB200_REQUIRE(n == obj->n && n_global > 0, "function: invalid sizes");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
@@ -1712,6 +2355,7 @@ void* nb200_objective_stream(const nb200_obj* obj)
 
 int nb200_objective_set_stream(nb200_obj* obj, void* stream, const int use_own)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_objective_set_stream");
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
@@ -1723,13 +2367,36 @@ int nb200_objective_set_stream(nb200_obj* obj, void* stream, const int use_own)
 
 int64_t nb200_objective_launches(const nb200_obj* obj)
 {
-    return obj != nullptr ? obj->launches : 0;
+    int64_t total = obj != nullptr ? obj->launches : 0;
+    for (size_t r = 0; obj != nullptr && r < obj->parts.size(); ++r)
+    {
+        total += obj->parts[r]->launches;
+    }
+    return total;
+}
+
+int nb200_objective_parts(const nb200_obj* obj)
+{
+    return obj == nullptr ? 0 : (obj->parts.empty() ? 1 : static_cast<int>(obj->parts.size()));
+}
+
+nb200_obj* nb200_objective_part(nb200_obj* obj, const int index)
+{
+    if (obj == nullptr || index < 0 || index >= nb200_objective_parts(obj))
+    {
+        return nullptr;
+    }
+    return obj->parts.empty() ? obj : obj->parts[static_cast<size_t>(index)];
 }
 
 int nb200_objective_enable_timing(nb200_obj* obj, const int enabled)
 {
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
     obj->timing = enabled != 0;
+    for (nb200_obj* part : obj->parts)
+    {
+        part->timing = enabled != 0;
+    }
     return NB200_OK;
 }
 
@@ -1738,6 +2405,15 @@ double nb200_objective_last_pass_ms(nb200_obj* obj)
     if (obj == nullptr)
     {
         return -1.0;
+    }
+    if (!obj->parts.empty())
+    {
+        double slowest = -1.0; // the evaluation is as long as its slowest device
+        for (nb200_obj* part : obj->parts)
+        {
+            slowest = std::max(slowest, nb200_objective_last_pass_ms(part));
+        }
+        return slowest;
     }
     if (obj->pass_pending > 0)
     {
@@ -1754,6 +2430,35 @@ double nb200_objective_last_pass_ms(nb200_obj* obj)
 int nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count, const int reset)
 {
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    if (!obj->parts.empty())
+    {
+        // the device with the largest total: the critical path of the group's evaluations (per-device figures through
+        // nb200_objective_part)
+        double  worst = -1.0, part_ms = 0.0;
+        int64_t worst_count = 0, part_count = 0;
+        for (nb200_obj* part : obj->parts)
+        {
+            const int status = nb200_objective_pass_stats(part, &part_ms, &part_count, reset);
+            if (status != NB200_OK)
+            {
+                return status;
+            }
+            if (part_ms > worst)
+            {
+                worst       = part_ms;
+                worst_count = part_count;
+            }
+        }
+        if (total_ms != nullptr)
+        {
+            *total_ms = worst;
+        }
+        if (count != nullptr)
+        {
+            *count = worst_count;
+        }
+        return NB200_OK;
+    }
     if (total_ms != nullptr)
     {
         *total_ms = obj->pass_ms_total;
@@ -1766,13 +2471,110 @@ int nb200_objective_pass_stats(nb200_obj* obj, double* total_ms, int64_t* count,
     {
         obj->pass_ms_total = 0.0;
         obj->pass_count    = 0;
+        obj->pass_samples.clear();
     }
     return NB200_OK;
+}
+
+int nb200_objective_pass_samples(nb200_obj* obj, double* pass_ms, const int64_t capacity, int64_t* count)
+{
+    NB200_REQUIRE(obj != nullptr && count != nullptr && (pass_ms != nullptr || capacity == 0), "objective: null argument");
+    const nb200_obj* source = obj->parts.empty() ? obj : obj->parts[0];
+    *count = static_cast<int64_t>(source->pass_samples.size());
+    for (int64_t i = 0; i < std::min<int64_t>(capacity, *count); ++i)
+    {
+        pass_ms[i] = source->pass_samples[static_cast<size_t>(i)];
+    }
+    return NB200_OK;
+}
+
+// the roofline denominators of this board, measured in the run that quotes them (probe.cuh)
+int nb200_probe_peak(nb200_ctx* ctx, const int kind, double* value)
+{
+    NB200_REQUIRE(ctx != nullptr && value != nullptr, "probe: null argument");
+    NB200_REQUIRE(kind >= NB200_PEAK_DMMA_TFLOPS && kind <= NB200_PEAK_HBM_READ_GBS, "probe: unknown kind");
+    if (!ctx->parts.empty())
+    {
+        ctx = ctx->parts[0];
+    }
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaEvent_t    e0 = nullptr, e1 = nullptr;
+    double*        out = nullptr;
+    unsigned char* src = nullptr;
+    const auto     run = [&]() -> int
+    {
+        NB200_CUDA_TRY(cudaEventCreate(&e0));
+        NB200_CUDA_TRY(cudaEventCreate(&e1));
+        const int blocks = ctx->sm_count * 8, threads = 256;
+        NB200_CUDA_TRY(cudaMalloc(&out, static_cast<size_t>(blocks) * threads * sizeof(double)));
+        constexpr int     kTile = 32768, kStages = 4;
+        const int64_t     tiles = (4LL << 30) / kTile; // 4 GiB: far beyond L2
+        const int         smem  = 128 + kStages * kTile;
+        if (kind == NB200_PEAK_HBM_READ_GBS)
+        {
+            NB200_CUDA_TRY(cudaMalloc(&src, static_cast<size_t>(tiles) * kTile));
+            NB200_CUDA_TRY(cudaMemsetAsync(src, 1, static_cast<size_t>(tiles) * kTile, ctx->stream));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(probe_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        }
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) // the first one warms up
+        {
+            NB200_CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+            switch (kind)
+            {
+            case NB200_PEAK_DMMA_TFLOPS: probe_dmma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, 1.0000001, 1e-9); break;
+            case NB200_PEAK_DFMA_TFLOPS: probe_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, 1.0000001, 1e-9); break;
+            default: probe_read_kernel<<<ctx->sm_count, 128, smem, ctx->stream>>>(src, tiles, out); break;
+            }
+            NB200_CUDA_TRY(cudaGetLastError());
+            NB200_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+            NB200_CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0.0f;
+            NB200_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0)
+            {
+                best = std::min(best, ms);
+            }
+        }
+        const double seconds = best * 1e-3;
+        const double warps   = static_cast<double>(blocks) * threads / 32.0;
+        switch (kind)
+        {
+        case NB200_PEAK_DMMA_TFLOPS: *value = warps * kProbeIters * 8.0 * (2.0 * 8 * 8 * 4) / seconds * 1e-12; break;
+        case NB200_PEAK_DFMA_TFLOPS: *value = warps * 32.0 * kProbeIters * 16.0 * 2.0 / seconds * 1e-12; break;
+        default: *value = static_cast<double>(tiles) * kTile / seconds * 1e-9; break;
+        }
+        return NB200_OK;
+    };
+    const int status = run();
+    cudaFree(out);
+    cudaFree(src);
+    if (e0 != nullptr)
+    {
+        cudaEventDestroy(e0);
+    }
+    if (e1 != nullptr)
+    {
+        cudaEventDestroy(e1);
+    }
+    return status;
 }
 
 int nb200_objective_set_variant(nb200_obj* obj, const int variant)
 {
     NB200_REQUIRE(obj != nullptr, "objective: null argument");
+    if (!obj->parts.empty())
+    {
+        for (nb200_obj* part : obj->parts)
+        {
+            const int status = nb200_objective_set_variant(part, variant);
+            if (status != NB200_OK)
+            {
+                return status;
+            }
+        }
+        return group_connect(obj);
+    }
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
     NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
     return setup_plan(obj, variant);
@@ -1782,6 +2584,22 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
 {
     NB200_REQUIRE(obj != nullptr && buffer != nullptr && size > 0, "objective: null argument");
     std::string text;
+    if (!obj->parts.empty())
+    {
+        const int status = nb200_objective_describe(obj->parts[0], buffer, size);
+        if (status != NB200_OK)
+        {
+            return status;
+        }
+        text = std::string(buffer) + " | group of " + std::to_string(obj->parts.size()) + " devices, sums " +
+               (obj->group_fused ? (obj->parts[0]->peer_wait == 0
+                                        ? "published into the first device's mailbox over peer memory (stream wait)"
+                                        : "exchanged inside the launch over peer memory")
+                                 : "gathered by peer copies (two-phase)");
+        std::strncpy(buffer, text.c_str(), static_cast<size_t>(size) - 1);
+        buffer[size - 1] = '\0';
+        return NB200_OK;
+    }
     if (obj->use_t1)
     {
         const t1_variant& var = kT1Variants[obj->t1.variant];
@@ -1842,6 +2660,13 @@ int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const doubl
     NB200_REQUIRE(allreduce != nullptr || n_global == 0 || n_global == obj->data->N || obj->peer_world > 1,
                   "lbfgs: a sharded solve needs the all-reduce callback or connected peers");
     NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    if (!obj->parts.empty())
+    {
+        NB200_REQUIRE(allreduce == nullptr && (n_global == 0 || n_global == obj->data->N),
+                      "lbfgs: a device group holds all samples; no all-reduce callback applies");
+        device_lbfgs_t solver(obj->parts[0], obj->data->N, nullptr, nullptr, solver_method_t{}, obj);
+        return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
+    }
     device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user);
     return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
 }
@@ -1869,6 +2694,13 @@ int nb200_cgd_minimize(nb200_obj* obj, double* x, const int64_t n, const int bet
     method.c2        = 1e-1; // solver::tolerance of the cgd family (cgd.cpp:77)
     method.orthotest = orthotest;
     method.eta       = eta;
+    if (!obj->parts.empty())
+    {
+        NB200_REQUIRE(allreduce == nullptr && (n_global == 0 || n_global == obj->data->N),
+                      "cgd: a device group holds all samples; no all-reduce callback applies");
+        device_lbfgs_t solver(obj->parts[0], obj->data->N, nullptr, nullptr, method, obj);
+        return solver.run(x, epsilon, max_evals, 1, fx, gradient_test, stats, status);
+    }
     device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user, method);
     return solver.run(x, epsilon, max_evals, 1, fx, gradient_test, stats, status);
 }
@@ -2140,6 +2972,7 @@ static int vgrad_batch_impl(nb200_obj* obj, const int64_t K, const double* x, co
 int nb200_vgrad_batch(nb200_obj* obj, const int64_t K, const double* x, const int64_t n, const double* l1,
                       const double* l2, double* gx, double* fx)
 {
+    NB200_NOT_ON_A_GROUP(obj, "nb200_vgrad_batch");
     return vgrad_batch_impl(obj, K, x, n, l1, l2, gx, fx, 0);
 }
 
@@ -2147,6 +2980,15 @@ int nb200_predict(nb200_ctx* ctx, const nb200_data* data, const double* W, const
 {
     NB200_REQUIRE(ctx != nullptr && data != nullptr && W != nullptr && b != nullptr && outputs != nullptr,
                   "predict: null argument");
+    NB200_REQUIRE(ctx->parts.size() == data->parts.size(), "predict: context and dataset are not on the same device group");
+    for (size_t r = 0; r < data->parts.size(); ++r) // a device group: every device predicts its own rows
+    {
+        const int status = nb200_predict(ctx->parts[r], data->parts[r], W, b, outputs + data->row0[r] * data->T);
+        if (status != NB200_OK || r + 1 == data->parts.size())
+        {
+            return status;
+        }
+    }
     NB200_REQUIRE(ctx->device == data->device, "predict: context and dataset live on different devices");
     NB200_CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t N = data->N, D = data->D, T = data->T;
@@ -2175,6 +3017,10 @@ static int loss_rows(nb200_ctx* ctx, const int loss, const double loss_param, co
                      const double* outputs, const int64_t N, const int64_t T, double* values, double* vgrads)
 {
     NB200_REQUIRE(ctx != nullptr && targets != nullptr && outputs != nullptr, "loss: null argument");
+    if (!ctx->parts.empty())
+    {
+        ctx = ctx->parts[0]; // host buffers in, host buffers out: one device of the group does it
+    }
     NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "loss: unknown loss");
     NB200_REQUIRE(N >= 0 && T > 0, "loss: invalid dimensions");
     if (N == 0)
@@ -2241,6 +3087,10 @@ int nb200_loss_error(nb200_ctx* ctx, const int error_kind, const double* targets
                   "loss error: null argument");
     NB200_REQUIRE(error_kind >= 0 && error_kind < NB200_ERROR_COUNT, "loss error: unknown error kind");
     NB200_REQUIRE(N >= 0 && T > 0, "loss error: invalid dimensions");
+    if (!ctx->parts.empty())
+    {
+        ctx = ctx->parts[0];
+    }
     if (N == 0)
     {
         return NB200_OK;
@@ -2294,6 +3144,17 @@ int nb200_evaluate(nb200_ctx* ctx, const nb200_data* data, const int loss, const
 {
     NB200_REQUIRE(ctx != nullptr && data != nullptr && W != nullptr && b != nullptr, "evaluate: null argument");
     NB200_REQUIRE(errors != nullptr || values != nullptr, "evaluate: nothing to compute");
+    NB200_REQUIRE(ctx->parts.size() == data->parts.size(), "evaluate: context and dataset are not on the same device group");
+    for (size_t r = 0; r < data->parts.size(); ++r) // a device group: every device evaluates its own rows
+    {
+        const int status = nb200_evaluate(ctx->parts[r], data->parts[r], loss, loss_param, error_kind, W, b,
+                                          errors != nullptr ? errors + data->row0[r] : nullptr,
+                                          values != nullptr ? values + data->row0[r] : nullptr);
+        if (status != NB200_OK || r + 1 == data->parts.size())
+        {
+            return status;
+        }
+    }
     NB200_REQUIRE(ctx->device == data->device, "evaluate: context and dataset live on different devices");
     NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_COUNT, "evaluate: unknown loss");
     NB200_REQUIRE(error_kind >= 0 && error_kind < NB200_ERROR_COUNT, "evaluate: unknown error kind");

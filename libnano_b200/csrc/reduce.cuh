@@ -62,7 +62,30 @@ struct finish_params
     int           flavour;  // 0 LINEAR, 1 SYNTH
     double        l1;
     double        l2;
+    // sample-sharded evaluation whose ranks PUBLISHED their sums into this rank's mailbox (vgrad_t1.cuh, peer_wait == 0):
+    // mail [world][col_stride] holds one reduced vector per rank; they are folded here in rank order (identical bits on
+    // every rank) and the all-reduced vector is also left in reduced_out. mail == nullptr: `reduced` is used as it is.
+    const double* mail;
+    int           world;
+    int64_t       col_stride;
+    double*       reduced_out;
 };
+
+// entry c of the (all-)reduced vector as seen by the thread that finishes it
+__device__ __forceinline__ double finish_reduced_at(const finish_params& p, const int64_t c)
+{
+    if (p.mail == nullptr)
+    {
+        return p.reduced[c];
+    }
+    double sum = 0.0;
+    for (int q = 0; q < p.world; ++q)
+    {
+        sum += __ldcg(p.mail + static_cast<int64_t>(q) * p.col_stride + c);
+    }
+    p.reduced_out[c] = sum;
+    return sum;
+}
 
 // block 0 also produces the function value (needs a reduction over W for the regularisers)
 __global__ void __launch_bounds__(256) finish_kernel(const finish_params p)
@@ -79,7 +102,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const finish_params p)
             // gb = acc.m_gb / N
             if (k < wsize)
             {
-                double g = __ddiv_rn(p.reduced[1 + p.T + k], samples);
+                double g = __ddiv_rn(finish_reduced_at(p, 1 + p.T + k), samples);
                 if (p.l1 > 0.0)
                 {
                     g = __dadd_rn(g, __ddiv_rn(__dmul_rn(p.l1, sign_of(p.x[k])), static_cast<double>(wsize)));
@@ -92,7 +115,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const finish_params p)
             }
             else if (k < wsize + p.T)
             {
-                p.gx[k] = __ddiv_rn(p.reduced[1 + (k - wsize)], samples);
+                p.gx[k] = __ddiv_rn(finish_reduced_at(p, 1 + (k - wsize)), samples);
             }
         }
         else
@@ -100,7 +123,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const finish_params p)
             // gw = G^T X / N (linear.cpp:66), then += alpha1 * sign(x) + alpha2 * x (elasticnet.cpp:76)
             if (k < wsize)
             {
-                const double g   = __ddiv_rn(p.reduced[1 + p.T + k], samples);
+                const double g   = __ddiv_rn(finish_reduced_at(p, 1 + p.T + k), samples);
                 const double reg = __dadd_rn(__dmul_rn(p.l1, sign_of(p.x[k])), __dmul_rn(p.l2, p.x[k]));
                 p.gx[k]          = __dadd_rn(g, reg);
             }
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const finish_params p)
         }
         if (threadIdx.x == 0)
         {
-            double fx = __ddiv_rn(p.reduced[0], samples);
+            double fx = __ddiv_rn(finish_reduced_at(p, 0), samples);
             if (p.flavour == 0)
             {
                 // fx += l1 * mean|w| ; fx += 0.5 * mean((sqrt(l2) * w)^2)   (function.cpp:158-166)

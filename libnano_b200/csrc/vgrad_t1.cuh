@@ -80,6 +80,15 @@ struct t1_params
     double*             peer_mail[kT1MaxPeers];
     unsigned long long* peer_flag[kT1MaxPeers];
     int*                peer_error;  // mapped host int: set when a peer did not show up in time
+    // peer_wait == 1: the launch itself waits for the peers' slices and folds them (compute + collective in ONE kernel:
+    // every CTA spins on per-CTA flags, so the launch holds the whole GPU until every peer has published).
+    // peer_wait == 0: the launch publishes its slices and leaves; the LAST CTA to publish raises ONE ready word per peer
+    // (behind the per-CTA flags: [2][world] words), the stream then waits on those words (cuStreamWaitValue64: no SM is
+    // held while waiting, so evaluations of different objectives cannot cross-wait) and peer_finish_kernel folds the
+    // slots in rank order.
+    int                 peer_wait;
+    unsigned long long* publish_counter; // CTAs of this device that have published (monotone, like grid_counter)
+    unsigned long long  publish_target;  // value at which every CTA of THIS launch has published
 };
 
 #ifdef __CUDACC__
@@ -538,7 +547,10 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
         return;
     }
 
-    // ---- cross-rank stage: publish this CTA's slice, wait for the same slice of every peer, fold in rank order ----
+    // ---- cross-rank stage: publish this CTA's slice; either leave (the stream waits) or wait here and fold ----------
+    // Both signals are always raised, so ranks in different wait modes still understand each other: a per-CTA flag
+    // (for peers that wait inside their launch, slice by slice) and, by the LAST CTA of this launch to publish, ONE
+    // ready word per peer (for peers whose stream waits: cuStreamWaitValue64 on [2][world] words behind the flags).
     __threadfence_system();
     __syncthreads();
     if (warp == 0)
@@ -548,6 +560,26 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
             // release: the slice written above is visible to rank `lane` before it sees the flag
             unsigned long long* flag = p.peer_flag[lane] + slot * G + blockIdx.x;
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.epoch) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+            // every CTA fenced its peer stores (system scope) before this update, and the release below is cumulative
+            // over what the acquiring CTA observed: a peer that sees the ready word sees every slice of this rank
+            unsigned long long arrived;
+            asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;" : "=l"(arrived) : "l"(p.publish_counter) : "memory");
+            if (arrived + 1ULL == p.publish_target)
+            {
+                __threadfence_system();
+                for (int q = 0; q < p.world; ++q)
+                {
+                    unsigned long long* ready = p.peer_flag[q] + 2ULL * p.world * G + slot;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready), "l"(p.epoch) : "memory");
+                }
+            }
+        }
+        if (p.peer_wait != 0 && lane < p.world)
+        {
             // acquire: wait for rank `lane`'s slice in MY mailbox (flags only grow; parity double-buffers the mail)
             const unsigned long long* mine =
                 p.peer_flag[p.rank] + (static_cast<unsigned long long>(parity) * p.world + lane) * G + blockIdx.x;
@@ -564,6 +596,10 @@ __device__ __forceinline__ void fold_partials(const t1_params& p, const double* 
             } while (seen < p.epoch);
         }
         __syncwarp();
+    }
+    if (p.peer_wait == 0)
+    {
+        return; // publish-only launch: peer_finish (finish_kernel with the mailbox) folds the slots
     }
     __syncthreads();
 

@@ -38,13 +38,31 @@ def critical(condition: bool, *message) -> None:
 
 
 class Context:
-    """One CUDA device (nb200_ctx)."""
+    """One CUDA device (nb200_ctx) — or, given a list of devices, a device GROUP: datasets pinned on it are split in
+    contiguous row blocks over the devices and objectives on them evaluate on all of them from this one process (what
+    libnano's thread pool does with the workers of one process, src/linear/function.cpp:53-57)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         handle = ctypes.c_void_p()
-        _lib.check(_lib.lib().nb200_init(device, ctypes.byref(handle)))
+        if isinstance(device, (list, tuple)):
+            devices = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            _lib.check(_lib.lib().nb200_init_multi(len(device), devices, ctypes.byref(handle)))
+            self.devices = [int(d) for d in device]
+            self.device = self.devices[0]
+        else:
+            _lib.check(_lib.lib().nb200_init(device, ctypes.byref(handle)))
+            self.devices = [int(device)]
+            self.device = device
         self.handle = handle
-        self.device = device
+
+    PEAKS = {"dmma_tflops": 0, "dfma_tflops": 1, "hbm_read_gbs": 2}
+
+    def probe_peak(self, what: str) -> float:
+        """A roofline denominator of this board measured now: 'dmma_tflops' (fp64 tensor pipe), 'dfma_tflops' (fp64 FMA
+        pipe) or 'hbm_read_gbs' (read-only bulk-copy stream)."""
+        value = ctypes.c_double()
+        _lib.check(_lib.lib().nb200_probe_peak(self.handle, self.PEAKS[what], ctypes.byref(value)))
+        return value.value
 
     def close(self):
         if getattr(self, "handle", None):
@@ -340,6 +358,24 @@ class _DeviceFunction(Function):
         _lib.check(_lib.lib().nb200_vgrad_sharded_device(self.handle, ctypes.c_void_p(x_ptr), self.size(), n_global,
                                                          ctypes.c_void_p(gx_ptr or 0), ctypes.c_void_p(fx_ptr)))
 
+    def peer_mode(self) -> int:
+        """0: publish-only launches + stream wait; 1: the launch waits for its peers; -1: not connected."""
+        return int(_lib.lib().nb200_objective_peer_mode(self.handle))
+
+    def parts(self) -> int:
+        """Devices this objective evaluates on (1 unless its dataset lives on a device group)."""
+        return int(_lib.lib().nb200_objective_parts(self.handle))
+
+    def part_stats(self, index: int, reset: bool = False):
+        """(describe, total pass ms, passes, launches) of the objective on device `index` of the group."""
+        part = ctypes.c_void_p(_lib.lib().nb200_objective_part(self.handle, index))
+        critical(bool(part), "function: no such part")
+        buffer = ctypes.create_string_buffer(512)
+        _lib.check(_lib.lib().nb200_objective_describe(part, buffer, 512))
+        total, count = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(_lib.lib().nb200_objective_pass_stats(part, ctypes.byref(total), ctypes.byref(count), int(reset)))
+        return buffer.value.decode(), total.value, count.value, int(_lib.lib().nb200_objective_launches(part))
+
     def sync(self) -> None:
         _lib.check(_lib.lib().nb200_objective_sync(self.handle))
 
@@ -368,6 +404,16 @@ class _DeviceFunction(Function):
         _lib.check(_lib.lib().nb200_objective_pass_stats(self.handle, ctypes.byref(total), ctypes.byref(count),
                                                          int(reset)))
         return total.value, count.value
+
+    def pass_samples(self, part: int = 0):
+        """Milliseconds of every timed pass since the last reset (of device `part` of a group)."""
+        handle = ctypes.c_void_p(_lib.lib().nb200_objective_part(self.handle, part))
+        critical(bool(handle), "function: no such part")
+        count = ctypes.c_int64()
+        _lib.check(_lib.lib().nb200_objective_pass_samples(handle, None, 0, ctypes.byref(count)))
+        out = np.empty(count.value, dtype=np.float64)
+        _lib.check(_lib.lib().nb200_objective_pass_samples(handle, _ptr(out), out.size, ctypes.byref(count)))
+        return out
 
     def host_profile(self, reset: bool = False):
         """Host-side wall clock of the host-buffer call since the last reset: (stage_us, enqueue_us, wait_us, calls)."""

@@ -80,45 +80,54 @@ class DeviceShard:
         return self.local.do_eval(x, gx)
 
     def connect_peers(self, group=None) -> bool:
-        """Set up the fused compute + collective path: every rank maps every other rank's mailbox (CUDA IPC over
-        NVLink), after which ONE kernel launch per rank does the pass over X AND the all-reduce. Returns False (and
-        leaves the NCCL two-phase path in place) when the objective is not on the single-target kernel."""
-        import torch.distributed as dist
-
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        if world < 2 or world > 8:
-            return False
-
-        def everyone(flag: bool) -> bool:
-            """Every rank takes part in every collective, whatever happened locally: no rank is left waiting."""
-            mine = self._torch.tensor([1 if flag else 0], dtype=self._torch.uint8, device="cuda")
-            votes = [self._torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(votes, mine, group=group)
-            return all(int(v.item()) == 1 for v in votes)
-
-        # (1) export this rank's mailbox (fails, e.g., when the objective is not on the single-target kernel)
-        handle, grid, ok = bytes(64), 0, True
-        try:
-            if not self.local.describe().startswith("t1"):
-                raise RuntimeError("not the single-target kernel")
-            handle, grid = self.local.peer_export(world)
-        except Exception:  # noqa: BLE001 - reported through the vote below
-            ok = False
-        mine = self._torch.tensor(list(handle) + [grid % 256, grid // 256, int(ok)], dtype=self._torch.uint8,
-                                  device="cuda")
-        gathered = [self._torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine, group=group)
-        blobs = [bytes(t.cpu().tolist()) for t in gathered]
-        if not all(b[66] == 1 for b in blobs) or not all(b[64:66] == blobs[0][64:66] for b in blobs):
-            return False  # some rank could not export, or the ranks run different grids: keep the NCCL path
-
-        # (2) map the peers' mailboxes (CUDA IPC); only if every rank succeeded is the fused path switched on
-        try:
-            self.local.peer_connect(rank, world, b"".join(b[:64] for b in blobs))
-        except Exception:  # noqa: BLE001
-            ok = False
-        self.fused = everyone(ok)
+        """Set up the fused compute + collective path (connect_local_peers); False leaves the NCCL two-phase path."""
+        self.fused = connect_local_peers(self.local, group)
         return self.fused
+
+
+def connect_local_peers(local, group=None) -> bool:
+    """Set up the fused compute + collective path of a rank-local objective: every rank maps every other rank's
+    mailbox (CUDA IPC over NVLink), after which ONE kernel launch per rank does the pass over X AND publishes its sums
+    into the peers' mailboxes. Returns False (nothing changed) when the objective is not on the single-target kernel or
+    any rank failed. Collective: every rank of `group` must call it, in the same order for every objective. All ranks
+    leave through a barrier, so no rank evaluates before every mailbox is mapped."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world < 2 or world > 8:
+        return False
+
+    def everyone(flag: bool) -> bool:
+        """Every rank takes part in every collective, whatever happened locally: no rank is left waiting."""
+        mine = torch.tensor([1 if flag else 0], dtype=torch.uint8, device="cuda")
+        votes = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(votes, mine, group=group)
+        return all(int(v.item()) == 1 for v in votes)
+
+    # (1) export this rank's mailbox (fails, e.g., when the objective is not on the single-target kernel)
+    handle, grid, ok = bytes(64), 0, True
+    try:
+        if not local.describe().startswith("t1"):
+            raise RuntimeError("not the single-target kernel")
+        handle, grid = local.peer_export(world)
+    except Exception:  # noqa: BLE001 - reported through the vote below
+        ok = False
+    mine = torch.tensor(list(handle) + [grid % 256, grid // 256, int(ok)], dtype=torch.uint8, device="cuda")
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    blobs = [bytes(t.cpu().tolist()) for t in gathered]
+    if not all(b[66] == 1 for b in blobs) or not all(b[64:66] == blobs[0][64:66] for b in blobs):
+        return False  # some rank could not export, or the ranks run different grids: keep the NCCL path
+
+    # (2) map the peers' mailboxes (CUDA IPC); only if every rank succeeded is the fused path switched on
+    try:
+        local.peer_connect(rank, world, b"".join(b[:64] for b in blobs))
+    except Exception:  # noqa: BLE001
+        ok = False
+    fused = everyone(ok)
+    dist.barrier(group=group)
+    return fused
 
 
 class ShardedFunction(Function):

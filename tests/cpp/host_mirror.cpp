@@ -4,6 +4,7 @@
 // Built and run by tests/test_cpp_host.py on the GPU box:  g++ -std=c++20 -Iinclude host_mirror.cpp libnb200.so
 #include <nano_b200/function.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -135,6 +136,39 @@ int main()
             refused = std::string(e.what()).find("incompatible initial point") != std::string::npos;
         }
         CHECK(refused);
+    }
+
+    // a device group behind the same interface: every visible device (at least two parts: one device serves twice on
+    // a one-GPU box). The evaluation must agree with the single-device objective to rounding (shard invariance) and
+    // be reproducible; the solver runs with its state on the first device.
+    {
+        const int         visible = nb200_device_count();
+        std::vector<int>  devices;
+        for (int d = 0; d < std::max(2, std::min(visible, 8)); ++d) devices.push_back(d < visible ? d : 0);
+        context_t          group(devices);
+        CHECK(group.devices() == static_cast<int>(devices.size()));
+        dataset_t          split(group, X.data(), Y.data(), N, D, T);
+        CHECK(split.samples() == N);
+        linear::function_t sharded(split, "mse", l1, l2);
+        std::vector<double> g3(gx.size()), g4(gx.size());
+        const double f3 = sharded({x.data(), static_cast<tensor_size_t>(x.size())}, {g3.data(), static_cast<tensor_size_t>(g3.size())});
+        const double f4 = sharded({x.data(), static_cast<tensor_size_t>(x.size())}, {g4.data(), static_cast<tensor_size_t>(g4.size())});
+        CHECK(f3 == f4 && g3 == g4);
+        CHECK(std::fabs(f3 - f2) <= 1e-13 * (1 + std::fabs(f2)));
+        double dsplit = 0.0;
+        for (size_t k = 0; k < gx.size(); ++k) dsplit = std::max(dsplit, std::fabs(g3[k] - gx[k]));
+        CHECK(dsplit <= 1e-13 * (1 + gmax));
+        const auto other = sharded.clone();
+        CHECK((*other)({x.data(), static_cast<tensor_size_t>(x.size())}) == f3);
+
+        const std::vector<double> x0(x.size(), 0.0);
+        linear::function_t smooth_single(data, "mse", 0.0, l2), smooth_group(split, "mse", 0.0, l2);
+        const auto a = minimize_lbfgs(smooth_single, x0, 1e-10, 10000);
+        const auto b = minimize_lbfgs(smooth_group, x0, 1e-10, 10000);
+        CHECK(a.m_status == solver_status::gradient_test && b.m_status == solver_status::gradient_test);
+        CHECK(std::fabs(a.m_fx - b.m_fx) <= 1e-10 * (1 + std::fabs(a.m_fx)));
+        std::printf("group of %d devices: f=%.15g lbfgs fx=%.15g (%d evaluations)\n", group.devices(), f3, b.m_fx,
+                    static_cast<int>(b.m_fcalls));
     }
 
     std::printf("OK f=%.15g |g|_inf=%.6g\n", f1, gmax);

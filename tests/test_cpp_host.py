@@ -31,4 +31,4 @@ def test_cpp_host_layer_compiles_and_links():
 @pytest.mark.gpu
 def test_cpp_host_layer_evaluates_on_the_gpu():
     result = subprocess.run([build()], capture_output=True, text=True, timeout=120)
-    assert result.returncode == 0 and result.stdout.startswith("OK"), result.stdout + result.stderr
+    assert result.returncode == 0 and "\nOK f=" in "\n" + result.stdout, result.stdout + result.stderr

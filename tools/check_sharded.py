@@ -2,7 +2,10 @@
 """Multi-GPU check, run under torchrun (one rank per GPU, NCCL):
   * ShardedFunction over row shards == the same objective over the whole dataset on one GPU (<= 1e-13 relative);
   * every rank ends with identical (f, g) bits;
-  * L-BFGS (restated driver) through the sharded objective reaches the single-GPU optimum.
+  * L-BFGS (restated driver) through the sharded objective reaches the single-GPU optimum;
+  * --fused: two connected objectives on their own streams, evaluated asynchronously in OPPOSITE order on even and odd
+    ranks (the cross-wait hazard of evaluations that hold the GPU while they wait for their peers): must complete,
+    with the bits of the in-order evaluation.
 Prints one JSON line on rank 0 and exits non-zero on any mismatch.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/check_sharded.py
@@ -95,6 +98,43 @@ def main():
         solve["max_dx"] = float(np.max(np.abs(single["x"] - solved["x"])))
         ok = ok and abs(single["fx"] - solved["fx"]) <= 1e-8 * (1 + abs(single["fx"])) and solve["max_dx"] <= 1e-3
     report["lbfgs"] = solve
+
+    if args_fused and world > 1:
+        from libnano_b200.sharded import connect_local_peers
+
+        N2, pair = 150001, []
+        for seed, D in ((3, 1024), (5, 512)):
+            row0, rows = shard_rows(N2, world, rank)
+            part = nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, rows, D, seed=seed, row_offset=row0)
+            f = nb.LinearFunction(part, nb.Loss("s-logistic"), 0.0, 1e-2)  # keeps its OWN stream
+            connected = connect_local_peers(f)
+            x = torch.from_numpy(np.random.default_rng(seed).uniform(-1, 1, D + 1) / np.sqrt(D)).cuda()
+            pair.append((f, connected, x, torch.zeros(D + 1, dtype=torch.float64, device="cuda"),
+                         torch.zeros(1, dtype=torch.float64, device="cuda")))
+        modes = [f.peer_mode() for f, *_ in pair]
+        crossed = {"connected": all(c for _, c, *_ in pair), "peer_modes": modes}
+        if crossed["connected"] and all(m == 0 for m in modes):
+            torch.cuda.synchronize()
+
+            def run(order):
+                for _ in range(8):
+                    for f, _, x, g, v in order:
+                        f.vgrad_sharded_device(x.data_ptr(), N2, g.data_ptr(), v.data_ptr())
+                for f, *_ in order:
+                    f.sync()
+                torch.cuda.synchronize()
+                return [(g.clone(), v.clone()) for _, _, _, g, v in pair]
+
+            in_order = run(pair)
+            opposite = run(pair if rank % 2 == 0 else pair[::-1])
+            crossed["completed"] = True
+            crossed["same_bits"] = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+                                       for a, b in zip(in_order, opposite))
+            crossed["finite"] = all(bool(torch.isfinite(a[1]).all()) and float(a[0].abs().max()) > 0 for a in in_order)
+            ok = ok and crossed["same_bits"] and crossed["finite"]
+        else:
+            crossed["skipped"] = "the launches wait for their peers in-kernel here: opposite orders would cross-wait"
+        report["opposite_order"] = crossed
     report["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(report), flush=True)
