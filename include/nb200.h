@@ -317,6 +317,28 @@ NB200_API int nb200_cgd_minimize(nb200_obj* obj, double* x, int64_t n, int beta,
                                  double orthotest, double eta, int64_t n_global, nb200_allreduce_fn allreduce,
                                  void* allreduce_user, double* fx, double* gradient_test, int64_t* stats, int* status);
 
+/* ---- gradient-boosting cousins of the linear objective ---------------------------------------------
+ * The same per-sample loss value / vgrad and accumulate-then-sum_reduce structure, without a feature matrix:
+ *   NB200_GBOOST_BIAS   gboost::bias_function_t  (src/gboost/function.cpp:67-126):  f(x) = mean_i loss(y_i, x), n = T
+ *   NB200_GBOOST_SCALE  gboost::scale_function_t (src/gboost/function.cpp:128-223): f(x) = mean_i loss(y_i, s_i + x[c_i] w_i),
+ *                       n = groups; cluster[i] = group of sample i or -1 (scale 0, no gradient contribution)
+ *   NB200_GBOOST_GRADS  gboost::grads_function_t (src/gboost/function.cpp:8-64):    f(o) = mean_i loss(y_i, o_i), n = N*T,
+ *                       gradient = the per-sample loss gradients / N
+ * targets / soutputs / woutputs: [N, T] host, row-major, gathered for the samples of the iterator (what
+ * targets_iterator_t::loop serves); cluster / groups / soutputs / woutputs are used by NB200_GBOOST_SCALE only.
+ * nb200_gboost_vgrad has the contract of nb200_vgrad (host x / gx / fx, gx nullable, size checked). */
+typedef struct nb200_gboost nb200_gboost;
+#define NB200_GBOOST_BIAS 0
+#define NB200_GBOOST_SCALE 1
+#define NB200_GBOOST_GRADS 2
+NB200_API int nb200_gboost_create(nb200_ctx* ctx, int kind, int loss, double loss_param, const double* targets, int64_t N,
+                                  int64_t T, const int32_t* cluster, int64_t groups, const double* soutputs,
+                                  const double* woutputs, nb200_gboost** out_obj);
+NB200_API int64_t nb200_gboost_size(const nb200_gboost* obj);
+NB200_API int64_t nb200_gboost_launches(const nb200_gboost* obj);
+NB200_API int     nb200_gboost_vgrad(nb200_gboost* obj, const double* x, int64_t n, double* gx, double* fx);
+NB200_API void    nb200_gboost_release(nb200_gboost* obj);
+
 /* ---- building blocks exposed on their own (reference: linear::predict, loss_t::value / loss_t::vgrad) -------- */
 
 /* outputs[N,T] (host) = X * W^T + b over the pinned dataset; W[T,D], b[T] host. */

@@ -7,6 +7,7 @@ There is no CPU fallback: every evaluation is a CUDA launch and a missing libnb2
 """
 from .function import (FLAVOUR_LINEAR, FLAVOUR_SYNTH, SYNTH_CLASSIFICATION, SYNTH_MULTICLASS, SYNTH_REGRESSION,
                        Context, Dataset, Function, LinearFunction, SyntheticFunction, critical)
+from .gboost import GBoostBiasFunction, GBoostGradsFunction, GBoostScaleFunction
 from .linear import LinearModel
 from .loss import LOSS_IDS, Loss
 from ._lib import LIB_PATH, Nb200Error
@@ -16,5 +17,5 @@ __version__ = "0.1.0"
 __all__ = [
     "Context", "Dataset", "Function", "LinearFunction", "SyntheticFunction", "LinearModel", "Loss", "LOSS_IDS", "critical",
     "Nb200Error", "LIB_PATH", "FLAVOUR_LINEAR", "FLAVOUR_SYNTH", "SYNTH_CLASSIFICATION", "SYNTH_REGRESSION",
-    "SYNTH_MULTICLASS",
+    "SYNTH_MULTICLASS", "GBoostBiasFunction", "GBoostScaleFunction", "GBoostGradsFunction",
 ]

@@ -23,6 +23,7 @@
 #include "kernel_tables.cuh"
 #include "batch.cuh"
 #include "probe.cuh"
+#include "gboost.cuh"
 
 using namespace nb200;
 
@@ -2485,6 +2486,196 @@ int nb200_objective_pass_samples(nb200_obj* obj, double* pass_ms, const int64_t 
     {
         pass_ms[i] = source->pass_samples[static_cast<size_t>(i)];
     }
+    return NB200_OK;
+}
+
+// ---- gradient-boosting cousins (gboost.cuh) ------------------------------------------------------------------------
+} // extern "C"
+
+struct nb200_gboost
+{
+    int          device{0};
+    cudaStream_t stream{nullptr};
+    int          kind{0}, loss{0};
+    double       loss_param{0.0};
+    int64_t      N{0}, T{0}, K{0}, n{0}, n_out{0};
+    int          blocks{0}, smem{0};
+    double *     d_targets{nullptr}, *d_soutputs{nullptr}, *d_woutputs{nullptr};
+    int*         d_cluster{nullptr};
+    double *     d_x{nullptr}, *d_out{nullptr}, *d_partials{nullptr}, *d_reduced{nullptr};
+    double *     h_x{nullptr}, *h_out{nullptr};
+    int64_t      launches{0};
+};
+
+extern "C" {
+
+void nb200_gboost_release(nb200_gboost* obj)
+{
+    if (obj == nullptr)
+    {
+        return;
+    }
+    cudaSetDevice(obj->device);
+    cudaFree(obj->d_targets);
+    cudaFree(obj->d_soutputs);
+    cudaFree(obj->d_woutputs);
+    cudaFree(obj->d_cluster);
+    cudaFree(obj->d_x);
+    cudaFree(obj->d_out);
+    cudaFree(obj->d_partials);
+    cudaFree(obj->d_reduced);
+    cudaFreeHost(obj->h_x);
+    cudaFreeHost(obj->h_out);
+    if (obj->stream != nullptr)
+    {
+        cudaStreamDestroy(obj->stream);
+    }
+    delete obj;
+}
+
+int nb200_gboost_create(nb200_ctx* ctx, const int kind, const int loss, const double loss_param, const double* targets,
+                        const int64_t N, const int64_t T, const int32_t* cluster, const int64_t groups,
+                        const double* soutputs, const double* woutputs, nb200_gboost** out_obj)
+{
+    NB200_REQUIRE(ctx != nullptr && targets != nullptr && out_obj != nullptr, "gboost: null argument");
+    NB200_REQUIRE(kind >= GBOOST_BIAS && kind <= GBOOST_GRADS, "gboost: unknown function kind");
+    NB200_REQUIRE(loss >= 0 && loss < NB200_LOSS_SYNTH_CAUCHY, "gboost: unknown loss");
+    NB200_REQUIRE(N > 0 && T > 0 && T < (1 << 20), "gboost: invalid dimensions");
+    NB200_REQUIRE(kind != GBOOST_SCALE ||
+                      (cluster != nullptr && soutputs != nullptr && woutputs != nullptr && groups > 0 && groups <= 2048),
+                  "gboost: the scale function needs cluster ids, strong and weak outputs and 1 to 2048 groups");
+    if (kind == GBOOST_SCALE)
+    {
+        for (int64_t i = 0; i < N; ++i)
+        {
+            NB200_REQUIRE(cluster[i] < groups, "gboost: cluster id out of range");
+        }
+    }
+    if (!ctx->parts.empty())
+    {
+        ctx = ctx->parts[0];
+    }
+    NB200_CUDA_TRY(cudaSetDevice(ctx->device));
+    auto* obj = new (std::nothrow) nb200_gboost{};
+    NB200_REQUIRE(obj != nullptr, "gboost: out of host memory");
+    obj->device     = ctx->device;
+    obj->kind       = kind;
+    obj->loss       = loss;
+    obj->loss_param = loss_param;
+    obj->N          = N;
+    obj->T          = T;
+    obj->K          = (kind == GBOOST_SCALE) ? groups : 0;
+    obj->n          = (kind == GBOOST_BIAS) ? T : (kind == GBOOST_SCALE ? groups : N * T);
+    obj->n_out      = (kind == GBOOST_BIAS) ? T : (kind == GBOOST_SCALE ? groups : 0);
+    obj->smem       = static_cast<int>((kGbWarps * obj->n_out + kGbWarps) * sizeof(double));
+    const auto build = [&]() -> int
+    {
+        NB200_REQUIRE(obj->smem <= ctx->smem_optin, "gboost: too many targets for the per-warp accumulators");
+        const size_t  rows  = static_cast<size_t>(N) * T * sizeof(double);
+        const int64_t iters = (N + 31) / 32; // at least this many warp iterations
+        obj->blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((iters + kGbWarps - 1) / kGbWarps,
+                                                                               4LL * ctx->sm_count)));
+        NB200_CUDA_TRY(cudaStreamCreateWithFlags(&obj->stream, cudaStreamNonBlocking));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_targets, rows));
+        NB200_CUDA_TRY(cudaMemcpy(obj->d_targets, targets, rows, cudaMemcpyHostToDevice));
+        if (kind == GBOOST_SCALE)
+        {
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_soutputs, rows));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_woutputs, rows));
+            NB200_CUDA_TRY(cudaMalloc(&obj->d_cluster, static_cast<size_t>(N) * sizeof(int)));
+            NB200_CUDA_TRY(cudaMemcpy(obj->d_soutputs, soutputs, rows, cudaMemcpyHostToDevice));
+            NB200_CUDA_TRY(cudaMemcpy(obj->d_woutputs, woutputs, rows, cudaMemcpyHostToDevice));
+            NB200_CUDA_TRY(cudaMemcpy(obj->d_cluster, cluster, static_cast<size_t>(N) * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        const size_t n = static_cast<size_t>(obj->n);
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_x, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_out, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(obj->blocks) * (1 + obj->n_out) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMalloc(&obj->d_reduced, static_cast<size_t>(1 + obj->n_out) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMallocHost(&obj->h_x, (n + 2) * sizeof(double)));
+        NB200_CUDA_TRY(cudaMallocHost(&obj->h_out, (n + 2) * sizeof(double)));
+        if (obj->smem > 48 * 1024)
+        {
+            NB200_CUDA_TRY(cudaFuncSetAttribute(gboost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->smem));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(gboost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, obj->smem));
+        }
+        return NB200_OK;
+    };
+    const int status = build();
+    if (status != NB200_OK)
+    {
+        const std::string message = g_last_error;
+        nb200_gboost_release(obj);
+        g_last_error = message;
+        return status;
+    }
+    *out_obj = obj;
+    return NB200_OK;
+}
+
+int64_t nb200_gboost_size(const nb200_gboost* obj)
+{
+    return obj != nullptr ? obj->n : 0;
+}
+
+int64_t nb200_gboost_launches(const nb200_gboost* obj)
+{
+    return obj != nullptr ? obj->launches : 0;
+}
+
+int nb200_gboost_vgrad(nb200_gboost* obj, const double* x, const int64_t n, double* gx, double* fx)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr, "function: null argument");
+    NB200_REQUIRE(n == obj->n, "function: invalid input size, expecting (" + std::to_string(obj->n) + ",), got (" +
+                                   std::to_string(n) + ",) instead!");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    const size_t bytes = static_cast<size_t>(n) * sizeof(double);
+    std::memcpy(obj->h_x, x, bytes);
+    NB200_CUDA_TRY(cudaMemcpyAsync(obj->d_x, obj->h_x, bytes, cudaMemcpyHostToDevice, obj->stream));
+    gboost_params p{};
+    p.targets    = obj->d_targets;
+    p.soutputs   = obj->d_soutputs;
+    p.woutputs   = obj->d_woutputs;
+    p.cluster    = obj->d_cluster;
+    p.x          = obj->d_x;
+    p.partials   = obj->d_partials;
+    p.gx         = obj->d_out;
+    p.N          = obj->N;
+    p.T          = static_cast<int>(obj->T);
+    p.K          = static_cast<int>(obj->K);
+    p.kind       = obj->kind;
+    p.loss       = obj->loss;
+    p.loss_param = obj->loss_param;
+    if (gx != nullptr)
+    {
+        gboost_kernel<true><<<obj->blocks, kGbWarps * 32, obj->smem, obj->stream>>>(p);
+    }
+    else
+    {
+        gboost_kernel<false><<<obj->blocks, kGbWarps * 32, obj->smem, obj->stream>>>(p);
+    }
+    NB200_CUDA_TRY(cudaGetLastError());
+    const int64_t cols = (gx != nullptr) ? 1 + obj->n_out : 1;
+    reduce_partials_kernel<<<static_cast<unsigned>((cols + 127) / 128), 128, 0, obj->stream>>>(
+        obj->d_partials, obj->blocks, 1 + obj->n_out, cols, obj->d_reduced);
+    NB200_CUDA_TRY(cudaGetLastError());
+    // the per-sample gradients of the grads function are already in d_out; bias / scale gradients come from the sums
+    double* g_dev = (gx != nullptr && obj->kind != GBOOST_GRADS) ? obj->d_out : nullptr;
+    gboost_finish_kernel<<<static_cast<unsigned>((std::max<int64_t>(obj->n_out, 1) + 255) / 256), 256, 0, obj->stream>>>(
+        obj->d_reduced, obj->n_out, obj->N, g_dev, obj->d_out + n);
+    NB200_CUDA_TRY(cudaGetLastError());
+    obj->launches += 3;
+    if (gx != nullptr)
+    {
+        NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out, obj->d_out, bytes, cudaMemcpyDeviceToHost, obj->stream));
+    }
+    NB200_CUDA_TRY(cudaMemcpyAsync(obj->h_out + n, obj->d_out + n, sizeof(double), cudaMemcpyDeviceToHost, obj->stream));
+    NB200_CUDA_TRY(cudaStreamSynchronize(obj->stream));
+    if (gx != nullptr)
+    {
+        std::memcpy(gx, obj->h_out, bytes);
+    }
+    *fx = obj->h_out[n];
     return NB200_OK;
 }
 

@@ -102,6 +102,9 @@ def lib():
         L.oracle_synth_vgrad.argtypes = [_dp, _dp, ctypes.c_double, _i64, _i64, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_double, _dp, _dp]
         L.oracle_hardware_threads.restype = ctypes.c_int
+        L.oracle_gboost_vgrad.restype = ctypes.c_double
+        L.oracle_gboost_vgrad.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, _i64, _i64,
+                                          ctypes.POINTER(ctypes.c_int32), _i64, _dp, _dp, _dp, _dp, _i64]
         # restated drivers (solvers.cpp)
         L.oracle_solver_callback = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_void_p, _dp, _dp)
         L.oracle_lbfgs.restype = ctypes.c_int
@@ -291,6 +294,28 @@ def upscale(istats, iscaling: str, tstats, tscaling: str, W, b):
     lib().oracle_upscale(_ptr(_f64(istats, (7, D))), SCALINGS[iscaling], _ptr(_f64(tstats, (7, T))), SCALINGS[tscaling],
                          D, T, _ptr(W), _ptr(b))
     return W, b
+
+
+GBOOST_KINDS = {"bias": 0, "scale": 1, "grads": 2}
+
+
+def gboost_vgrad(kind: str, loss_id: str, targets, x, cluster=None, groups=0, soutputs=None, woutputs=None,
+                 want_grad=True, batch=100, param=0.5):
+    """f, g of gboost::{bias,scale,grads}_function_t::do_eval (src/gboost/function.cpp) over targets[N, T]."""
+    targets = _f64(targets)
+    N, T = targets.shape
+    n = {"bias": T, "scale": groups, "grads": N * T}[kind]
+    x = _f64(x, (n,))
+    gx = np.empty_like(x) if want_grad else None
+    ids = None
+    if kind == "scale":
+        ids = np.ascontiguousarray(cluster, dtype=np.int32)
+        soutputs, woutputs = _f64(soutputs, (N, T)), _f64(woutputs, (N, T))
+    fx = lib().oracle_gboost_vgrad(GBOOST_KINDS[kind], loss_kind(loss_id), param, _ptr(targets), N, T,
+                                   None if ids is None else ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), groups,
+                                   _ptr(soutputs) if kind == "scale" else None,
+                                   _ptr(woutputs) if kind == "scale" else None, _ptr(x), _ptr(gx), batch)
+    return fx, gx
 
 
 def hardware_threads() -> int:

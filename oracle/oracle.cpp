@@ -987,6 +987,100 @@ double oracle_synth_vgrad(const double* X, const double* Y, const double bopt, c
     return fx;
 }
 
+// gboost::{bias,scale,grads}_function_t::do_eval (src/gboost/function.cpp:26-50, 85-126, 151-223): targets_iterator_t
+// serves the samples in batches; per batch the outputs are formed, loss_t::value / vgrad run over the batch and the
+// accumulator sums values and gradients; sum_reduce divides by the sample count (src/gboost/accumulator.cpp:20-47).
+// kind: 0 bias (n = T), 1 scale (n = groups), 2 grads (n = N * T). One accumulator (one worker).
+double oracle_gboost_vgrad(const int kind, const int loss, const double param, const double* targets, const int64_t N,
+                           const int64_t T, const int32_t* cluster, const int64_t groups, const double* soutputs,
+                           const double* woutputs, const double* x, double* gx, const int64_t batch)
+{
+    const int64_t       n = (kind == 0) ? T : (kind == 1 ? groups : N * T);
+    std::vector<double> outputs(static_cast<size_t>(batch * T)), vgrads(static_cast<size_t>(batch * T));
+    std::vector<double> acc_g(static_cast<size_t>(kind == 2 ? 0 : n), 0.0);
+    double              acc_f = 0.0;
+    for (int64_t begin = 0; begin < N; begin += batch)
+    {
+        const int64_t end = std::min(N, begin + batch);
+        for (int64_t i = begin; i < end; ++i)
+        {
+            for (int64_t t = 0; t < T; ++t)
+            {
+                double o;
+                if (kind == 0)
+                {
+                    o = x[t]; // output = bias (function.cpp:102-103)
+                }
+                else if (kind == 1)
+                {
+                    const int32_t group = cluster[i];
+                    const double  scale = (group < 0) ? 0.0 : x[group]; // function.cpp:173-177
+                    o                   = soutputs[i * T + t] + scale * woutputs[i * T + t];
+                }
+                else
+                {
+                    o = x[i * T + t];
+                }
+                outputs[static_cast<size_t>((i - begin) * T + t)] = o;
+            }
+        }
+        double batch_f = 0.0; // accumulator.m_loss_fx.sum()
+        for (int64_t i = begin; i < end; ++i)
+        {
+            batch_f += loss_value<double>(loss, param, targets + i * T, outputs.data() + (i - begin) * T, T);
+        }
+        acc_f += batch_f;
+        if (gx != nullptr)
+        {
+            for (int64_t i = begin; i < end; ++i)
+            {
+                double* g = vgrads.data() + (i - begin) * T;
+                loss_vgrad<double>(loss, param, targets + i * T, outputs.data() + (i - begin) * T, T, g);
+                if (kind == 2)
+                {
+                    for (int64_t t = 0; t < T; ++t)
+                    {
+                        gx[i * T + t] = g[t] / static_cast<double>(N); // grads.vector() / denom (function.cpp:36)
+                    }
+                }
+            }
+            if (kind == 0)
+            {
+                // m_gx += gmatrix.colwise().sum() (function.cpp:112-114): per batch, rows in order
+                for (int64_t t = 0; t < T; ++t)
+                {
+                    double column = 0.0;
+                    for (int64_t i = begin; i < end; ++i)
+                    {
+                        column += vgrads[static_cast<size_t>((i - begin) * T + t)];
+                    }
+                    acc_g[static_cast<size_t>(t)] += column;
+                }
+            }
+            else if (kind == 1)
+            {
+                for (int64_t i = begin; i < end; ++i) // function.cpp:188-200
+                {
+                    const int32_t group = cluster[i];
+                    if (group < 0)
+                    {
+                        continue;
+                    }
+                    acc_g[static_cast<size_t>(group)] += dot_plain(vgrads.data() + (i - begin) * T, woutputs + i * T, T);
+                }
+            }
+        }
+    }
+    if (gx != nullptr && kind != 2)
+    {
+        for (int64_t k = 0; k < n; ++k)
+        {
+            gx[k] = acc_g[static_cast<size_t>(k)] / static_cast<double>(N);
+        }
+    }
+    return acc_f / static_cast<double>(N);
+}
+
 int oracle_hardware_threads(void)
 {
     const auto n = std::thread::hardware_concurrency();

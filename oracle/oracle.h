@@ -119,6 +119,13 @@ void oracle_upscale(const double* istats, int iscaling, const double* tstats, in
 /* make_samples (src/function/mlearn/ridge.cpp:23-26) */
 int64_t oracle_synth_samples(int64_t dims, double sratio);
 
+/* gboost::bias_function_t / scale_function_t / grads_function_t::do_eval (src/gboost/function.cpp:26-50, 85-126, 151-223)
+ * over targets[N,T] (+ cluster[N], soutputs / woutputs[N,T] for the scale function); kind: 0 bias (n = T), 1 scale
+ * (n = groups), 2 grads (n = N * T); gx nullable; `batch` rows per targets_iterator_t::loop range. */
+double oracle_gboost_vgrad(int kind, int loss, double param, const double* targets, int64_t N, int64_t T,
+                           const int32_t* cluster, int64_t groups, const double* soutputs, const double* woutputs,
+                           const double* x, double* gx, int64_t batch);
+
 int oracle_hardware_threads(void);
 
 #ifdef __cplusplus

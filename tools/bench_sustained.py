@@ -64,6 +64,17 @@ def main():
         time.sleep(1.5)  # cool-down: every configuration starts from a similar state
         function.enable_timing(True)
         function.pass_stats(reset=True)
+        # burst exactly as bench.py times it: 5 warm-up launches after the idle period, then 20 timed ones
+        for _ in range(5):
+            function.vgrad_device(x_dev.data_ptr(), g_ptr, f_dev.data_ptr())
+        function.sync()
+        function.pass_stats(reset=True)
+        for _ in range(20):
+            function.vgrad_device(x_dev.data_ptr(), g_ptr, f_dev.data_ptr())
+        function.sync()
+        burst = function.pass_samples()
+        function.pass_stats(reset=True)
+        time.sleep(1.5)
         batches = []
         t_start = time.perf_counter()
         while time.perf_counter() - t_start < args.seconds:
@@ -82,7 +93,11 @@ def main():
         bytes_alg = 8 * rows * features + 8 * rows + 16 * (features + 1)
         print(json.dumps({
             "rows": rows, "features": features, "loss": loss, "value_only": bool(args.value_only),
-            "kernel": function.describe(), "first_batch_us": round(batches[0][1], 1), "steady_us": round(steady, 1),
+            "kernel": function.describe(), "burst_us_median": round(1e3 * float(np.median(burst)), 1),
+            "burst_us_mean": round(1e3 * float(np.mean(burst)), 1),
+            "burst_gbs": round(bytes_alg / float(np.mean(burst)) / 1e6, 1),
+            "first_batch_us": round(batches[0][1], 1), "steady_us": round(steady, 1),
+            "batches_us": [round(b[1], 1) for b in batches[:6]],
             "first_gbs": round(bytes_alg / batches[0][1] / 1e3, 1), "steady_gbs": round(bytes_alg / steady / 1e3, 1),
             "steady_sm_mhz": float(np.median(sm)) if sm else None, "steady_power_w": float(np.median(pw)) if pw else None,
             "launches": 25 * len(batches)}), flush=True)
