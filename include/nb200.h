@@ -317,6 +317,19 @@ NB200_API int nb200_cgd_minimize(nb200_obj* obj, double* x, int64_t n, int beta,
                                  double orthotest, double eta, int64_t n_global, nb200_allreduce_fn allreduce,
                                  void* allreduce_user, double* fx, double* gradient_test, int64_t* stats, int* status);
 
+/* nano::solver_osga_t::do_minimize (src/solver/osga.cpp:59-147; the non-smooth driver: hinge / mae losses, lasso and
+ * elastic-net regularisation) with z0, xb, x, x', g, h and h_hat resident in HBM: per iteration one f(x, g), one
+ * value-only f(x'), two small kernels for the O(n) algebra (u = U(gamma, h) is never materialised) and a handful of
+ * scalars through mapped memory; the parameter update (alpha, eta, gamma) and the stopping tests (eta < epsilon; the
+ * value / patience test of src/solver/track.cpp:24-59) run on the host. lambda, alpha_max, kappa_prime, kappa: the
+ * solver::osga::* parameters (defaults 0.9, 0.7, 0.1, 1.1); strong_convexity: function_t::strong_convexity().
+ * x: in = x0, out = the best point. Sharded: connected peers (n_global = all samples) or a device group.
+ * stats = {fcalls, gcalls, iterations}; status: 0 max_evals, 1 gradient test, 2 eta < epsilon, 3 value test, 4 failed. */
+NB200_API int nb200_osga_minimize(nb200_obj* obj, double* x, int64_t n, double epsilon, int64_t max_evals,
+                                  int64_t patience, double lambda, double alpha_max, double kappa_prime, double kappa,
+                                  double strong_convexity, int64_t n_global, double* fx, double* eta, int64_t* stats,
+                                  int* status);
+
 /* ---- gradient-boosting cousins of the linear objective ---------------------------------------------
  * The same per-sample loss value / vgrad and accumulate-then-sum_reduce structure, without a feature matrix:
  *   NB200_GBOOST_BIAS   gboost::bias_function_t  (src/gboost/function.cpp:67-126):  f(x) = mean_i loss(y_i, x), n = T

@@ -77,6 +77,10 @@ SIGNATURES = {
     "nb200_cgd_minimize": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.c_int, ctypes.c_double, c_i64,
                                           ctypes.c_double, ctypes.c_double, c_i64, ctypes.c_void_p, ctypes.c_void_p,
                                           c_double_p, c_double_p, ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int)]),
+    "nb200_osga_minimize": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i64, ctypes.c_double, c_i64, c_i64,
+                                           ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                           ctypes.c_double, c_i64, c_double_p, c_double_p, ctypes.POINTER(c_i64),
+                                           ctypes.POINTER(ctypes.c_int)]),
     "nb200_gboost_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p, c_i64,
                                            c_i64, ctypes.POINTER(ctypes.c_int32), c_i64, c_double_p, c_double_p,
                                            c_void_pp]),

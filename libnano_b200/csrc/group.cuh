@@ -126,13 +126,13 @@ inline int group_enqueue_eval(nb200_obj* group, const double* x_dev, const bool 
 
 // evaluation entry of the device-resident solvers: a plain objective or a group
 inline int solver_enqueue_eval(nb200_obj* obj, nb200_obj* group, const double* x_dev, const int64_t n_global,
-                               double* gx_out, double* fx_out)
+                               double* gx_out, double* fx_out, const bool want_grad = true)
 {
     if (group != nullptr)
     {
-        return group_enqueue_eval(group, x_dev, true, n_global, gx_out, fx_out);
+        return group_enqueue_eval(group, x_dev, want_grad, n_global, gx_out, fx_out);
     }
     // one launch; with connected peers the cross-rank all-reduce is part of it (vgrad_t1.cuh)
-    return enqueue_eval(obj, x_dev, true, true, n_global, gx_out, fx_out, obj->peer_world > 1);
+    return enqueue_eval(obj, x_dev, want_grad, true, n_global, want_grad ? gx_out : nullptr, fx_out, obj->peer_world > 1);
 }
 } // namespace nb200

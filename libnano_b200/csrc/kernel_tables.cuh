@@ -24,6 +24,7 @@ struct t1_variant
 
 using mt_fwd_kernel_t = void (*)(const mt_forward_params);
 using mt_bwd_kernel_t = void (*)(const mt_backward_params);
+using mt_tma_kernel_t = void (*)(const mt_forward_params, const CUtensorMap);
 
 struct mt_variant
 {
@@ -31,6 +32,8 @@ struct mt_variant
     mt_fwd_kernel_t grad;
     mt_fwd_kernel_t value;
     mt_bwd_kernel_t backward;
+    mt_tma_kernel_t grad_tma;  // forward with the X tile fed through a tensor map and the epilogue on its own warps
+    mt_tma_kernel_t value_tma;
 };
 
 using ft_kernel_t = void (*)(const ft_params);

@@ -64,6 +64,10 @@ struct nb200_data
     // a dataset on a device group: rows [row0[r], row0[r + 1]) live on parts[r] (X, Y above stay null)
     std::vector<nb200_data*> parts;
     std::vector<int64_t>     row0;
+    // tensor map of X for the many-target forward (box = 16 features x 128 rows, 128-byte swizzle); x_map_ok == false
+    // (odd D, or the driver refused) keeps the cp.async-fed kernel
+    CUtensorMap x_map{};
+    bool        x_map_ok{false};
 };
 
 namespace
@@ -152,7 +156,7 @@ bool plan_ft(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         }
         plan.variant        = v;
         plan.rows_per_stage = static_cast<int>(rps);
-        plan.stages         = static_cast<int>(std::min<int64_t>(stages, 3)); // deeper rings bought nothing for T = 1
+        plan.stages         = static_cast<int>(std::min<int64_t>(stages, env_int("NB200_FT_STAGES", 3)));
         plan.stage_stride   = static_cast<int>(stride);
         plan.y_offset       = static_cast<int>(x_bytes);
         plan.smem_bytes     = static_cast<int>(kFtHeaderSize + plan.stages * stride);
@@ -197,7 +201,8 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         const int64_t y_bytes  = round_up(kFdRows * T * 8, 128);
         const int64_t stride   = round_up(x_bytes + y_bytes, 128);
         const int64_t offset   = var.header + w_bytes;
-        const int64_t stages   = std::min<int64_t>(kFdMaxStages, (smem_optin - offset) / stride);
+        const int64_t stages   = std::min<int64_t>(std::min<int64_t>(kFdMaxStages, env_int("NB200_FD_STAGES", kFdMaxStages)),
+                                                 (smem_optin - offset) / stride);
         if (stages < 2)
         {
             return false;
@@ -223,6 +228,7 @@ struct mt_geometry
 {
     int variant{0};
     int fwd_grid{0}, fwd_stages{0}, fwd_smem{0};
+    int tma_stages{0}, tma_smem{0}; // the tensor-map-fed forward (0 stages: does not fit)
     int splits{0}, bwd_grid{0}, bwd_stages{0}, bwd_smem{0}, t_ld{0};
 };
 
@@ -268,6 +274,17 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     geo.fwd_grid   = static_cast<int>(std::min<int64_t>((N + kMtBM - 1) / kMtBM, sm_count));
     geo.fwd_stages = static_cast<int>(fwd_stages);
     geo.fwd_smem   = static_cast<int>(fwd_header + fwd_stages * fwd_stage);
+    // tensor-map-fed forward: barriers, the [64][TP + 2] output tile (1 KiB granules: the stages behind it are 128-byte
+    // swizzle atoms), then stages of a dense X tile + the packed W tile
+    const int64_t tma_otile = round_up((kMtBM / 2) * (TP + 2) * 8, 1024);
+    const int64_t tma_stage = kMtXTileBytes + round_up(TP * kMtLd * 8, 1024);
+    int64_t       tma_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - kMtTmaHeader - tma_otile) / tma_stage);
+    if (const int forced = env_int("NB200_MT_STAGES", 0); forced >= 2)
+    {
+        tma_stages = std::min<int64_t>(tma_stages, forced);
+    }
+    geo.tma_stages = tma_stages >= 2 ? static_cast<int>(tma_stages) : 0;
+    geo.tma_smem   = static_cast<int>(kMtTmaHeader + tma_otile + std::max<int64_t>(tma_stages, 0) * tma_stage);
     geo.splits     = static_cast<int>(splits);
     geo.bwd_grid   = static_cast<int>(ctiles * splits);
     geo.bwd_stages = static_cast<int>(bwd_stages);
@@ -339,7 +356,11 @@ bool plan_t1(const int v, const int64_t N, const int64_t D, const int sm_count, 
     const int64_t avail    = static_cast<int64_t>(smem_optin) - kT1HeaderSize - w_bytes;
     const int64_t row_b    = D * 8;
     const int64_t target   = env_int("NB200_STAGE_BYTES", 65536);
-    const int     stages_x = env_int("NB200_STAGES", kT1MaxStages);
+    // TWO stages of ~64 KiB in flight per SM: measured on B200 (profiles/r02_stages_sweep.jsonl), a third stage costs
+    // 5-8 % of the bandwidth at full clocks for every width (7.28 -> 6.8 TB/s: 28 MB of evict-first lines in flight over
+    // the 148 SMs instead of 19 MB) and buys nothing at the power cap; 128 KiB covers latency x bandwidth per SM
+    // (~2 us x 49 GB/s = 98 KB). NB200_STAGES overrides (tuning).
+    const int     stages_x = env_int("NB200_STAGES", 2);
 
     int64_t rpg = std::max<int64_t>(1, target / (NG * row_b));
     if (rpg > var.RW)
@@ -431,6 +452,7 @@ struct nb200_obj
     bool    use_mt{false};
     int     mt_variant{0}; // index into kMtVariants
     int     mt_fwd_grid{0}, mt_fwd_stages{0}, mt_fwd_smem{0};
+    bool    mt_tma{false}; // the forward runs mt_forward_tma_kernel (mt_fwd_stages / smem are then that kernel's)
     int     mt_splits{0}, mt_bwd_grid{0}, mt_bwd_stages{0}, mt_bwd_smem{0}, mt_t_ld{0};
 
     // fused cross-rank all-reduce over peer memory (single-target path): mailbox + flags, see vgrad_t1.cuh
@@ -609,16 +631,14 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         }
         else
         {
-            // measured on B200 (profiles/r01_sustained_*.jsonl): the board sits at its 1000 W power cap while it
-            // streams fp64 from HBM, so the variant with the fewest instructions per row wins the steady state —
-            // several rows per warp iteration (one reduction and one loss chain per RW rows), two alternating sets of
-            // four consumer warps for rows up to 4 KiB, four consumer warps for 8 KiB rows
-            // 8 KiB rows: four consumer warps with whole rows (27) are 6 % faster than rows split over warp pairs (37)
-            // while the board is cool — a solve on a shard of a few GiB ends before the power cap bites — and 7-10 %
-            // slower at the cap, where every evaluation of a large shard runs (2^23 rows: 10.33 vs 9.62 ms, profiles/);
-            // 37 does not need the exact width and wins clearly for D < 1024; 16 KiB rows: variant 39
-            const bool long_passes = static_cast<double>(N) * static_cast<double>(D) * 8.0 >= 16.0 * 1024 * 1024 * 1024;
-            const int  preferred[] = {36, 35, 34, 33, (D == 1024 && !long_passes) ? 27 : 37, 27, 39};
+            // measured on B200 (profiles/r01_sustained_*.jsonl, r02_variants_d1024.jsonl): the board sits at its 1000 W
+            // power cap while it streams fp64 from HBM, so the variant with the fewest instructions per row wins the
+            // steady state — several rows per warp iteration (one reduction and one loss chain per RW rows), two
+            // alternating sets of four consumer warps for rows up to 4 KiB, rows split over warp pairs (37) for rows up to
+            // 8 KiB, 16 KiB rows: variant 39. With two stages in flight these are also the fastest variants at full
+            // clocks (D = 1024, logistic: 37 runs 1.181 ms cool / 1.219 ms at the cap, whole-row variant 27 1.182 / 1.346),
+            // so one choice per width serves a single solve and a long tuner run alike.
+            const int preferred[] = {36, 35, 34, 33, 37, 27, 39};
             for (const int v : preferred)
             {
                 if (!ok)
@@ -690,8 +710,9 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         const mt_variant& var = kMtVariants[geo.variant];
         obj->mt_variant    = geo.variant;
         obj->mt_fwd_grid   = geo.fwd_grid;
-        obj->mt_fwd_stages = geo.fwd_stages;
-        obj->mt_fwd_smem   = geo.fwd_smem;
+        obj->mt_tma        = data->x_map_ok && geo.tma_stages >= 2 && env_int("NB200_MT_LEGACY_FORWARD", 0) == 0;
+        obj->mt_fwd_stages = obj->mt_tma ? geo.tma_stages : geo.fwd_stages;
+        obj->mt_fwd_smem   = obj->mt_tma ? geo.tma_smem : geo.fwd_smem;
         obj->mt_splits     = geo.splits;
         obj->mt_bwd_grid   = geo.bwd_grid;
         obj->mt_bwd_stages = geo.bwd_stages;
@@ -699,6 +720,11 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
         obj->mt_t_ld       = geo.t_ld;
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        if (obj->mt_tma)
+        {
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.tma_smem));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.value_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.tma_smem));
+        }
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials, static_cast<size_t>(geo.fwd_grid) * (1 + T) * sizeof(double)));
         NB200_CUDA_TRY(cudaMalloc(&obj->d_partials_gw, static_cast<size_t>(geo.splits) * T * D * sizeof(double)));
@@ -1097,7 +1123,15 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         f.y_broadcast     = 0;
         f.per_target_loss = 0;
         f.fb_stride       = static_cast<int>(1 + T);
-        (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
+        if (obj->mt_tma)
+        {
+            (want_grad ? var.grad_tma : var.value_tma)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(
+                f, data->x_map);
+        }
+        else
+        {
+            (want_grad ? var.grad : var.value)<<<obj->mt_fwd_grid, kMtThreads, obj->mt_fwd_smem, obj->stream>>>(f);
+        }
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;
         if (want_grad)
@@ -1423,6 +1457,7 @@ int make_group_objective(nb200_data* data, const int loss, const double loss_par
     } while (0)
 } // namespace
 #include "lbfgs.cuh"
+#include "osga.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // C ABI
@@ -1553,6 +1588,39 @@ void nb200_ctx_release(nb200_ctx* ctx)
     }
 }
 
+// Tensor map of X[N, D] for the many-target forward: a box of 16 features x 128 rows lands in shared memory as dense
+// 128-byte rows under the 128-byte swizzle; elements outside the matrix are filled with zeros. The encoder comes from
+// the driver through the runtime (libnb200.so does not link libcuda).
+static bool encode_x_map(const double* X, const int64_t N, const int64_t D, CUtensorMap* map)
+{
+    using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const encode_fn encode = []() -> encode_fn
+    {
+        void*                           entry = nullptr;
+        cudaDriverEntryPointQueryResult found = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &entry, cudaEnableDefault, &found) != cudaSuccess ||
+            found != cudaDriverEntryPointSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<encode_fn>(entry);
+    }();
+    if (encode == nullptr || D % 2 != 0 || N >= (1LL << 31) || D >= (1LL << 31))
+    {
+        return false; // (rows must start on 16-byte boundaries: the global stride is a multiple of 16 bytes)
+    }
+    const cuuint64_t dims[2]    = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * sizeof(double)};
+    const cuuint32_t box[2]     = {static_cast<cuuint32_t>(kMtBK), static_cast<cuuint32_t>(kMtBM)};
+    const cuuint32_t estrides[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(X), dims, strides, box, estrides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int alloc_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const int64_t T, nb200_data** out_data)
 {
     NB200_REQUIRE(ctx != nullptr && out_data != nullptr, "dataset: null argument");
@@ -1592,6 +1660,7 @@ static int alloc_dataset(nb200_ctx* ctx, const int64_t N, const int64_t D, const
         delete data;
         return fail(NB200_ERR_CUDA, std::string("dataset: cannot allocate HBM: ") + cudaGetErrorString(err));
     }
+    data->x_map_ok = encode_x_map(data->X, N, D, &data->x_map);
     *out_data = data;
     return NB200_OK;
 }
@@ -2698,7 +2767,7 @@ int nb200_probe_peak(nb200_ctx* ctx, const int kind, double* value)
         NB200_CUDA_TRY(cudaEventCreate(&e1));
         const int blocks = ctx->sm_count * 8, threads = 256;
         NB200_CUDA_TRY(cudaMalloc(&out, static_cast<size_t>(blocks) * threads * sizeof(double)));
-        constexpr int     kTile = 32768, kStages = 4;
+        constexpr int     kTile = 65536, kStages = 2;
         const int64_t     tiles = (4LL << 30) / kTile; // 4 GiB: far beyond L2
         const int         smem  = 128 + kStages * kTile;
         if (kind == NB200_PEAK_HBM_READ_GBS)
@@ -2821,7 +2890,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     }
     else if (obj->use_mt)
     {
-        text = "dmma NT8=" + std::to_string(kMtVariants[obj->mt_variant].NT8) + " fwd_grid=" +
+        text = std::string(obj->mt_tma ? "dmma-tma" : "dmma") + " NT8=" + std::to_string(kMtVariants[obj->mt_variant].NT8) + " fwd_grid=" +
                std::to_string(obj->mt_fwd_grid) + " fwd_stages=" + std::to_string(obj->mt_fwd_stages) +
                " fwd_smem=" + std::to_string(obj->mt_fwd_smem) + " bwd_grid=" + std::to_string(obj->mt_bwd_grid) +
                " splits=" + std::to_string(obj->mt_splits) + " bwd_stages=" + std::to_string(obj->mt_bwd_stages) +
@@ -2860,6 +2929,35 @@ int nb200_lbfgs_minimize(nb200_obj* obj, double* x, const int64_t n, const doubl
     }
     device_lbfgs_t solver(obj, n_global > 0 ? n_global : obj->data->N, allreduce, allreduce_user);
     return solver.run(x, epsilon, max_evals, history, fx, gradient_test, stats, status);
+}
+
+int nb200_osga_minimize(nb200_obj* obj, double* x, const int64_t n, const double epsilon, const int64_t max_evals,
+                        const int64_t patience, const double lambda, const double alpha_max, const double kappa_prime,
+                        const double kappa, const double strong_convexity, const int64_t n_global, double* fx,
+                        double* eta, int64_t* stats, int* status)
+{
+    NB200_REQUIRE(obj != nullptr && x != nullptr && fx != nullptr && eta != nullptr && stats != nullptr && status != nullptr,
+                  "osga: null argument");
+    NB200_REQUIRE(n == obj->n, "solver: incompatible initial point (" + std::to_string(n) + " dimensions), expecting " +
+                                   std::to_string(obj->n) + " dimensions!");
+    NB200_REQUIRE(epsilon > 0.0 && max_evals > 0 && patience > 0 && lambda > 0.0 && lambda < 1.0 && alpha_max > 0.0 &&
+                      alpha_max < 1.0 && kappa_prime > 0.0 && kappa_prime < kappa && strong_convexity >= 0.0,
+                  "osga: invalid parameters");
+    NB200_REQUIRE(n_global == 0 || n_global == obj->data->N || (obj->parts.empty() && obj->peer_world > 1),
+                  "osga: a sharded solve needs connected peers (or a device group)");
+    NB200_CUDA_TRY(cudaSetDevice(obj->device));
+    osga_params_t q;
+    q.epsilon          = epsilon;
+    q.max_evals        = max_evals;
+    q.patience         = patience;
+    q.lambda           = lambda;
+    q.alpha_max        = alpha_max;
+    q.kappa_prime      = kappa_prime;
+    q.kappa            = kappa;
+    q.strong_convexity = strong_convexity;
+    nb200_obj* const first = obj->parts.empty() ? obj : obj->parts[0];
+    device_osga_t    solver(first, obj->parts.empty() ? nullptr : obj, n_global > 0 ? n_global : obj->data->N);
+    return solver.run(x, q, fx, eta, stats, status);
 }
 
 int nb200_cgd_minimize(nb200_obj* obj, double* x, const int64_t n, const int beta, const double epsilon,

@@ -67,12 +67,12 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(double* out, const doub
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// read-only stream: every CTA pulls 32 KiB tiles through a 4-deep ring of 1-D bulk copies (the way the single-target
+// read-only stream: every CTA pulls 64 KiB tiles through a 2-deep ring of 1-D bulk copies (the way the single-target
 // kernel reads X) and touches one word per tile, so the bytes really arrive
 __global__ void __launch_bounds__(128) probe_read_kernel(const unsigned char* __restrict__ src, const int64_t tiles,
                                                          double* out)
 {
-    constexpr int kTile = 32768, kStages = 4;
+    constexpr int kTile = 65536, kStages = 2;
     extern __shared__ __align__(1024) unsigned char probe_smem[];
     uint64_t*      bars   = reinterpret_cast<uint64_t*>(probe_smem);
     unsigned char* stages = probe_smem + 128;

@@ -13,6 +13,8 @@
 // row is bound by the copy engine's request rate (measured: 9 TFLOP/s), so they travel as 16-byte cp.async chunks.
 #pragma once
 
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched from the driver at run time)
+
 #include "common.cuh"
 #include "loss.cuh"
 
@@ -30,6 +32,9 @@ constexpr int kMtProducerWarps = 4;   // a whole warpgroup, so that its register
 constexpr int kMtThreads       = (kMtWarps + kMtProducerWarps) * 32;
 constexpr int kMtProducerRegs  = 40;  // 384 threads x 168 registers at launch -> 128 x 40 + 256 x 232
 constexpr int kMtConsumerRegs  = 232;
+constexpr int kMtEpilogueRows     = 4;   // rows a warp evaluates together in the loss epilogue (independent fp64 chains)
+constexpr int kMtTmaHeader        = 1024; // barriers
+constexpr int kMtXTileBytes       = kMtBM * kMtBK * 8; // 128 rows x 128 bytes, dense, 128-byte swizzled
 
 struct mt_forward_params
 {
@@ -106,6 +111,159 @@ __device__ __forceinline__ double quad_max(double v)
     v        = (v < o) ? o : v;
     o        = __shfl_xor_sync(0xffffffffu, v, 2);
     return (v < o) ? o : v;
+}
+
+// Loss epilogue of `row_count` consecutive rows whose outputs sit in shared memory (row stride TPs): value, dL and
+// the per-lane column sums. kMtEpilogueRows rows are evaluated TOGETHER: one row at a time the epilogue is a chain of
+// dependent fp64 instructions (max -> exp -> sum -> log, or the elementwise loss) plus the latency of the targets'
+// global load, ~4900 cycles per row with the tensor pipe idle behind it (measured: 2.2 of the forward's 14.6 ms at
+// config 3); interleaved rows overlap those latencies. Lanes stride the targets (t = lane + 32 k).
+template <int TP, bool GRAD>
+__device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, const double* orows, const int64_t row_first,
+                                                 const int row_count, const int lane, double& fsum,
+                                                 double (&gbacc)[(TP + 31) / 32], double (&lossacc)[(TP + 31) / 32])
+{
+    constexpr int TPs = TP + 2;
+    constexpr int TL  = (TP + 31) / 32;
+    constexpr int R   = kMtEpilogueRows;
+    const int     T     = p.T;
+    const int     dl_ld = T + (T & 1);
+    for (int r0 = 0; r0 < row_count; r0 += R)
+    {
+        double y[R][TL];
+        bool   live[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+        {
+            live[j]            = r0 + j < row_count;
+            const int64_t row  = row_first + r0 + (live[j] ? j : 0);
+            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
+#pragma unroll
+            for (int k = 0; k < TL; ++k)
+            {
+                const int t = lane + 32 * k;
+                y[j][k]     = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
+            }
+        }
+        if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
+        {
+            // classnll.h:19-37
+            double omax[R], sumexp[R], dot[R];
+            double ex[R][TL];
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const double* orow = orows + (r0 + (live[j] ? j : 0)) * TPs;
+                omax[j]            = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < TL; ++k)
+                {
+                    const int t = lane + 32 * k;
+                    if (t < T)
+                    {
+                        omax[j] = max_of(omax[j], orow[t]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                omax[j] = warp_allreduce_max(omax[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const double* orow = orows + (r0 + (live[j] ? j : 0)) * TPs;
+                sumexp[j] = dot[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < TL; ++k)
+                {
+                    const int t = lane + 32 * k;
+                    ex[j][k]    = 0.0;
+                    if (t < T)
+                    {
+                        const double o = orow[t];
+                        ex[j][k]       = exp(__dsub_rn(o, omax[j]));
+                        sumexp[j] += ex[j][k];
+                        dot[j] += __dmul_rn(__dadd_rn(1.0, y[j][k]), o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                sumexp[j] = warp_allreduce_sum(sumexp[j]);
+                dot[j]    = warp_allreduce_sum(dot[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                if (live[j])
+                {
+                    fsum += __dadd_rn(__dsub_rn(log(sumexp[j]), __dmul_rn(0.5, dot[j])), omax[j]);
+                    if (GRAD)
+                    {
+                        const int64_t row = row_first + r0 + j;
+#pragma unroll
+                        for (int k = 0; k < TL; ++k)
+                        {
+                            const int t = lane + 32 * k;
+                            if (t < T)
+                            {
+                                const double gv =
+                                    __dsub_rn(__ddiv_rn(ex[j][k], sumexp[j]), __dmul_rn(0.5, __dadd_rn(1.0, y[j][k])));
+                                p.dL[row * dl_ld + t] = gv;
+                                gbacc[k] += gv;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const double* orow = orows + (r0 + (live[j] ? j : 0)) * TPs;
+                const int64_t row  = row_first + r0 + j;
+                double        sum  = 0.0;
+#pragma unroll
+                for (int k = 0; k < TL; ++k)
+                {
+                    const int t = lane + 32 * k;
+                    if (t < T && live[j])
+                    {
+                        double term, gv;
+                        loss_term<GRAD>(p.loss, p.loss_param, y[j][k], orow[t], term, gv);
+                        sum += term;
+                        lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
+                        if (GRAD)
+                        {
+                            p.dL[row * dl_ld + t] = gv;
+                            gbacc[k] += gv;
+                        }
+                    }
+                }
+                sum = warp_allreduce_sum(sum);
+                if (live[j])
+                {
+                    fsum += loss_post(p.loss, sum);
+                }
+            }
+        }
+        if (GRAD && dl_ld != T && lane == 0)
+        {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                if (live[j])
+                {
+                    p.dL[(row_first + r0 + j) * dl_ld + T] = 0.0; // the pad column of an odd T
+                }
+            }
+        }
+    }
 }
 
 template <int NT8, bool GRAD>
@@ -272,94 +430,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
         const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
         const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
-        for (int r = 0; r < row_count; ++r)
-        {
-            const int64_t row  = row_first + r;
-            double*       orow = orows + r * TPs;
-            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
-            double        y[TL]; // (fetching the next row's targets one row ahead was measured: no gain)
-#pragma unroll
-            for (int k = 0; k < TL; ++k)
-            {
-                const int t = lane + 32 * k;
-                y[k]        = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
-            }
-
-            if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
-            {
-                // classnll.h:19-37
-                double omax = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < TL; ++k)
-                {
-                    const int t = lane + 32 * k;
-                    if (t < T)
-                    {
-                        omax = max_of(omax, orow[t]);
-                    }
-                }
-                omax = warp_allreduce_max(omax);
-                double ex[TL];
-                double sumexp = 0.0, dot = 0.0;
-#pragma unroll
-                for (int k = 0; k < TL; ++k)
-                {
-                    const int t = lane + 32 * k;
-                    ex[k]       = 0.0;
-                    if (t < T)
-                    {
-                        const double o = orow[t];
-                        ex[k]          = exp(__dsub_rn(o, omax));
-                        sumexp += ex[k];
-                        dot += __dmul_rn(__dadd_rn(1.0, y[k]), o);
-                    }
-                }
-                sumexp = warp_allreduce_sum(sumexp);
-                dot    = warp_allreduce_sum(dot);
-                fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                if (GRAD)
-                {
-#pragma unroll
-                    for (int k = 0; k < TL; ++k)
-                    {
-                        const int t = lane + 32 * k;
-                        if (t < T)
-                        {
-                            const double gv =
-                                __dsub_rn(__ddiv_rn(ex[k], sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y[k])));
-                            p.dL[row * dl_ld + t] = gv;
-                            gbacc[k] += gv;
-                        }
-                    }
-                }
-            }
-            else
-            {
-                double sum = 0.0;
-#pragma unroll
-                for (int k = 0; k < TL; ++k)
-                {
-                    const int t = lane + 32 * k;
-                    if (t < T)
-                    {
-                        double term, gv;
-                        loss_term<GRAD>(p.loss, p.loss_param, y[k], orow[t], term, gv);
-                        sum += term;
-                        lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
-                        if (GRAD)
-                        {
-                            p.dL[row * dl_ld + t] = gv;
-                            gbacc[k] += gv;
-                        }
-                    }
-                }
-                fsum += loss_post(p.loss, warp_allreduce_sum(sum));
-            }
-            if (GRAD && dl_ld != T && lane == 0)
-            {
-                p.dL[row * dl_ld + T] = 0.0; // the pad column of an odd T
-            }
-        }
+        mt_epilogue_rows<TP, GRAD>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
         __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
         }
     }
@@ -391,6 +462,219 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
         for (int q = 0; q < kMtWarps; ++q)
         {
             sum += fold[q * kFold + src];
+        }
+        out[c] = sum;
+    }
+}
+
+// 2-D tiled copy global -> shared through a tensor map (the TMA engine proper; SASS UTMALDG): box = 16 features x 128
+// rows of X, rows and columns past the matrix come back as zeros, completion as transaction bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, const int c0, const int c1,
+                                            uint64_t* bar, const uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+                 "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+// The forward contraction fed by the tensor-map engine: ONE lane issues, per k-chunk, one 2-D tiled copy of the X tile
+// (128 rows x 16 features = dense 128-byte rows under the 128-byte swizzle; rows / columns past the matrix arrive as
+// zeros, so nothing is masked) and one bulk copy of the packed W tile — instead of 128 threads issuing 1024 16-byte
+// cp.async chunks per stage. Fragment rows are permuted — lane group g reads tile row (g % 4) * 2 + g / 4 — so that
+// with the swizzle (16-byte chunk index ^= row % 8) both half-warps of every 64-bit A-fragment load hit 16 distinct
+// 8-byte slots. The epilogue stays on the consumer warps, each on its own 16 rows (no cross-warp synchronisation): a
+// variant with the epilogue on dedicated warps, overlapped with the next tile's DMMAs, was measured SLOWER — the loss's
+// fp64 instructions share the FP64 unit with the DMMAs, and behind a saturated DMMA queue every one of them waited
+// ~130 cycles (profiles/r02_mt_forward_roles.jsonl).
+template <int NT8, bool GRAD>
+__global__ void __launch_bounds__(kMtThreads, 1)
+    mt_forward_tma_kernel(const mt_forward_params p, const __grid_constant__ CUtensorMap x_map)
+{
+    constexpr int TP    = NT8 * 8;
+    constexpr int TPs   = TP + 2;  // row stride of the output tile
+    constexpr int TL    = (TP + 31) / 32;
+    constexpr int kFold = 8 * TPs; // distance between the warps' fold rows (each inside that warp's 8 tile rows)
+    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit 8 tile rows");
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + kMtMaxStages;
+    constexpr int kOtileBytes = ((kMtBM / 2) * TPs * 8 + 1023) / 1024 * 1024;
+    double*        otile  = reinterpret_cast<double*>(smem + kMtTmaHeader); // [64][TPs]: 8 rows per warp at a time
+    unsigned char* stage0 = smem + kMtTmaHeader + kOtileBytes;              // 1 KiB aligned (swizzle atom)
+    const int      T      = p.T;
+    const int      D      = p.D;
+    const int      w_bytes = T * kMtLd * 8;
+    // the W region holds all TP padded rows (the fragment loads of the rows past T read stale shared memory whose
+    // products land in accumulator columns nobody looks at — it must still be this CTA's shared memory), and every
+    // stage starts on a 1 KiB boundary: the swizzle is a function of the shared-memory ADDRESS bits
+    constexpr int  stage_bytes = kMtXTileBytes + (TP * kMtLd * 8 + 1023) / 1024 * 1024;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < p.stages; ++s)
+        {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, kMtWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int     kchunks = (D + kMtBK - 1) / kMtBK;
+    const int64_t tiles   = (p.N + kMtBM - 1) / kMtBM;
+
+    if (warp >= kMtWarps)
+    {
+        // ===== producer warpgroup: one lane, two copies per stage =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMtProducerRegs));
+        if (warp == kMtWarps && lane == 0)
+        {
+            const uint64_t policy_x = l2_policy_evict_first();
+            const uint64_t policy_w = l2_policy_evict_last();
+            int            s        = 0;
+            uint32_t       phase    = 1; // the first lap passes at once
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+            {
+                const int row0 = static_cast<int>(tile * kMtBM);
+                for (int kc = 0; kc < kchunks; ++kc)
+                {
+                    mbar_wait(empty_bar + s, phase);
+                    unsigned char* xs = stage0 + static_cast<int64_t>(s) * stage_bytes;
+                    mbar_arrive_expect_tx(full_bar + s, static_cast<uint32_t>(kMtXTileBytes + w_bytes));
+                    tma_load_2d(xs, &x_map, kc * kMtBK, row0, full_bar + s, policy_x);
+                    bulk_copy_g2s(xs + kMtXTileBytes, p.W + static_cast<int64_t>(kc) * T * kMtLd,
+                                  static_cast<uint32_t>(w_bytes), full_bar + s, policy_w);
+                    if (++s == p.stages)
+                    {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps: rows [warp*16, warp*16 + 16) of the tile, all targets =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMtConsumerRegs));
+    const int g   = lane >> 2;
+    const int tig = lane & 3;
+    const int rho = (g & 3) * 2 + (g >> 2); // tile row (within an m8 tile) served by this lane group
+    // byte offset of this lane's A element in k-step kk: row * 128 + ((chunk ^ rho) << 4) + (tig & 1) * 8 with
+    // chunk = 2 kk + (tig >> 1)  (rho == row % 8: the warp's rows start at a multiple of 8)
+    const int a_row = (warp * 16 + rho) * 128 + (tig & 1) * 8;
+    const int a_hi  = tig >> 1;
+
+    double gbacc[TL], lossacc[TL];
+#pragma unroll
+    for (int k = 0; k < TL; ++k)
+    {
+        gbacc[k] = lossacc[k] = 0.0;
+    }
+    double fsum = 0.0;
+
+    int      s     = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        double acc[2][NT8][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+        {
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+                acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            }
+        }
+
+        for (int kc = 0; kc < kchunks; ++kc)
+        {
+            mbar_wait(full_bar + s, phase);
+            const unsigned char* xs = stage0 + static_cast<int64_t>(s) * stage_bytes;
+            const double*        wb = reinterpret_cast<const double*>(xs + kMtXTileBytes) + g * kMtLd + tig;
+#pragma unroll
+            for (int kk = 0; kk < kMtBK / 4; ++kk)
+            {
+                const int    off = a_row + (((2 * kk + a_hi) ^ rho) << 4);
+                const double a0  = *reinterpret_cast<const double*>(xs + off);
+                const double a1  = *reinterpret_cast<const double*>(xs + off + 8 * 128);
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+                    const double bv = wb[nt * 8 * kMtLd + kk * 4];
+                    dmma_m8n8k4(acc[0][nt][0], acc[0][nt][1], a0, bv);
+                    dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, bv);
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+            {
+                mbar_arrive(empty_bar + s);
+            }
+            if (++s == p.stages)
+            {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+
+        // ----- epilogue: accumulator fragments (+ bias) -> this warp's 8 rows of the shared output tile (the two m8
+        //       tiles take turns), then the row-wise loss over them -----
+        double* orows = otile + (warp * 8) * TPs;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+        {
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+                const int    col = nt * 8 + tig * 2;
+                const double b0  = (col < T) ? p.b[col] : 0.0;
+                const double b1  = (col + 1 < T) ? p.b[col + 1] : 0.0;
+                *reinterpret_cast<double2*>(orows + rho * TPs + col) =
+                    make_double2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
+            }
+            __syncwarp();
+            const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
+            const int     row_count =
+                static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
+            mt_epilogue_rows<TP, GRAD>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
+            __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
+        }
+    }
+
+    // ----- fold the 8 consumer warps in warp order (the output tile is dead: it hosts the per-warp fold rows) -----
+    double* mine = otile + warp * kFold;
+    if (lane == 0)
+    {
+        mine[0] = fsum; // identical on every lane
+    }
+#pragma unroll
+    for (int k = 0; k < TL; ++k)
+    {
+        const int t = lane + 32 * k;
+        if (t < TP)
+        {
+            mine[1 + t]      = GRAD ? gbacc[k] : 0.0;
+            mine[1 + TP + t] = lossacc[k];
+        }
+    }
+    named_bar_sync(1, kMtWarps * 32);
+    double*   out   = p.partials_fb + static_cast<int64_t>(blockIdx.x) * p.fb_stride;
+    const int ncols = p.per_target_loss ? (1 + 2 * T) : (GRAD ? 1 + T : 1);
+    for (int c = threadIdx.x; c < ncols; c += kMtWarps * 32)
+    {
+        const int src = (c <= T) ? c : (1 + TP + (c - 1 - T)); // [loss | dL sums | per-target loss sums]
+        double    sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kMtWarps; ++q)
+        {
+            sum += otile[q * kFold + src];
         }
         out[c] = sum;
     }

@@ -242,7 +242,9 @@ class FitResult:
         return self.params.shape[0]
 
     def add(self, params):
-        params = np.asarray(params, dtype=np.float64).reshape(-1, len(self.param_names))
+        params = np.asarray(params, dtype=np.float64)
+        # (a model without hyper-parameters still has trials: rows of zero columns)
+        params = params.reshape(-1, len(self.param_names)) if self.param_names else params.reshape(params.shape[0], 0)
         count = params.shape[0]
         self.params = np.concatenate([self.params, params])
         self.train = np.concatenate([self.train, np.full((count, self.folds, 2), np.nan)])
@@ -310,33 +312,49 @@ class LinearModel:
 
     def fit(self, ctx, X, Y, loss, samples=None, solver=None, folds: int = 5, seed: int = 42,
             tuner_max_evals: int = 100, tuner: str = "local-search", splitter: str = "k-fold",
-            batch_trials: bool = False, _backend=None) -> FitResult:
+            batch_trials: bool | None = None, _backend=None) -> FitResult:
         """linear_t::fit (src/linear.cpp:79-116). X[N, D], Y[N, T] host arrays; `loss`: Loss or its id; `solver`:
         callable (function, x0) -> dict with "x" (default_solver); `tuner`: "local-search" or "surrogate" (the reference's
         default, src/machine/params.cpp:11); `batch_trials`: solve the trials the tuner asks for together on each fold
         with solver.lbfgs_batch - ONE pass over X per round for all of them (nb200_vgrad_batch) - when the objective
-        is smooth (l1reg = 0, smooth loss, one target); returns the FitResult, keeps (weights, bias)."""
+        is smooth (l1reg = 0, smooth loss, one target). None (the default) batches whenever that applies and no custom
+        `solver` was given; returns the FitResult, keeps (weights, bias).
+
+        A model without hyper-parameters ("ordinary") is still cross-validated once over the folds, like ml::tune does
+        (its callback runs with one parameter-free trial, src/machine/tune.cpp:48-52), so the result always carries
+        train / validation statistics."""
         backend = _backend or _DeviceBackend(ctx)
         loss = Loss(loss) if isinstance(loss, str) else loss
+        if batch_trials is None:
+            batch_trials = solver is None
         solver = solver or default_solver
         X = np.ascontiguousarray(X, dtype=np.float64)
         Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
         samples = np.arange(X.shape[0]) if samples is None else np.asarray(samples, dtype=np.int64)
         spaces = self.make_param_spaces()
-        result = FitResult(MODELS[self.kind], folds if spaces else 0)
+        result = FitResult(MODELS[self.kind], folds)
 
-        if spaces:
+        if folds > 0:
             critical(splitter in SPLITTERS, "splitter: unknown id <", splitter, ">")
             splits = SPLITTERS[splitter](samples, folds, seed)
-            # per fold, pinned once for all the trials: the scaled training samples (what the objective reads) and
-            # both splits unscaled (the upscaled model is evaluated on them)
+            # per fold, pinned once for all the trials: the scaled training samples (what the objective reads) and the
+            # splits unscaled (the upscaled model is evaluated on them). Class targets are never scaled, so there the
+            # training statistics come from the scaled copy and the model in the scaled space (the outputs are the
+            # same numbers: upscale is the inverse map) and the unscaled training split is not pinned a second time.
             scaled_sets = [self._prepare(backend, loss, X[train], Y[train]) for train, _ in splits]
-            train_sets = [backend.pin(X[train], Y[train]) for train, _ in splits]
+            targets_scaled = loss.error_kind == ERROR_ABSDIFF and self.scaling != "none"
+            train_sets = [backend.pin(X[train], Y[train]) for train, _ in splits] if targets_scaled else None
             valid_sets = [backend.pin(X[valid], Y[valid]) for _, valid in splits]
 
             def store(trial, fold, W, b, x):
                 result.extras[trial][fold] = x
-                result.train[trial, fold] = train_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                if train_sets is not None:
+                    result.train[trial, fold] = train_sets[fold].evaluate(loss, W, b).mean(axis=1)
+                else:
+                    isize, tsize = scaled_sets[fold].inputs, scaled_sets[fold].targets
+                    x = np.asarray(x)
+                    result.train[trial, fold] = scaled_sets[fold].evaluate(
+                        loss, x[:isize * tsize].reshape(tsize, isize), x[isize * tsize:]).mean(axis=1)
                 result.valid[trial, fold] = valid_sets[fold].evaluate(loss, W, b).mean(axis=1)
 
             def batched_callback(new_params, old_trials):
@@ -373,10 +391,11 @@ class LinearModel:
                         store(old_trials + trial, fold, W, b, state["x"])
                 return [result.value(trial) for trial in range(old_trials, result.trials())]
 
-            tune(spaces, callback, tuner_max_evals, tuner)
+            if spaces:
+                tune(spaces, callback, tuner_max_evals, tuner)
+            else:
+                callback(np.zeros((1, 0)))                     # no hyper-parameters: one trial over the folds
             params = result.params[result.optimum_trial()]
-        else:
-            params = np.zeros(0)
 
         # refit with the optimum hyper-parameters on all the given samples (linear.cpp:99-112)
         W, b, state = self._fit_once(backend, loss, solver, self._prepare(backend, loss, X[samples], Y[samples]), params)

@@ -147,11 +147,11 @@ def test_device_resident_lbfgs_contract(ctx):
         lbfgs(function, np.zeros(4))
 
 
-def test_host_driven_osga_matches_the_restated_driver(ctx, oracle):
-    # libnano_b200.solver.osga and oracle/solvers.cpp restate the same algorithm independently: same GPU objective,
-    # same start => the same trajectory up to rounding
+def test_device_resident_osga_matches_the_restated_driver(ctx, oracle):
+    # nb200_osga_minimize (every vector in HBM), libnano_b200.solver.osga_host (numpy vectors) and oracle/solvers.cpp
+    # restate the same algorithm independently: same GPU objective, same start => the same trajectory up to rounding
     import libnano_b200 as nb
-    from libnano_b200.solver import osga
+    from libnano_b200.solver import osga, osga_host
 
     N, D = 3000, 16
     X, Y, _ = make_problem(5, N, D, 1, True)
@@ -164,6 +164,31 @@ def test_host_driven_osga_matches_the_restated_driver(ctx, oracle):
         assert abs(mine["iterations"] - ref["iterations"]) <= max(2, ref["iterations"] // 20)
         assert abs(mine["fx"] - ref["fx"]) <= 1e-6 * (1 + abs(ref["fx"]))
         assert mine["fcalls"] == 2 * mine["iterations"] + 1 and mine["gcalls"] == mine["iterations"] + 1
+        assert gpu.fcalls() == mine["fcalls"] and gpu.gcalls() == mine["gcalls"]
+        host = osga_host(gpu.clone(), x0, epsilon=1e-6, max_evals=2000)
+        assert host["status"] == mine["status"]
+        assert abs(host["iterations"] - mine["iterations"]) <= max(2, mine["iterations"] // 20)
+        assert abs(host["fx"] - mine["fx"]) <= 1e-6 * (1 + abs(mine["fx"]))
+        assert np.max(np.abs(host["x"] - mine["x"])) <= 1e-3
+
+
+def test_device_resident_osga_on_a_device_group(oracle):
+    # the same solve with the samples split over a device group (one device serving twice on a one-GPU box)
+    import libnano_b200 as nb
+    from libnano_b200.solver import osga
+    from test_gpu_group import group_devices
+
+    X, Y, _ = make_problem(6, 5000, 32, 1, True)
+    whole_ctx, group_ctx = nb.Context(0), nb.Context(group_devices(2))
+    whole = nb.LinearFunction(nb.Dataset.pin(whole_ctx, X, Y), nb.Loss("s-hinge"), 1e-2, 1e-2)
+    split = nb.LinearFunction(nb.Dataset.pin(group_ctx, X, Y), nb.Loss("s-hinge"), 1e-2, 1e-2)
+    a = osga(whole, np.zeros(33), epsilon=1e-6, max_evals=3000)
+    b = osga(split, np.zeros(33), epsilon=1e-6, max_evals=3000)
+    assert a["status"] == b["status"] and abs(a["fx"] - b["fx"]) <= 1e-6 * (1 + abs(a["fx"]))
+    with pytest.raises(RuntimeError, match="incompatible initial point"):
+        osga(split, np.zeros(5))
+    group_ctx.close()
+    whole_ctx.close()
 
 
 @pytest.mark.parametrize("loss_id,l1,l2", [("s-hinge", 1e-2, 0.0), ("s-hinge", 1e-2, 1e-2), ("mae", 1e-2, 0.0)])

@@ -33,6 +33,14 @@ class OracleDataset:
         self.istats = self.tstats = None
         self.iscaling = self.tscaling = "none"
 
+    @property
+    def inputs(self):
+        return self.X.shape[1]
+
+    @property
+    def targets(self):
+        return self.Y.shape[1]
+
     def scale(self, inputs="standard", targets="none"):
         self.istats, self.tstats = self.oracle.scalar_stats(self.X), self.oracle.scalar_stats(self.Y)
         self.iscaling, self.tscaling = inputs, targets
@@ -329,7 +337,10 @@ def test_ordinary_fit_recovers_the_generating_model(oracle, scaling):
     X, Y, W, b = linear_datasource(1, 120, 6, T=2)
     model = nb_linear.LinearModel("ordinary", scaling)
     result = model.fit(None, X, Y, "mse", solver=cpu_solver(oracle), _backend=OracleBackend(oracle))
-    assert result.trials() == 0 and result.optimum_params() == {}
+    # no hyper-parameters: ml::tune still runs one parameter-free trial over the folds (src/machine/tune.cpp:48-52)
+    assert result.trials() == 1 and result.optimum_params() == {} and result.optimum_trial() == 0
+    assert result.train.shape == (1, 5, 2) and np.all(np.isfinite(result.train)) and np.all(np.isfinite(result.valid))
+    assert result.value(0) < 1e-5
     assert np.max(np.abs(model.weights() - W)) < 1e-6 and np.max(np.abs(model.bias() - b)) < 1e-6
     assert np.max(result.refit["errors"]) < 1e-5 and result.refit["state"]["status"] == "gradient_test"
     outputs = model.predict(None, X, _backend=OracleBackend(oracle))
