@@ -69,6 +69,8 @@ def parse_args():
                         help="N > 1: 'peer' = sums published into the peers' mailboxes from inside the kernel (NVLink), "
                              "'nccl' = two phases around torch.distributed.all_reduce, 'auto' = peer if it can be set up")
     parser.add_argument("--parity-rows", type=int, default=1 << 14, help="rows of the in-run parity dataset (all ranks)")
+    parser.add_argument("--no-balance", action="store_true",
+                        help="N > 1: keep equal row blocks instead of sizing them by each GPU's measured speed")
     return parser.parse_args()
 
 
@@ -569,7 +571,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import libnano_b200 as nb
-    from libnano_b200.sharded import ShardedFunction
+    from libnano_b200.sharded import ShardedFunction, balanced_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -641,6 +643,41 @@ def run_b200(args):
         return step_device
 
     step_device = make_step(local, function, n_global)
+
+    # ---- (0) N > 1: size the row blocks by each GPU's measured speed ----------------------------------------------
+    # the boards sit at the power cap at different clocks (their kernel times are 1.3 % apart on an 8 x B200 box) and a
+    # sharded evaluation is as slow as its slowest rank; the partition is re-cut ONCE, before the timed regions, from a
+    # calibration region identical to the timed one, and stays static afterwards (libnano_b200.sharded.balanced_rows)
+    partition = {"rows": [rows] * world, "balanced": False}
+    if world > 1 and not args.no_balance:
+        calibration = h.region(step_device, local, args.steps, args.warmup)
+        mine_ms = float(np.median(calibration["passes"]))
+        measured = [None] * world
+        dist.all_gather_object(measured, mine_ms)
+        row0s, new_rows = balanced_rows(n_global, [ms / rows for ms in measured])
+        partition = {"rows": new_rows, "balanced": True, "calibration_kernel_ms": measured}
+        if max(abs(r - rows) for r in new_rows) > 1e-4 * rows:
+            local.close()
+            data.close()
+            del function, local, data
+            data = nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, new_rows[rank], features, seed=SEED,
+                                    row_offset=row0s[rank], noise=0.1)
+            local = nb.LinearFunction(data, nb.Loss(LOSS_ID), 0.0, L2REG)
+            if args.variant >= 0:
+                local.set_variant(args.variant)
+            function = ShardedFunction.from_local(local, n_global)
+            if collective == "peer":
+                connected = [None] * world
+                ok = False
+                try:
+                    ok = function.connect_peers()
+                except Exception:  # noqa: BLE001
+                    ok = False
+                dist.all_gather_object(connected, ok)
+                if not all(connected):
+                    raise SystemExit("bench.py: the peers could not be re-connected after re-cutting the row blocks")
+            step_device = make_step(local, function, n_global)
+    my_rows = partition["rows"][rank]
     main = h.region(step_device, local, args.steps, args.warmup)
     f_device = float(f_dev.item())
     clocks = sampler.window(*main["window"])
@@ -664,7 +701,8 @@ def run_b200(args):
     peer_mode = local.peer_mode()
 
     # ---- (4) per-rank evidence (what limits the 1 -> N curve) --------------------------------------------------------
-    mine = {"rank": rank, "kernel_ms": summary(main["passes"]), "step_ms": main["own_ms"] / args.steps, "clocks": clocks}
+    mine = {"rank": rank, "rows": my_rows, "kernel_ms": summary(main["passes"]), "step_ms": main["own_ms"] / args.steps,
+            "clocks": clocks}
     per_rank = [mine]
     if world > 1:
         per_rank = [None] * world
@@ -711,7 +749,7 @@ def run_b200(args):
 
     work = float(n_global) * features * args.steps  # samples*features over all ranks
     kernel = summary(main["passes"])
-    bytes_alg = algorithmic_bytes(rows, features)
+    bytes_alg = algorithmic_bytes(my_rows, features)  # rank 0's launch
     peak, peak_source = measured_hbm_peak()
     achieved = bytes_alg / (kernel["mean"] * 1e-3) / 1e9
     config = workload_config(args, world)
@@ -728,6 +766,7 @@ def run_b200(args):
                            "none": "none (single GPU)"}.get(collective, collective),
             "settle": f"{args.settle_seconds} s idle before the warm-up of each timed region, so every region starts "
                       "from the same board state",
+            "partition": partition,
         },
         "e2e": {"value": work / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"] / args.steps,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 1),
@@ -737,7 +776,7 @@ def run_b200(args):
                 "clocks": e2e_clocks},
         "gpu_launches": int(main["launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(kernel_text, rows, features), "kernel": "vgrad_t1_kernel",
+                     "traffic": recorded_traffic(kernel_text, my_rows, features), "kernel": "vgrad_t1_kernel",
                      "kernel_ms": kernel["mean"], "kernel_ms_distribution": kernel, "launches_timed": kernel["launches"],
                      "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peak_source},
         "clocks": clocks,

@@ -3031,6 +3031,11 @@ static int ensure_batch(nb200_obj* obj, const int64_t Kp)
         const mt_variant& var = kMtVariants[geo.variant];
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.value, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.fwd_smem));
+        if (geo.tma_stages >= 2)
+        {
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.tma_smem));
+            NB200_CUDA_TRY(cudaFuncSetAttribute(var.value_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.tma_smem));
+        }
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.backward, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.bwd_smem));
     }
     const size_t K = static_cast<size_t>(Kp);
@@ -3197,13 +3202,21 @@ static int vgrad_batch_impl(nb200_obj* obj, const int64_t K, const double* x, co
     f.N               = N;
     f.D               = static_cast<int>(D);
     f.T               = static_cast<int>(Kp);
-    f.stages          = geo.fwd_stages;
     f.loss            = obj->loss;
     f.loss_param      = obj->loss_param;
     f.y_broadcast     = 1;
     f.per_target_loss = 1;
     f.fb_stride       = static_cast<int>(1 + 2 * Kp);
-    (grad ? var.grad : var.value)<<<geo.fwd_grid, kMtThreads, geo.fwd_smem, st>>>(f);
+    if (data->x_map_ok && geo.tma_stages >= 2 && env_int("NB200_MT_LEGACY_FORWARD", 0) == 0)
+    {
+        f.stages = geo.tma_stages;
+        (grad ? var.grad_tma : var.value_tma)<<<geo.fwd_grid, kMtThreads, geo.tma_smem, st>>>(f, data->x_map);
+    }
+    else
+    {
+        f.stages = geo.fwd_stages;
+        (grad ? var.grad : var.value)<<<geo.fwd_grid, kMtThreads, geo.fwd_smem, st>>>(f);
+    }
     NB200_CUDA_TRY(cudaGetLastError());
     obj->launches += 1;
     if (grad)

@@ -777,20 +777,44 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
         const int     rows = static_cast<int>(min(static_cast<int64_t>(kMtBwdRows), p.N - chunk * kMtBwdRows));
         const double* gs   = stage0 + static_cast<int64_t>(s) * stage_doubles;
         const double* xs   = gs + dl_doubles;
-#pragma unroll
-        for (int kk = 0; kk < kMtBwdRows / 4; ++kk)
+        if (rows == kMtBwdRows)
         {
-            const int  k  = kk * 4 + tig; // row inside the stage
-            const bool in = k < rows;
-            const double b0 = in ? xs[k * kMtBwdLd + (2 * warp) * 8 + g] : 0.0;
-            const double b1 = in ? xs[k * kMtBwdLd + (2 * warp + 1) * 8 + g] : 0.0;
+            // full stage: no predicates at all. The dL columns past T (the last target tile) are whatever the shared
+            // memory holds — they only reach accumulator rows m >= T, which are never stored — and plain loads let the
+            // compiler run them well ahead of the DMMAs that use them (the predicated form re-zeroed each register
+            // right behind the DMMA reading it and kept only three fragments in flight).
 #pragma unroll
-            for (int mt = 0; mt < NT8; ++mt)
+            for (int kk = 0; kk < kMtBwdRows / 4; ++kk)
             {
-                const int    m = mt * 8 + g;
-                const double a = (in && m < T) ? gs[k * t_ld + m] : 0.0;
-                dmma_m8n8k4(acc[mt][0][0], acc[mt][0][1], a, b0);
-                dmma_m8n8k4(acc[mt][1][0], acc[mt][1][1], a, b1);
+                const int    k  = kk * 4 + tig;
+                const double b0 = xs[k * kMtBwdLd + (2 * warp) * 8 + g];
+                const double b1 = xs[k * kMtBwdLd + (2 * warp + 1) * 8 + g];
+#pragma unroll
+                for (int mt = 0; mt < NT8; ++mt)
+                {
+                    const double a = gs[k * t_ld + mt * 8 + g];
+                    dmma_m8n8k4(acc[mt][0][0], acc[mt][0][1], b0, a);
+                    dmma_m8n8k4(acc[mt][1][0], acc[mt][1][1], b1, a);
+                }
+            }
+        }
+        else
+        {
+#pragma unroll 1
+            for (int kk = 0; kk < kMtBwdRows / 4; ++kk)
+            {
+                const int    k  = kk * 4 + tig; // row inside the stage
+                const bool   in = k < rows;
+                const double b0 = in ? xs[k * kMtBwdLd + (2 * warp) * 8 + g] : 0.0;
+                const double b1 = in ? xs[k * kMtBwdLd + (2 * warp + 1) * 8 + g] : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < NT8; ++mt)
+                {
+                    const int    m = mt * 8 + g;
+                    const double a = (in && m < T) ? gs[k * t_ld + m] : 0.0;
+                    dmma_m8n8k4(acc[mt][0][0], acc[mt][0][1], b0, a);
+                    dmma_m8n8k4(acc[mt][1][0], acc[mt][1][1], b1, a);
+                }
             }
         }
         __syncwarp();
@@ -800,22 +824,25 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
         }
     }
 
+    // The products are formed transposed — the X fragment is the A operand (reused by the NT8 DMMAs that follow, the
+    // operand pattern of the forward, which the tensor pipe sustains at a higher rate), the dL fragment the B operand —
+    // so lane (g, tig) holds gW^T[column (2 warp + j) * 8 + g][target 8 mt + 2 tig + {0, 1}].
     double* out = p.partials_gw + static_cast<int64_t>(split) * T * D;
 #pragma unroll
     for (int mt = 0; mt < NT8; ++mt)
     {
-        const int t = mt * 8 + g;
-        if (t < T)
-        {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j)
+        {
+            // columns past the partial tile multiplied whatever the stage held: they are simply not stored
+            const int col = ct * kMtBwdCols + (2 * warp + j) * 8 + g;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
             {
-                // columns past the partial tile multiplied whatever the stage held: they are simply not stored
-                const int col = ct * kMtBwdCols + (2 * warp + j) * 8 + tig * 2;
-                if (col < D)
+                const int t = mt * 8 + tig * 2 + e;
+                if (t < T && col < D)
                 {
-                    *reinterpret_cast<double2*>(out + static_cast<int64_t>(t) * D + col) =
-                        make_double2(acc[mt][j][0], acc[mt][j][1]);
+                    out[static_cast<int64_t>(t) * D + col] = acc[mt][j][e];
                 }
             }
         }

@@ -27,6 +27,31 @@ def shard_rows(n_global: int, world_size: int, rank: int):
     return row0, rows
 
 
+def balanced_rows(n_global: int, seconds_per_row):
+    """Row counts proportional to each rank's measured speed (1 / seconds_per_row), summing to n_global exactly.
+
+    The ranks of a sample-sharded evaluation finish together only if their shards match their speed: boards that sit
+    at the power cap run at different clocks (1.3 % apart on an 8 x B200 box, profiles/r02_bench_8gpu.json), and the
+    evaluation is as slow as its slowest rank. The partition stays STATIC — contiguous blocks in rank order, sizes
+    fixed before the first evaluation — so results are reproducible for a given partition. Returns (row0s, rows)."""
+    speeds = 1.0 / np.asarray(seconds_per_row, dtype=np.float64)
+    critical(speeds.ndim == 1 and speeds.size > 0 and bool(np.all(np.isfinite(speeds))) and bool(np.all(speeds > 0)),
+             "sharding: the measured times must be positive and finite")
+    critical(n_global >= speeds.size, "sharding: every rank needs at least one sample")
+    ideal = n_global * speeds / speeds.sum()
+    rows = np.maximum(np.floor(ideal).astype(np.int64), 1)
+    # hand the remainder out (or take an excess back) where the rounding error is largest; fixed tie-break by rank
+    while rows.sum() != n_global:
+        error = ideal - rows
+        if rows.sum() < n_global:
+            rows[int(np.argmax(error))] += 1
+        else:
+            candidates = np.where(rows > 1, error, np.inf)
+            rows[int(np.argmin(candidates))] -= 1
+    row0s = np.concatenate([[0], np.cumsum(rows)[:-1]])
+    return [int(v) for v in row0s], [int(v) for v in rows]
+
+
 class _CudaBufferView:
     """Zero-copy view of a device buffer for torch.as_tensor (CUDA array interface v2)."""
 

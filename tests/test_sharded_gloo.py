@@ -139,3 +139,20 @@ def test_host_driven_solvers_stay_in_lock_step_over_gloo(oracle, solver_id):
         p.join(timeout=240)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert list(out) == [1] * world
+
+
+def test_balanced_rows_follow_the_measured_speeds():
+    from libnano_b200.sharded import balanced_rows
+
+    row0s, rows = balanced_rows(1 << 26, [9.4255, 9.5263, 9.5089, 9.5467, 9.4695, 9.4956, 9.4408, 9.5233])
+    assert sum(rows) == 1 << 26 and row0s[0] == 0
+    assert all(a + b == c for a, b, c in zip(row0s, rows, row0s[1:]))
+    assert rows[0] == max(rows) and rows[3] == min(rows)              # the fastest rank holds the most rows
+    times = [r * t for r, t in zip(rows, [9.4255, 9.5263, 9.5089, 9.5467, 9.4695, 9.4956, 9.4408, 9.5233])]
+    assert max(times) / min(times) - 1.0 < 1e-6                        # everyone finishes together
+    assert balanced_rows(10, [1.0, 1.0, 1.0]) == ([0, 4, 7], [4, 3, 3])
+    assert balanced_rows(3, [1.0, 1e-9, 1.0])[1] == [1, 1, 1]
+    with pytest.raises(RuntimeError, match="positive and finite"):
+        balanced_rows(100, [1.0, 0.0])
+    with pytest.raises(RuntimeError, match="at least one sample"):
+        balanced_rows(1, [1.0, 1.0])
