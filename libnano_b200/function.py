@@ -124,6 +124,13 @@ class Dataset:
         _lib.check(_lib.lib().nb200_dataset_read(self.handle, row0, rows, _ptr(X), _ptr(Y)))
         return X, Y
 
+    def read_targets(self, row0: int = 0, rows: int | None = None):
+        """The targets of rows [row0, row0 + rows) without their inputs."""
+        rows = self.samples - row0 if rows is None else rows
+        Y = np.empty((rows, self.targets), dtype=np.float64)
+        _lib.check(_lib.lib().nb200_dataset_read(self.handle, row0, rows, None, _ptr(Y)))
+        return Y
+
     SCALINGS = {"none": 0, "mean": 1, "minmax": 2, "standard": 3}  # nano::scaling_type (dataset/scaling.h:10-16)
 
     def scale(self, inputs: str = "standard", targets: str = "none", enable_inputs=None, enable_targets=None):

@@ -575,3 +575,83 @@ def test_invalid_requests_fail_like_critical(ctx):
         nb.LinearFunction(data, nb.Loss("mse")).vgrad_batch(np.zeros((2, 8)), 0.0, 0.0)  # batch needs one target
     with pytest.raises(RuntimeError):
         nb.Loss("s-hinge").value(ctx, np.zeros((2, 2)), np.zeros((2, 3)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: the oracle where the host can hold the data, size-independent properties beyond
+# ----------------------------------------------------------------------------------------------------------------
+def test_config2_shape_matches_the_oracle(ctx, oracle):
+    # BASELINE configs[1]: s-logistic, 2^20 x 1024 x 1 — the rows generated in HBM, read back (8 GiB) and evaluated by the
+    # oracle on every host thread; same x, l2 = 1e-2 (VERDICT r01 weak #1 ii)
+    import libnano_b200 as nb
+
+    N, D = 1 << 20, 1024
+    data = nb.Dataset.synth(ctx, nb.SYNTH_CLASSIFICATION, N, D, seed=42, noise=0.1)
+    function = nb.LinearFunction(data, nb.Loss("s-logistic"), 0.0, 1e-2)
+    x = np.random.default_rng(0).uniform(-1.0, 1.0, D + 1) / np.sqrt(D)
+    gx = np.empty_like(x)
+    fx = function(x, gx)
+    X, Y = data.read()
+    f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-logistic", x, l2=1e-2, threads=oracle.hardware_threads())
+    assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY
+    function.close()
+    data.close()
+
+
+@pytest.mark.parametrize("N,D,T,loss_id,kind", [
+    (1 << 23, 1024, 1, "s-logistic", "classification"),   # config 4's shard (64 GiB of X)
+    (1 << 24, 512, 1, "s-hinge", "classification"),       # config 5 (64 GiB)
+    (1 << 22, 2048, 100, "s-classnll", "multiclass"),     # config 3 (64 GiB + 3.1 GiB of targets)
+])
+def test_full_size_known_answers_at_zero(ctx, N, D, T, loss_id, kind):
+    """At x = 0 every output is 0, so the loss and the bias gradient have closed forms that only need the targets:
+    logistic f = log 2, gb = -mean(y) / 2 (logistic.h:19-41); hinge f = 1, gb = -mean(y) (hinge.h:19-29); softmax
+    f = log T, gb_k = 1 / T - (share of class k) (classnll.h:19-37). The weight gradient is -dL-weighted column means of
+    X: checked on the first rows' contribution through linearity in the SAMPLES — the objective over N rows is the
+    mean of the objectives over two halves (shard invariance), evaluated here at the full size."""
+    import libnano_b200 as nb
+
+    synth = nb.SYNTH_MULTICLASS if kind == "multiclass" else nb.SYNTH_CLASSIFICATION
+    data = nb.Dataset.synth(ctx, synth, N, D, T=T, seed=42)
+    function = nb.LinearFunction(data, nb.Loss(loss_id), 0.0, 0.0)
+    n = function.size()
+    g = np.empty(n)
+    f = function(np.zeros(n), g)
+    # targets only (8 N T bytes), in slices
+    sums = np.zeros(T)
+    step = 1 << 20
+    for row0 in range(0, N, step):
+        sums += data.read_targets(row0, min(step, N - row0)).sum(axis=0)
+    mean_y = sums / N
+    gb = g[T * D:]
+    if loss_id == "s-logistic":
+        assert abs(f - np.log(2.0)) <= 1e-15 and np.max(np.abs(gb + mean_y / 2.0)) <= 1e-13
+    elif loss_id == "s-hinge":
+        assert abs(f - 1.0) <= 1e-15 and np.max(np.abs(gb + mean_y)) <= 1e-13
+    else:
+        share = (mean_y + 1.0) / 2.0            # targets are -1 / +1 one-hot
+        assert abs(f - np.log(float(T))) <= 1e-13 and np.max(np.abs(gb - (1.0 / T - share))) <= 1e-13
+    assert np.all(np.isfinite(g)) and function.launches() >= 1
+    function.close()
+
+    # shard invariance at the full size: the same rows as two half-size datasets (generated by row offset)
+    half = N // 2
+    data.close()
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1.0, 1.0, n) / np.sqrt(D)
+    parts = []
+    for row0 in (0, half):
+        part = nb.Dataset.synth(ctx, synth, half, D, T=T, seed=42, row_offset=row0)
+        fn = nb.LinearFunction(part, nb.Loss(loss_id), 0.0, 0.0)
+        gp = np.empty(n)
+        parts.append((fn(x, gp), gp))
+        fn.close()
+        part.close()
+    whole = nb.Dataset.synth(ctx, synth, N, D, T=T, seed=42)
+    fn = nb.LinearFunction(whole, nb.Loss(loss_id), 0.0, 0.0)
+    gw = np.empty(n)
+    fw = fn(x, gw)
+    assert rel_f(fw, 0.5 * (parts[0][0] + parts[1][0])) <= 1e-13
+    assert rel_g(gw, 0.5 * (parts[0][1] + parts[1][1])) <= 1e-13
+    fn.close()
+    whole.close()
