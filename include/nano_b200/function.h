@@ -283,6 +283,8 @@ enum class solver_status
 {
     max_iters     = 0, // include/nano/solver/status.h
     gradient_test = 1,
+    specific_test = 2, // OSGA: eta < epsilon
+    value_test    = 3, // OSGA: no improvement within `patience` iterations
     failed        = 4
 };
 
@@ -343,6 +345,24 @@ inline solver_state_t minimize_cgd(const linear::function_t& function, const std
                                 int* status) {
                                 return nb200_cgd_minimize(obj, x, n, beta, epsilon, max_evals, orthotest, eta, 0, nullptr,
                                                           nullptr, fx, gtest, stats, status);
+                            });
+}
+
+// solver_osga_t::do_minimize (src/solver/osga.cpp:59-147), device-resident: the driver for non-smooth objectives
+// (hinge / mae losses, lasso and elastic-net terms). m_gradient_test carries OSGA's eta on return.
+// defaults: src/solver.cpp:45-51 (epsilon, max_evals, patience), osga.cpp:49-51 (lambda, alpha_max, kappas)
+inline solver_state_t minimize_osga(const linear::function_t& function, const std::vector<scalar_t>& x0,
+                                    const scalar_t epsilon = 1e-8, const tensor_size_t max_evals = 1000,
+                                    const tensor_size_t patience = 100, const scalar_t lambda = 0.9,
+                                    const scalar_t alpha_max = 0.7, const scalar_t kappa_prime = 0.1,
+                                    const scalar_t kappa = 1.1)
+{
+    return detail::minimize(function, x0,
+                            [&](nb200_obj* obj, scalar_t* x, int64_t n, scalar_t* fx, scalar_t* eta, int64_t* stats,
+                                int* status) {
+                                return nb200_osga_minimize(obj, x, n, epsilon, max_evals, patience, lambda, alpha_max,
+                                                           kappa_prime, kappa, function.strong_convexity(), 0, fx, eta,
+                                                           stats, status);
                             });
 }
 } // namespace nano_b200

@@ -74,6 +74,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// A consumer warp hands a stage it has READ with ordinary shared-memory loads (generic proxy) back to the producer, whose
+// refill is a bulk / tensor-map copy (async proxy). The cross-proxy fence orders every lane's loads before the refill
+// that follows the arrival. Without it the arrival alone was measured NOT to be enough: in the many-target forward a
+// refill overtook loads still in flight about once per 10^6 stage uses (one warp's 16 rows of one tile wrong, different
+// rows on every run). Called by all 32 lanes; one arrival per warp.
+__device__ __forceinline__ void mbar_release_stage(uint64_t* empty_bar, const int lane)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+    {
+        mbar_arrive(empty_bar);
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, const uint32_t tx_bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tx_bytes)

@@ -274,9 +274,9 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     geo.fwd_grid   = static_cast<int>(std::min<int64_t>((N + kMtBM - 1) / kMtBM, sm_count));
     geo.fwd_stages = static_cast<int>(fwd_stages);
     geo.fwd_smem   = static_cast<int>(fwd_header + fwd_stages * fwd_stage);
-    // tensor-map-fed forward: barriers, the [64][TP + 2] output tile (1 KiB granules: the stages behind it are 128-byte
+    // tensor-map-fed forward: barriers, the [128][TP + 2] output tile (1 KiB granules: the stages behind it are 128-byte
     // swizzle atoms), then stages of a dense X tile + the packed W tile
-    const int64_t tma_otile = round_up((kMtBM / 2) * (TP + 2) * 8, 1024);
+    const int64_t tma_otile = round_up(kMtBM * (TP + 2) * 8, 1024);
     const int64_t tma_stage = kMtXTileBytes + round_up(TP * kMtLd * 8, 1024);
     int64_t       tma_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - kMtTmaHeader - tma_otile) / tma_stage);
     if (const int forced = env_int("NB200_MT_STAGES", 0); forced >= 2)

@@ -327,11 +327,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         }
         if constexpr (EARLY || !GRAD)
         {
-            __syncwarp();
-            if (lane == 0)
-            {
-                mbar_arrive(empty_bar + s);
-            }
+            mbar_release_stage(empty_bar + s, lane);
         }
 
         // exchange: every warp ends up with the full outputs in fragment layout, summed in warp order
@@ -490,11 +486,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         }
         if constexpr (GRAD && !EARLY)
         {
-            __syncwarp();
-            if (lane == 0)
-            {
-                mbar_arrive(empty_bar + s);
-            }
+            mbar_release_stage(empty_bar + s, lane);
         }
     }
 

@@ -236,11 +236,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) vgrad_ft_kernel(const ft_params
             // the stage can be refilled as soon as its last rows (and targets) are in registers
             if (j == last_own)
             {
-                __syncwarp();
-                if (lane == 0)
-                {
-                    mbar_arrive(empty_bar + s);
-                }
+                mbar_release_stage(empty_bar + s, lane);
             }
 
             // partial outputs of this warp's column slice for every (row, target) pair, reduced over the lanes. The

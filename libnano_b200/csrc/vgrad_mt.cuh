@@ -33,6 +33,7 @@ constexpr int kMtThreads       = (kMtWarps + kMtProducerWarps) * 32;
 constexpr int kMtProducerRegs  = 40;  // 384 threads x 168 registers at launch -> 128 x 40 + 256 x 232
 constexpr int kMtConsumerRegs  = 232;
 constexpr int kMtEpilogueRows     = 4;   // rows a warp evaluates together in the loss epilogue (independent fp64 chains)
+constexpr int kMtEpilogueRowsTma  = 8;   // ... in the tensor-map-fed forward, whose accumulators are all dead by then
 constexpr int kMtTmaHeader        = 1024; // barriers
 constexpr int kMtXTileBytes       = kMtBM * kMtBK * 8; // 128 rows x 128 bytes, dense, 128-byte swizzled
 
@@ -118,14 +119,13 @@ __device__ __forceinline__ double quad_max(double v)
 // dependent fp64 instructions (max -> exp -> sum -> log, or the elementwise loss) plus the latency of the targets'
 // global load, ~4900 cycles per row with the tensor pipe idle behind it (measured: 2.2 of the forward's 14.6 ms at
 // config 3); interleaved rows overlap those latencies. Lanes stride the targets (t = lane + 32 k).
-template <int TP, bool GRAD>
+template <int TP, bool GRAD, int R>
 __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, const double* orows, const int64_t row_first,
                                                  const int row_count, const int lane, double& fsum,
                                                  double (&gbacc)[(TP + 31) / 32], double (&lossacc)[(TP + 31) / 32])
 {
     constexpr int TPs = TP + 2;
     constexpr int TL  = (TP + 31) / 32;
-    constexpr int R   = kMtEpilogueRows;
     const int     T     = p.T;
     const int     dl_ld = T + (T & 1);
     for (int r0 = 0; r0 < row_count; r0 += R)
@@ -404,11 +404,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
                     dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, bv);
                 }
             }
-            __syncwarp();
-            if (lane == 0)
-            {
-                mbar_arrive(empty_bar + s);
-            }
+            mbar_release_stage(empty_bar + s, lane);
         }
 
         // ----- epilogue: accumulator fragments (+ bias) -> this warp's 16 rows of the shared output tile, then a
@@ -430,7 +426,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_forward_kernel(const mt_forw
 
         const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
         const int     row_count = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
-        mt_epilogue_rows<TP, GRAD>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
+        mt_epilogue_rows<TP, GRAD, kMtEpilogueRows>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
         __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
         }
     }
@@ -494,14 +490,14 @@ __global__ void __launch_bounds__(kMtThreads, 1)
     constexpr int TP    = NT8 * 8;
     constexpr int TPs   = TP + 2;  // row stride of the output tile
     constexpr int TL    = (TP + 31) / 32;
-    constexpr int kFold = 8 * TPs; // distance between the warps' fold rows (each inside that warp's 8 tile rows)
-    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit 8 tile rows");
+    constexpr int kFold = 16 * TPs; // distance between the warps' fold rows (each inside that warp's 16 tile rows)
+    static_assert(1 + 2 * TP <= kFold, "the fold row [loss | dL sums | per-target loss sums] must fit the warp's rows");
 
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty_bar = full_bar + kMtMaxStages;
-    constexpr int kOtileBytes = ((kMtBM / 2) * TPs * 8 + 1023) / 1024 * 1024;
-    double*        otile  = reinterpret_cast<double*>(smem + kMtTmaHeader); // [64][TPs]: 8 rows per warp at a time
+    constexpr int kOtileBytes = (kMtBM * TPs * 8 + 1023) / 1024 * 1024;
+    double*        otile  = reinterpret_cast<double*>(smem + kMtTmaHeader); // [128][TPs]: 16 rows per warp
     unsigned char* stage0 = smem + kMtTmaHeader + kOtileBytes;              // 1 KiB aligned (swizzle atom)
     const int      T      = p.T;
     const int      D      = p.D;
@@ -612,11 +608,7 @@ __global__ void __launch_bounds__(kMtThreads, 1)
                     dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, bv);
                 }
             }
-            __syncwarp();
-            if (lane == 0)
-            {
-                mbar_arrive(empty_bar + s);
-            }
+            mbar_release_stage(empty_bar + s, lane);
             if (++s == p.stages)
             {
                 s = 0;
@@ -624,9 +616,9 @@ __global__ void __launch_bounds__(kMtThreads, 1)
             }
         }
 
-        // ----- epilogue: accumulator fragments (+ bias) -> this warp's 8 rows of the shared output tile (the two m8
-        //       tiles take turns), then the row-wise loss over them -----
-        double* orows = otile + (warp * 8) * TPs;
+        // ----- epilogue: ALL accumulator fragments (+ bias) -> this warp's 16 rows of the shared output tile, then the
+        //       row-wise loss over them, eight rows at a time (the accumulator registers are free by then) -----
+        double* orows = otile + (warp * 16) * TPs;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
         {
@@ -636,16 +628,16 @@ __global__ void __launch_bounds__(kMtThreads, 1)
                 const int    col = nt * 8 + tig * 2;
                 const double b0  = (col < T) ? p.b[col] : 0.0;
                 const double b1  = (col + 1 < T) ? p.b[col + 1] : 0.0;
-                *reinterpret_cast<double2*>(orows + rho * TPs + col) =
+                *reinterpret_cast<double2*>(orows + (mt * 8 + rho) * TPs + col) =
                     make_double2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
             }
-            __syncwarp();
-            const int64_t row_first = tile * kMtBM + warp * 16 + mt * 8;
-            const int     row_count =
-                static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(8), p.N - row_first)));
-            mt_epilogue_rows<TP, GRAD>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
-            __syncwarp(); // the next m8 tile / the next tile's epilogue overwrites this warp's rows
         }
+        __syncwarp();
+        const int64_t row_first = tile * kMtBM + warp * 16;
+        const int     row_count =
+            static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(16), p.N - row_first)));
+        mt_epilogue_rows<TP, GRAD, kMtEpilogueRowsTma>(p, orows, row_first, row_count, lane, fsum, gbacc, lossacc);
+        __syncwarp(); // the next tile's epilogue overwrites this warp's rows
     }
 
     // ----- fold the 8 consumer warps in warp order (the output tile is dead: it hosts the per-warp fold rows) -----
@@ -817,11 +809,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt_backward_kernel(const mt_bac
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0)
-        {
-            mbar_arrive(empty_bar + s);
-        }
+        mbar_release_stage(empty_bar + s, lane);
     }
 
     // The products are formed transposed — the X fragment is the A operand (reused by the NT8 DMMAs that follow, the

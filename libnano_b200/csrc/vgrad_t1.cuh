@@ -258,11 +258,7 @@ __device__ __forceinline__ void consume_rows(const t1_params& p, uint64_t* full_
             // the stage can be refilled as soon as the last rows this warp owns are in registers
             if (i + RW >= count)
             {
-                __syncwarp();
-                if (lane == 0)
-                {
-                    mbar_arrive(empty_bar + s);
-                }
+                mbar_release_stage(empty_bar + s, lane);
             }
 
             // the RW partial dots are reduced together (recursive halving: RW - 1 exchanges instead of 5 * RW); the

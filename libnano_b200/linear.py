@@ -376,7 +376,9 @@ class LinearModel:
             def callback(new_params):                          # ml::tune's tuner_callback (tune.cpp:19-46)
                 old_trials = result.trials()
                 result.add(new_params)
-                batchable = (batch_trials and loss.smooth() and Y.shape[1] == 1
+                # (nb200_vgrad_batch runs on one device: a device group solves its trials one by one)
+                one_device = len(getattr(ctx, "devices", [0])) == 1
+                batchable = (batch_trials and one_device and loss.smooth() and Y.shape[1] == 1
                              and all(self._regularisers(params)[0] == 0.0 for params in new_params))
                 if batchable:
                     batched_callback(new_params, old_trials)

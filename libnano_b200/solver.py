@@ -499,7 +499,10 @@ def rqb(function, x0, epsilon: float = 1e-8, max_evals: int = 1000, max_size: in
                 break
             fy = float(function(y, gy))
             fyhat = bundle.fhat(y)
-            gyhat = apply_metric(cx - y) / t
+            # gyhat = M (x - y) / t (csearch.cpp:73) with y = x - t M^-1 G'a is the aggregate gradient G'a itself: taken
+            # from the bundle instead of another n x n product (M and its inverse are kept consistent by the rank-one
+            # updates, so the two differ by rounding only)
+            gyhat = bundle.solution_g
             step = y - cx
             delta = cfx - fyhat + 0.5 * float(gyhat @ step)
             error = cfx - fy + float(gy @ step)

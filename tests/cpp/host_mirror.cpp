@@ -169,6 +169,13 @@ int main()
         CHECK(std::fabs(a.m_fx - b.m_fx) <= 1e-10 * (1 + std::fabs(a.m_fx)));
         std::printf("group of %d devices: f=%.15g lbfgs fx=%.15g (%d evaluations)\n", group.devices(), f3, b.m_fx,
                     static_cast<int>(b.m_fcalls));
+
+        // the non-smooth objective (l1 > 0) through the device-resident OSGA, single device and group: same optimum
+        const auto c = minimize_osga(function, x0, 1e-6, 3000);
+        const auto d = minimize_osga(sharded, x0, 1e-6, 3000);
+        CHECK(c.m_status == d.m_status && c.m_status != solver_status::failed);
+        CHECK(c.m_fx < f2 && std::fabs(c.m_fx - d.m_fx) <= 1e-6 * (1 + std::fabs(c.m_fx)));
+        CHECK(c.m_fcalls == 2 * c.m_iterations + 1 && c.m_gcalls == c.m_iterations + 1); // src/solver/osga.cpp:101,112
     }
 
     std::printf("OK f=%.15g |g|_inf=%.6g\n", f1, gmax);

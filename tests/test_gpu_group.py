@@ -251,3 +251,19 @@ def test_sharded_processes_under_torchrun(mode):
     done = subprocess.run(command, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert done.returncode == 0, done.stdout[-4000:] + done.stderr[-4000:]
     assert '"ok": true' in done.stdout
+
+
+def test_linear_model_fit_on_a_device_group():
+    """linear_t::fit (src/linear.cpp:79-116) with every dataset of the fit split over the devices of one process."""
+    import libnano_b200 as nb
+    from test_linear_model import linear_datasource
+
+    X, Y, W, b = linear_datasource(4, 3000, 64, noise=0.05)
+    group = nb.Context(group_devices(2))
+    model = nb.LinearModel("ridge")
+    result = model.fit(group, X, Y, "mse", folds=2)
+    assert result.trials() >= 5 and np.all(np.isfinite(result.valid))
+    assert np.max(np.abs(model.weights() - W)) < 0.05 and np.max(np.abs(model.bias() - b)) < 0.05
+    outputs = model.predict(group, X)
+    assert np.max(np.abs(outputs - (X @ model.weights().T + model.bias()))) < 1e-10
+    group.close()
