@@ -115,10 +115,13 @@ __device__ __forceinline__ double quad_max(double v)
 }
 
 // Loss epilogue of `row_count` consecutive rows whose outputs sit in shared memory (row stride TPs): value, dL and
-// the per-lane column sums. kMtEpilogueRows rows are evaluated TOGETHER: one row at a time the epilogue is a chain of
+// the per-lane column sums. Several rows are evaluated TOGETHER: one row at a time the epilogue is a chain of
 // dependent fp64 instructions (max -> exp -> sum -> log, or the elementwise loss) plus the latency of the targets'
 // global load, ~4900 cycles per row with the tensor pipe idle behind it (measured: 2.2 of the forward's 14.6 ms at
-// config 3); interleaved rows overlap those latencies. Lanes stride the targets (t = lane + 32 k).
+// config 3); interleaved rows overlap those latencies. Lanes stride the targets (t = lane + 32 k). The softmax takes R
+// rows per step (its chain is the longest); the elementwise losses take 8 / TL rows per step in a loop that is NOT
+// unrolled further — every element carries the switch over the loss family, and R x TL copies of it (44 000
+// instructions per kernel) cost more in instruction fetch than the extra overlap returned.
 template <int TP, bool GRAD, int R>
 __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, const double* orows, const int64_t row_first,
                                                  const int row_count, const int lane, double& fsum,
@@ -128,26 +131,25 @@ __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, con
     constexpr int TL  = (TP + 31) / 32;
     const int     T     = p.T;
     const int     dl_ld = T + (T & 1);
-    for (int r0 = 0; r0 < row_count; r0 += R)
+    if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
     {
-        double y[R][TL];
-        bool   live[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-        {
-            live[j]            = r0 + j < row_count;
-            const int64_t row  = row_first + r0 + (live[j] ? j : 0);
-            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
-#pragma unroll
-            for (int k = 0; k < TL; ++k)
-            {
-                const int t = lane + 32 * k;
-                y[j][k]     = (t < T) ? (p.y_broadcast ? yrow[0] : yrow[t]) : 0.0;
-            }
-        }
-        if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
+        for (int r0 = 0; r0 < row_count; r0 += R)
         {
             // classnll.h:19-37
+            double y[R][TL];
+            bool   live[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                live[j]            = r0 + j < row_count;
+                const double* yrow = p.Y + (row_first + r0 + (live[j] ? j : 0)) * T;
+#pragma unroll
+                for (int k = 0; k < TL; ++k)
+                {
+                    const int t = lane + 32 * k;
+                    y[j][k]     = (t < T) ? yrow[t] : 0.0;
+                }
+            }
             double omax[R], sumexp[R], dot[R];
             double ex[R][TL];
 #pragma unroll
@@ -219,48 +221,64 @@ __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, con
                     }
                 }
             }
-        }
-        else
-        {
-#pragma unroll
-            for (int j = 0; j < R; ++j)
+            if (GRAD && dl_ld != T && lane == 0)
             {
-                const double* orow = orows + (r0 + (live[j] ? j : 0)) * TPs;
-                const int64_t row  = row_first + r0 + j;
-                double        sum  = 0.0;
 #pragma unroll
-                for (int k = 0; k < TL; ++k)
+                for (int j = 0; j < R; ++j)
                 {
-                    const int t = lane + 32 * k;
-                    if (t < T && live[j])
+                    if (live[j])
                     {
-                        double term, gv;
-                        loss_term<GRAD>(p.loss, p.loss_param, y[j][k], orow[t], term, gv);
-                        sum += term;
-                        lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
-                        if (GRAD)
-                        {
-                            p.dL[row * dl_ld + t] = gv;
-                            gbacc[k] += gv;
-                        }
+                        p.dL[(row_first + r0 + j) * dl_ld + T] = 0.0; // the pad column of an odd T
                     }
-                }
-                sum = warp_allreduce_sum(sum);
-                if (live[j])
-                {
-                    fsum += loss_post(p.loss, sum);
                 }
             }
         }
-        if (GRAD && dl_ld != T && lane == 0)
-        {
+        return;
+    }
+
+    constexpr int RE = (8 / TL) < 2 ? 2 : (8 / TL); // rows per step: eight independent elements per lane
+#pragma unroll 1
+    for (int r0 = 0; r0 < row_count; r0 += RE)
+    {
+        double sum[RE];
 #pragma unroll
-            for (int j = 0; j < R; ++j)
+        for (int j = 0; j < RE; ++j)
+        {
+            const bool    live = r0 + j < row_count;
+            const int64_t row  = row_first + r0 + (live ? j : 0);
+            const double* orow = orows + (r0 + (live ? j : 0)) * TPs;
+            const double* yrow = p.Y + row * (p.y_broadcast ? 1 : T);
+            sum[j]             = 0.0;
+#pragma unroll
+            for (int k = 0; k < TL; ++k)
             {
-                if (live[j])
+                const int t = lane + 32 * k;
+                if (t < T && live)
                 {
-                    p.dL[(row_first + r0 + j) * dl_ld + T] = 0.0; // the pad column of an odd T
+                    const double y = p.y_broadcast ? yrow[0] : yrow[t];
+                    double       term, gv;
+                    loss_term<GRAD>(p.loss, p.loss_param, y, orow[t], term, gv);
+                    sum[j] += term;
+                    lossacc[k] += loss_post(p.loss, term); // one output per model: the factor applies per term
+                    if (GRAD)
+                    {
+                        p.dL[row * dl_ld + t] = gv;
+                        gbacc[k] += gv;
+                    }
                 }
+            }
+            if (GRAD && dl_ld != T && lane == 0 && live)
+            {
+                p.dL[row * dl_ld + T] = 0.0; // the pad column of an odd T
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RE; ++j)
+        {
+            sum[j] = warp_allreduce_sum(sum[j]);
+            if (r0 + j < row_count)
+            {
+                fsum += loss_post(p.loss, sum[j]);
             }
         }
     }
