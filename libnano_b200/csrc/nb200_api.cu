@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <numeric>
 #include <random>
 #include <vector>
 
@@ -265,7 +266,18 @@ bool plan_mt(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     const int64_t bwd_stages = std::min<int64_t>(kMtMaxStages, (smem_optin - 256) / bwd_stage);
     const int64_t ctiles     = (D + kMtBwdCols - 1) / kMtBwdCols;
     const int64_t chunks     = (N + kMtBwdRows - 1) / kMtBwdRows;
-    const int64_t splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, sm_count / std::max<int64_t>(ctiles, 1)));
+    int64_t       splits     = std::max<int64_t>(1, std::min<int64_t>(chunks, sm_count / std::max<int64_t>(ctiles, 1)));
+    // one CTA per SM leaves SMs idle when ctiles does not divide their number (D = 2048: 16 x 9 = 144 of 148). With
+    // enough rows the row ranges are cut finer instead, into the smallest count that makes the grid a whole number of
+    // waves (16 x 37 = 4 x 148): CTAs are handed out as SMs free up, so every SM works until the end
+    if (ctiles * splits < sm_count)
+    {
+        const int64_t unit = sm_count / std::gcd<int64_t>(sm_count, ctiles);
+        if (chunks >= unit * 64 && unit * T * D * 8 <= (int64_t{256} << 20) && env_int("NB200_MT_WAVES", 1) != 0)
+        {
+            splits = unit;
+        }
+    }
     if (fwd_stages < 2 || bwd_stages < 2 || ctiles > sm_count)
     {
         return false;
