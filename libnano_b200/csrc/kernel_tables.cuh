@@ -7,6 +7,7 @@
 #pragma once
 
 #include "vgrad_fd.cuh"
+#include "vgrad_fr.cuh"
 #include "vgrad_ft.cuh"
 #include "vgrad_mt.cuh"
 #include "vgrad_t1.cuh"
@@ -50,8 +51,9 @@ using fd_kernel_t = void (*)(const fd_params);
 
 struct fd_variant
 {
-    int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8
-    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader)
+    int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8; NSETS == 0: the row-split kernel of
+                                 // vgrad_fr.cuh (short rows, D <= 64 * NS8)
+    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / kFrHeader)
     fd_kernel_t grad;
     fd_kernel_t value;
 };

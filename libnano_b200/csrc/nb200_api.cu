@@ -181,7 +181,8 @@ struct fd_plan
 };
 
 // W (T x ld) and at least two stages of 8 padded rows must fit next to the header; false otherwise
-bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan)
+bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan,
+             const bool row_split_ok = false)
 {
     static const bool fd_one_set = env_int("NB200_FD_ONE_SET", 0) != 0; // A/B knob (tools/gpu_round44.sh)
     if (!(N > 0 && D > 0 && D % 2 == 0 && T >= 2))
@@ -191,6 +192,38 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     for (int v = 0; v < kNumFdVariants; ++v)
     {
         const fd_variant& var = kFdVariants[v];
+        if (var.NSETS == 0)
+        {
+            // the row-split kernel (vgrad_fr.cuh): groups of 64 rows, one 8-row tile per ring stage, at least a group
+            // and two more tiles in flight
+            if (!row_split_ok || 8 * var.NT8 < T || 64LL * var.NS8 < D)
+            {
+                continue;
+            }
+            const int64_t slice   = 8LL * var.NS8;
+            const int64_t ld      = kFdWarps * slice + 4;
+            const int64_t w_bytes = round_up(T * ld * 8, 128);
+            const int64_t x_bytes = kFdRows * ld * 8;
+            const int64_t stride  = round_up(x_bytes + round_up(kFdRows * T * 8, 128), 128);
+            const int64_t offset  = var.header + w_bytes;
+            const int64_t stages  = std::min<int64_t>(kFrMaxStages, (smem_optin - offset) / stride);
+            if (stages < kFrGroup + 2)
+            {
+                continue;
+            }
+            plan.variant      = v;
+            plan.slice        = static_cast<int>(slice);
+            plan.ld           = static_cast<int>(ld);
+            plan.stages       = static_cast<int>(stages);
+            plan.stage_stride = static_cast<int>(stride);
+            plan.y_offset     = static_cast<int>(x_bytes);
+            plan.w_offset     = var.header;
+            plan.stage_offset = static_cast<int>(offset);
+            plan.smem_bytes   = static_cast<int>(offset + stages * stride);
+            plan.num_tiles    = (N + kFrGroupRows - 1) / kFrGroupRows; // groups
+            plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+            return plan.grid > 0;
+        }
         if (8 * var.NT8 < T || (64LL / var.NSETS) * var.NS8 < D || (fd_one_set && var.NSETS > 1))
         {
             continue;
@@ -687,8 +720,10 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     // (T = 3, 4: the CUDA-core kernel wins where D fills its 512- / 1024-column layouts, the tensor-pipe one elsewhere)
     const bool ft_sweet  = (D > 384 && D <= 512) || D > 896;
     const bool prefer_fd = D >= 200 && (T >= 5 || (T >= 3 && !ft_sweet));
-    if (one_pass && forced_variant != -6 && (prefer_fd || forced_variant == -5) &&
-        plan_fd(N, D, T, data->sm_count, data->smem_optin, handful))
+    // short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh; NB200_FR=0: A/B knob)
+    const bool short_rows = D <= 256 && T >= 3 && T <= 16 && env_int("NB200_FR", 1) != 0;
+    if (one_pass && forced_variant != -6 && (prefer_fd || short_rows || forced_variant == -5) &&
+        plan_fd(N, D, T, data->sm_count, data->smem_optin, handful, short_rows))
     {
         const fd_variant& var = kFdVariants[handful.variant];
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, handful.smem_bytes));
@@ -2885,7 +2920,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     else if (obj->use_fd)
     {
         const fd_variant& var = kFdVariants[obj->fd.variant];
-        text = "fd NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
+        text = std::string(var.NSETS == 0 ? "fr" : "fd") + " NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
                std::to_string(var.NSETS) + " grid=" +
                std::to_string(obj->fd.grid) + " ld=" + std::to_string(obj->fd.ld) + " stages=" +
                std::to_string(obj->fd.stages) + " stage_bytes=" + std::to_string(obj->fd.stage_stride) +

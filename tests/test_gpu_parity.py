@@ -482,7 +482,7 @@ def test_handful_of_targets_one_pass_tensor_parity(ctx, oracle, N, D, T, loss_id
         Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
     function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
     function.set_variant(-5)
-    assert function.describe().startswith("fd"), function.describe()
+    assert function.describe().startswith(("fd", "fr")), function.describe()  # (short rows: the row-split kernel)
     fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
     g2 = np.empty_like(x)
     assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
@@ -490,6 +490,62 @@ def test_handful_of_targets_one_pass_tensor_parity(ctx, oracle, N, D, T, loss_id
     g3 = np.empty_like(x)
     f3 = function(x, g3)
     assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+@pytest.mark.parametrize("N,D,T", [(999, 100, 10), (77, 18, 5), (1, 64, 4), (500, 130, 3), (1000, 128, 7)])
+def test_feature_split_kernel_still_covers_short_rows(ctx, oracle, monkeypatch, N, D, T):
+    # NB200_FR=0 keeps the feature-split kernel (vgrad_fd.cuh) on the short rows the row-split one now takes
+    monkeypatch.setenv("NB200_FR", "0")
+    X, Y, x = make_problem(N + D + T, N, D, T, True)
+    function = gpu_function(ctx, X, Y, "s-classnll", 0.1, 0.2)
+    function.set_variant(-5)
+    assert function.describe().startswith("fd"), function.describe()
+    check_against_oracle(oracle, function, X, Y, "s-classnll", x, 0.1, 0.2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# a handful of targets over short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh): 3 <= T <= 16, even D <= 256
+# ----------------------------------------------------------------------------------------------------------------
+FR_SHAPES = [(3000, 256, 10), (999, 100, 10), (77, 18, 5), (1, 64, 4), (63, 2, 3), (64, 4, 16), (65, 200, 16),
+             (129, 128, 8), (500, 130, 3), (1000, 128, 7), (4099, 256, 16), (640, 254, 9), (2051, 66, 13),
+             (148 * 64 * 2 + 1, 32, 10)]
+
+
+@pytest.mark.parametrize("N,D,T", FR_SHAPES)
+@pytest.mark.parametrize("loss_id", ["s-classnll", "mse", "m-logistic", "m-hinge", "mae"])
+def test_short_rows_row_split_tensor_parity(ctx, oracle, N, D, T, loss_id):
+    X, Y, x = make_problem(N + 5 * D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):
+        Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    assert function.describe().startswith("fr"), function.describe()  # the heuristic choice for D <= 256, T >= 3
+    fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
+    function.set_variant(-3)
+    g3 = np.empty_like(x)
+    f3 = function(x, g3)
+    assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+def test_short_rows_ragged_row_counts(ctx, oracle):
+    for D, T in ((256, 10), (100, 10), (64, 16)):
+        rng = np.random.default_rng(D + T)
+        counts = [1, 2, 7, 8, 9, 15, 17, 63, 64, 65, 127, 128, 129, 1183, 148 * 64 + 1]
+        Xall = rng.uniform(-1, 1, (max(counts), D))
+        labels = rng.integers(0, T, max(counts))
+        Yall = -np.ones((max(counts), T))
+        Yall[np.arange(max(counts)), labels] = 1.0
+        x = rng.uniform(-1, 1, (D + 1) * T) / np.sqrt(D)
+        for N in counts:
+            X, Y = Xall[:N], Yall[:N]
+            function = gpu_function(ctx, X, Y, "s-classnll", 0.0, 1e-2)
+            assert function.describe().startswith("fr"), function.describe()
+            gx = np.empty_like(x)
+            fx = function(x, gx)
+            f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-classnll", x, l2=1e-2)
+            assert rel_f(fx, f_ref) <= PARITY and rel_g(gx, g_ref) <= PARITY, (N, D, T, function.describe())
+            assert rel_f(function(x), f_ref) <= PARITY
 
 
 def test_handful_of_targets_ragged_row_counts_and_heuristic(ctx, oracle):
@@ -662,6 +718,7 @@ def test_full_size_known_answers_at_zero(ctx, N, D, T, loss_id, kind):
     (128 * 148 * 16, 2048, 100, "s-classnll", "multiclass", 60),   # tensor-map forward, 3 stages, 16 tiles per CTA
     (1 << 20, 2048, 128, "s-classnll", "multiclass", 8),           # tensor-map forward, 2 stages, T = 128
     (1 << 21, 784, 10, "s-classnll", "multiclass", 20),            # one-pass tensor-pipe kernel
+    (1 << 22, 256, 10, "s-classnll", "multiclass", 20),            # ... its row-split cousin for short rows
     (1 << 22, 1024, 1, "s-logistic", "classification", 20),        # single-target kernel
 ])
 def test_repeated_evaluations_are_bit_identical(ctx, N, D, T, loss_id, kind, repeats):
