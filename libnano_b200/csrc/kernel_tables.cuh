@@ -51,9 +51,9 @@ using fd_kernel_t = void (*)(const fd_params);
 
 struct fd_variant
 {
-    int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8; NSETS == 0: the row-split kernel of
-                                 // vgrad_fr.cuh (short rows, D <= 64 * NS8)
-    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / kFrHeader)
+    int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8; NSETS < 0: the row-split kernel of
+                                 // vgrad_fr.cuh (short rows, D <= 64 * NS8) with -NSETS tiles per warp and group
+    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / fr_header(TPW))
     fd_kernel_t grad;
     fd_kernel_t value;
 };

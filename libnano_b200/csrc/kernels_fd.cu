@@ -8,13 +8,14 @@ namespace
 #define NB200_FD_ENTRY(NT8, NS8, NSETS)                                                                                \
     fd_variant{NT8, NS8, NSETS, fd_layout<NT8>::kHeader, vgrad_fd_kernel<NT8, NS8, NSETS, true>,                       \
                vgrad_fd_kernel<NT8, NS8, NSETS, false>}
-#define NB200_FR_ENTRY(NT8, NS8)                                                                                       \
-    fd_variant{NT8, NS8, 0, kFrHeader, vgrad_fr_kernel<NT8, NS8, true>, vgrad_fr_kernel<NT8, NS8, false>}
+#define NB200_FR_ENTRY(NT8, NS8, TPW)                                                                                  \
+    fd_variant{NT8, NS8, -(TPW), fr_header(TPW), vgrad_fr_kernel<NT8, NS8, TPW, true>,                                 \
+               vgrad_fr_kernel<NT8, NS8, TPW, false>}
 // the first entry that covers (T, D) is taken: short rows go to the row-split kernel (vgrad_fr.cuh) where the caller
 // allows it; for T <= 8 two alternating sets of four warps (each warp twice the columns)
 const fd_variant kVariants[] = {
-    NB200_FR_ENTRY(1, 1),     NB200_FR_ENTRY(1, 2),     NB200_FR_ENTRY(1, 4),
-    NB200_FR_ENTRY(2, 1),     NB200_FR_ENTRY(2, 2),     NB200_FR_ENTRY(2, 4),
+    NB200_FR_ENTRY(1, 1, 2),  NB200_FR_ENTRY(1, 2, 2),  NB200_FR_ENTRY(1, 4, 1),
+    NB200_FR_ENTRY(2, 1, 2),  NB200_FR_ENTRY(2, 2, 2),  NB200_FR_ENTRY(2, 4, 1),
     NB200_FD_ENTRY(1, 8, 2),  NB200_FD_ENTRY(1, 16, 2), NB200_FD_ENTRY(1, 24, 2), NB200_FD_ENTRY(1, 28, 2),
     NB200_FD_ENTRY(1, 32, 2),
     NB200_FD_ENTRY(1, 2, 1),  NB200_FD_ENTRY(1, 4, 1),  NB200_FD_ENTRY(1, 6, 1),  NB200_FD_ENTRY(1, 8, 1),

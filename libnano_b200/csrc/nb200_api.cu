@@ -192,10 +192,11 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
     for (int v = 0; v < kNumFdVariants; ++v)
     {
         const fd_variant& var = kFdVariants[v];
-        if (var.NSETS == 0)
+        if (var.NSETS < 0)
         {
-            // the row-split kernel (vgrad_fr.cuh): groups of 64 rows, one 8-row tile per ring stage, at least a group
-            // and two more tiles in flight
+            // the row-split kernel (vgrad_fr.cuh): groups of 8 TPW tiles, one 8-row tile per ring stage, at least a
+            // group and two more tiles in flight
+            const int64_t tiles = fr_group_tiles(-var.NSETS);
             if (!row_split_ok || 8 * var.NT8 < T || 64LL * var.NS8 < D)
             {
                 continue;
@@ -207,7 +208,7 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
             const int64_t stride  = round_up(x_bytes + round_up(kFdRows * T * 8, 128), 128);
             const int64_t offset  = var.header + w_bytes;
             const int64_t stages  = std::min<int64_t>(kFrMaxStages, (smem_optin - offset) / stride);
-            if (stages < kFrGroup + 2)
+            if (stages < tiles + 2)
             {
                 continue;
             }
@@ -220,7 +221,7 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
             plan.w_offset     = var.header;
             plan.stage_offset = static_cast<int>(offset);
             plan.smem_bytes   = static_cast<int>(offset + stages * stride);
-            plan.num_tiles    = (N + kFrGroupRows - 1) / kFrGroupRows; // groups
+            plan.num_tiles    = (N + tiles * kFdRows - 1) / (tiles * kFdRows); // groups
             plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
             return plan.grid > 0;
         }
@@ -720,8 +721,9 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     // (T = 3, 4: the CUDA-core kernel wins where D fills its 512- / 1024-column layouts, the tensor-pipe one elsewhere)
     const bool ft_sweet  = (D > 384 && D <= 512) || D > 896;
     const bool prefer_fd = D >= 200 && (T >= 5 || (T >= 3 && !ft_sweet));
-    // short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh; NB200_FR=0: A/B knob)
-    const bool short_rows = D <= 256 && T >= 3 && T <= 16 && env_int("NB200_FR", 1) != 0;
+    // short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh; NB200_FR=0: A/B knob); also for T = 2, where it beats
+    // the CUDA-core kernel at these widths (256 x 2: 0.53 against 0.73 ms, 64 x 2: 1.34 against 2.60 at 2 GiB of X)
+    const bool short_rows = D <= 256 && T >= 2 && T <= 16 && env_int("NB200_FR", 1) != 0;
     if (one_pass && forced_variant != -6 && (prefer_fd || short_rows || forced_variant == -5) &&
         plan_fd(N, D, T, data->sm_count, data->smem_optin, handful, short_rows))
     {
@@ -2920,7 +2922,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     else if (obj->use_fd)
     {
         const fd_variant& var = kFdVariants[obj->fd.variant];
-        text = std::string(var.NSETS == 0 ? "fr" : "fd") + " NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
+        text = std::string(var.NSETS < 0 ? "fr" : "fd") + " NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
                std::to_string(var.NSETS) + " grid=" +
                std::to_string(obj->fd.grid) + " ld=" + std::to_string(obj->fd.ld) + " stages=" +
                std::to_string(obj->fd.stages) + " stage_bytes=" + std::to_string(obj->fd.stage_stride) +

@@ -3,8 +3,8 @@
 //
 // vgrad_fd.cuh splits the forward over the features of one 8-row tile: every tile costs a CTA-wide exchange of partial
 // outputs behind a barrier, and all eight warps then evaluate the same tile's loss. That fixed cost (~4000 cycles per
-// tile, measured) does not shrink with the row: at D = 256 the kernel read X at 1.06 TB/s. Here a GROUP is 64 rows =
-// eight m8 tiles in eight consecutive ring stages, and per group
+// tile, measured) does not shrink with the row: at D = 256 the kernel read X at 1.06 TB/s. Here a GROUP is 64 TPW rows
+// = 8 TPW m8 tiles in as many consecutive ring stages (TPW = 2 tiles per warp for D <= 128), and per group
 //
 //   * forward, split over rows: warp w multiplies ITS tile over the full width, O_w[8, TP] = X_w W^T (four
 //     independent accumulator chains per target tile), src/linear/util.cpp:19-20 — no partial sums to exchange;
@@ -24,25 +24,37 @@
 
 namespace nb200
 {
-constexpr int kFrMaxStages = 16;
-constexpr int kFrGroup     = kFdWarps;            // tiles per group: one per consumer warp
-constexpr int kFrGroupRows = kFrGroup * kFdRows;  // 64
-constexpr int kFrBars      = 0;                   // full [16] | empty [16]
-constexpr int kFrDl        = 256;                 // dL tiles [2][64][kFdLdd]
-constexpr int kFrFold      = kFrDl + 2 * kFrGroupRows * kFdLdd * 8; // per-warp fold rows [8][1 + 16]
-constexpr int kFrHeader    = (kFrFold + kFdWarps * 17 * 8 + 127) / 128 * 128;
+constexpr int kFrMaxStages = 32;
+constexpr int kFrBars      = 0;    // full [32] | empty [32]
+constexpr int kFrDl        = 512;  // dL tiles [2][64 TPW][kFdLdd], then the per-warp fold rows [8][1 + 16]
+
+// TPW: tiles per warp and group (a group is 8 TPW tiles = 64 TPW rows in as many consecutive ring stages)
+__host__ __device__ constexpr int fr_group_tiles(const int tpw)
+{
+    return kFdWarps * tpw;
+}
+__host__ __device__ constexpr int fr_fold_offset(const int tpw)
+{
+    return kFrDl + 2 * fr_group_tiles(tpw) * kFdRows * kFdLdd * 8;
+}
+__host__ __device__ constexpr int fr_header(const int tpw)
+{
+    return (fr_fold_offset(tpw) + kFdWarps * 17 * 8 + 127) / 128 * 128;
+}
 
 #ifdef __CUDACC__
 
-// fd_params: num_tiles = number of 64-row groups, slice = 8 * NS8 columns per warp, ld = 64 * NS8 + 4
-template <int NT8, int NS8, bool GRAD>
+// fd_params: num_tiles = number of groups, slice = 8 * NS8 columns per warp, ld = 64 * NS8 + 4
+template <int NT8, int NS8, int TPW, bool GRAD>
 __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params p)
 {
+    constexpr int kTiles = fr_group_tiles(TPW); // tiles (= ring stages) per group; warp w owns tiles w, w + 8, ...
+    constexpr int kRows  = kTiles * kFdRows;    // rows per group
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + kFrBars);
     uint64_t* empty_bar = full_bar + kFrMaxStages;
     double*   dl_tiles  = reinterpret_cast<double*>(smem + kFrDl);
-    double*   fold      = reinterpret_cast<double*>(smem + kFrFold);
+    double*   fold      = reinterpret_cast<double*>(smem + fr_fold_offset(TPW));
     double*   w_s       = reinterpret_cast<double*>(smem + p.w_offset);
 
     const int warp = threadIdx.x >> 5;
@@ -98,10 +110,10 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
         uint32_t       phase  = 1;
         for (int64_t group = blockIdx.x; group < groups; group += gridDim.x)
         {
-            for (int i = 0; i < kFrGroup; ++i)
+            for (int i = 0; i < kTiles; ++i)
             {
                 mbar_wait(empty_bar + s, phase);
-                const int64_t  row0    = group * kFrGroupRows + i * kFdRows;
+                const int64_t  row0    = group * kRows + i * kFdRows;
                 const int      rows    = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kFdRows), p.N - row0)));
                 const uint32_t bytes_y = static_cast<uint32_t>((rows * ty * 8 + 15) / 16 * 16);
                 unsigned char* stage   = smem + p.stage_offset + static_cast<int64_t>(s) * p.stage_stride;
@@ -169,31 +181,51 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
 
     int it     = 0; // stage uses so far: use `it` sits in stage it % stages, phase (it / stages) & 1
     int parity = 0;
-    for (int64_t group = blockIdx.x; group < groups; group += gridDim.x, it += kFrGroup)
+    for (int64_t group = blockIdx.x; group < groups; group += gridDim.x, it += kTiles)
     {
-        const int64_t group_row0 = group * kFrGroupRows;
-        // ----- forward of this warp's tile over the full width -----
-        const int own_it = it + warp;
-        const int own_s  = own_it % p.stages;
-        mbar_wait(full_bar + own_s, static_cast<uint32_t>((own_it / p.stages) & 1));
-        const double* xo   = reinterpret_cast<const double*>(smem + p.stage_offset + static_cast<int64_t>(own_s) * p.stage_stride);
-        const double* yo   = reinterpret_cast<const double*>(smem + p.stage_offset + static_cast<int64_t>(own_s) * p.stage_stride + p.y_offset);
-        const int     rows = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kFdRows), p.N - group_row0 - warp * kFdRows)));
-        const bool    row_ok = g < rows; // rows beyond the data hold stale bytes: keep them out of every sum
-        double        o[NT8][2];
-        {
-            constexpr int CH = 4; // independent accumulator chains per target tile (a DMMA depends on the previous one)
-            double        part[CH][NT8][2];
+        const int64_t group_row0 = group * kRows;
+        // ----- forward of this warp's TPW tiles (tile u * 8 + warp of the group) over the full width -----
+        const double* xo[TPW];
+        bool          row_ok[TPW]; // rows beyond the data hold stale bytes: keep them out of every sum
+        double        y[TPW][NT8][2];
+        double        o[TPW][NT8][2];
 #pragma unroll
-            for (int c = 0; c < CH; ++c)
+        for (int u = 0; u < TPW; ++u)
+        {
+            const int use = it + u * kFdWarps + warp;
+            const int s   = use % p.stages;
+            mbar_wait(full_bar + s, static_cast<uint32_t>((use / p.stages) & 1));
+            xo[u] = reinterpret_cast<const double*>(smem + p.stage_offset + static_cast<int64_t>(s) * p.stage_stride);
+            const double* yo = reinterpret_cast<const double*>(smem + p.stage_offset + static_cast<int64_t>(s) * p.stage_stride + p.y_offset);
+            row_ok[u] = group_row0 + (u * kFdWarps + warp) * kFdRows + g < p.N;
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
             {
 #pragma unroll
-                for (int nt = 0; nt < NT8; ++nt)
+                for (int j = 0; j < 2; ++j)
                 {
-                    part[c][nt][0] = part[c][nt][1] = 0.0;
+                    const int t = nt * 8 + tig * 2 + j;
+                    y[u][nt][j] = (row_ok[u] && t < T) ? yo[g * T + t] : 0.0;
                 }
             }
-            const double* xa = xo + g * ld + tig;
+        }
+        {
+            // CH independent accumulator chains per tile and target tile (a DMMA depends on the previous one of its chain)
+            constexpr int CH = 4 / TPW;
+            double        part[TPW][CH][NT8][2];
+#pragma unroll
+            for (int u = 0; u < TPW; ++u)
+            {
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                {
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt)
+                    {
+                        part[u][c][nt][0] = part[u][c][nt][1] = 0.0;
+                    }
+                }
+            }
             const double* wb = w_s + g * ld + tig;
             int           kk = 0;
 #pragma unroll 2
@@ -202,12 +234,21 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
 #pragma unroll
                 for (int c = 0; c < CH; ++c)
                 {
-                    const double a = row_ok ? xa[(kk + c) * 4] : 0.0;
+                    double bv[NT8];
 #pragma unroll
                     for (int nt = 0; nt < NT8; ++nt)
                     {
-                        const double bv = t_in[nt] ? wb[nt * 8 * ld + (kk + c) * 4] : 0.0;
-                        dmma_m8n8k4(part[c][nt][0], part[c][nt][1], a, bv);
+                        bv[nt] = t_in[nt] ? wb[nt * 8 * ld + (kk + c) * 4] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < TPW; ++u)
+                    {
+                        const double a = row_ok[u] ? xo[u][g * ld + tig + (kk + c) * 4] : 0.0;
+#pragma unroll
+                        for (int nt = 0; nt < NT8; ++nt)
+                        {
+                            dmma_m8n8k4(part[u][c][nt][0], part[u][c][nt][1], a, bv[nt]);
+                        }
                     }
                 }
             }
@@ -216,45 +257,47 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
             {
                 if (kk + c < ksteps)
                 {
-                    const double a = row_ok ? xa[(kk + c) * 4] : 0.0;
+                    double bv[NT8];
 #pragma unroll
                     for (int nt = 0; nt < NT8; ++nt)
                     {
-                        const double bv = t_in[nt] ? wb[nt * 8 * ld + (kk + c) * 4] : 0.0;
-                        dmma_m8n8k4(part[c][nt][0], part[c][nt][1], a, bv);
+                        bv[nt] = t_in[nt] ? wb[nt * 8 * ld + (kk + c) * 4] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < TPW; ++u)
+                    {
+                        const double a = row_ok[u] ? xo[u][g * ld + tig + (kk + c) * 4] : 0.0;
+#pragma unroll
+                        for (int nt = 0; nt < NT8; ++nt)
+                        {
+                            dmma_m8n8k4(part[u][c][nt][0], part[u][c][nt][1], a, bv[nt]);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
+            for (int u = 0; u < TPW; ++u)
             {
-                double s0 = part[0][nt][0], s1 = part[0][nt][1];
 #pragma unroll
-                for (int c = 1; c < CH; ++c) // chain order: fixed
+                for (int nt = 0; nt < NT8; ++nt)
                 {
-                    s0 += part[c][nt][0];
-                    s1 += part[c][nt][1];
+                    double s0 = part[u][0][nt][0], s1 = part[u][0][nt][1];
+#pragma unroll
+                    for (int c = 1; c < CH; ++c) // chain order: fixed
+                    {
+                        s0 += part[u][c][nt][0];
+                        s1 += part[u][c][nt][1];
+                    }
+                    o[u][nt][0] = s0 + bias[nt][0]; // product first, then + bias (src/linear/util.cpp:19-20)
+                    o[u][nt][1] = s1 + bias[nt][1];
                 }
-                o[nt][0] = s0 + bias[nt][0]; // product first, then + bias (src/linear/util.cpp:19-20)
-                o[nt][1] = s1 + bias[nt][1];
-            }
-        }
-        double y[NT8][2];
-#pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
-        {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-            {
-                const int t = nt * 8 + tig * 2 + j;
-                y[nt][j]    = (row_ok && t < T) ? yo[g * T + t] : 0.0;
             }
         }
 
         // ----- the group's rows, this warp's columns -> B fragments of the backward product; stages back to the producer
-        double xb[2 * kFrGroup][NS8]; // k-step kk = rows 4 kk .. 4 kk + 3 of the group
+        double xb[2 * kTiles][NS8]; // k-step kk = rows 4 kk .. 4 kk + 3 of the group
 #pragma unroll
-        for (int i = 0; i < kFrGroup; ++i)
+        for (int i = 0; i < kTiles; ++i)
         {
             const int use = it + i;
             const int s   = use % p.stages;
@@ -275,67 +318,91 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
                     }
                 }
             }
-            mbar_release_stage(empty_bar + s, lane);
+        }
+        // one cross-proxy fence for the whole group (see mbar_release_stage: the loads above must be ordered before the
+        // refills), then lane i hands stage i back — a fence per stage made every tile wait for its own loads
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane < kTiles)
+        {
+            mbar_arrive(empty_bar + (it + lane) % p.stages);
         }
 
-        // ----- loss + dL of this warp's tile from its fragments: lane (g, tig) holds row g, targets 8 nt + 2 tig + {0, 1}
-        double dl[NT8][2];
+        // ----- loss + dL of this warp's tiles from its fragments: lane (g, tig) holds row g, targets 8 nt + 2 tig + {0, 1}
+        double dl[TPW][NT8][2];
 #pragma unroll
-        for (int nt = 0; nt < NT8; ++nt)
+        for (int u = 0; u < TPW; ++u)
         {
-            dl[nt][0] = dl[nt][1] = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt)
+            {
+                dl[u][nt][0] = dl[u][nt][1] = 0.0;
+            }
         }
         if (p.loss == LOSS_CLASSNLL)
         {
-            // classnll.h:19-37: the four lanes of a quad hold the whole row
-            double omax = -INFINITY;
+            // classnll.h:19-37: the four lanes of a quad hold the whole row; the TPW tiles' chains are independent
+            double omax[TPW], sumexp[TPW], dot[TPW];
+            double ex[TPW][NT8][2];
 #pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
+            for (int u = 0; u < TPW; ++u)
             {
+                omax[u] = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                {
-                    if (nt * 8 + tig * 2 + j < T)
-                    {
-                        omax = max_of(omax, o[nt][j]);
-                    }
-                }
-            }
-            omax = quad_max(omax);
-            double ex[NT8][2];
-            double sumexp = 0.0, dot = 0.0;
-#pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
-            {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                {
-                    ex[nt][j] = 0.0;
-                    if (nt * 8 + tig * 2 + j < T)
-                    {
-                        ex[nt][j] = exp(__dsub_rn(o[nt][j], omax));
-                        sumexp += ex[nt][j];
-                        dot += __dmul_rn(__dadd_rn(1.0, y[nt][j]), o[nt][j]);
-                    }
-                }
-            }
-            sumexp = quad_sum(sumexp);
-            dot    = quad_sum(dot);
-            if (row_ok)
-            {
-                fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                if (GRAD)
+                for (int nt = 0; nt < NT8; ++nt)
                 {
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt)
+                    for (int j = 0; j < 2; ++j)
                     {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
+                        if (nt * 8 + tig * 2 + j < T)
                         {
-                            if (nt * 8 + tig * 2 + j < T)
+                            omax[u] = max_of(omax[u], o[u][nt][j]);
+                        }
+                    }
+                }
+                omax[u] = quad_max(omax[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < TPW; ++u)
+            {
+                sumexp[u] = dot[u] = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                    {
+                        ex[u][nt][j] = 0.0;
+                        if (nt * 8 + tig * 2 + j < T)
+                        {
+                            ex[u][nt][j] = exp(__dsub_rn(o[u][nt][j], omax[u]));
+                            sumexp[u] += ex[u][nt][j];
+                            dot[u] += __dmul_rn(__dadd_rn(1.0, y[u][nt][j]), o[u][nt][j]);
+                        }
+                    }
+                }
+                sumexp[u] = quad_sum(sumexp[u]);
+                dot[u]    = quad_sum(dot[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < TPW; ++u)
+            {
+                if (row_ok[u])
+                {
+                    fsum += __dadd_rn(__dsub_rn(log(sumexp[u]), __dmul_rn(0.5, dot[u])), omax[u]);
+                    if (GRAD)
+                    {
+#pragma unroll
+                        for (int nt = 0; nt < NT8; ++nt)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
                             {
-                                dl[nt][j] = __dsub_rn(__ddiv_rn(ex[nt][j], sumexp),
-                                                      __dmul_rn(0.5, __dadd_rn(1.0, y[nt][j])));
+                                if (nt * 8 + tig * 2 + j < T)
+                                {
+                                    dl[u][nt][j] = __dsub_rn(__ddiv_rn(ex[u][nt][j], sumexp[u]),
+                                                             __dmul_rn(0.5, __dadd_rn(1.0, y[u][nt][j])));
+                                }
                             }
                         }
                     }
@@ -344,41 +411,49 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
         }
         else
         {
-            double sum = 0.0;
 #pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
+            for (int u = 0; u < TPW; ++u)
             {
+                double sum = 0.0;
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int nt = 0; nt < NT8; ++nt)
                 {
-                    if (row_ok && nt * 8 + tig * 2 + j < T)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
                     {
-                        double term;
-                        loss_term<GRAD>(p.loss, p.loss_param, y[nt][j], o[nt][j], term, dl[nt][j]);
-                        sum += term;
+                        if (row_ok[u] && nt * 8 + tig * 2 + j < T)
+                        {
+                            double term;
+                            loss_term<GRAD>(p.loss, p.loss_param, y[u][nt][j], o[u][nt][j], term, dl[u][nt][j]);
+                            sum += term;
+                        }
                     }
                 }
+                fsum += loss_post(p.loss, quad_sum(sum)); // tile order: fixed
             }
-            fsum += loss_post(p.loss, quad_sum(sum));
         }
 
         if constexpr (GRAD)
         {
-            // ----- the eight dL tiles meet in shared memory: [64 rows][kFdLdd], rows beyond the data carry dL = 0 -----
-            double* tiles = dl_tiles + parity * (kFrGroupRows * kFdLdd);
+            // ----- the dL tiles meet in shared memory: [rows of the group][kFdLdd], rows beyond the data carry dL = 0 -----
+            double* tiles = dl_tiles + parity * (kRows * kFdLdd);
 #pragma unroll
-            for (int nt = 0; nt < NT8; ++nt)
+            for (int u = 0; u < TPW; ++u)
             {
-                gbsum[nt][0] += dl[nt][0];
-                gbsum[nt][1] += dl[nt][1];
-                *reinterpret_cast<double2*>(tiles + (warp * kFdRows + g) * kFdLdd + nt * 8 + tig * 2) =
-                    make_double2(dl[nt][0], dl[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
+                {
+                    gbsum[nt][0] += dl[u][nt][0];
+                    gbsum[nt][1] += dl[u][nt][1];
+                    *reinterpret_cast<double2*>(tiles + ((u * kFdWarps + warp) * kFdRows + g) * kFdLdd + nt * 8 + tig * 2) =
+                        make_double2(dl[u][nt][0], dl[u][nt][1]);
+                }
             }
             named_bar_sync(1, kFdWarps * 32);
             parity ^= 1;
-            // ----- backward, split over columns: gW[:, slice] += dL^T X[:, slice]; k runs over the 64 rows -----
+            // ----- backward, split over columns: gW[:, slice] += dL^T X[:, slice]; k runs over the group's rows -----
 #pragma unroll
-            for (int kk = 0; kk < 2 * kFrGroup; ++kk)
+            for (int kk = 0; kk < 2 * kTiles; ++kk)
             {
                 const int r = kk * 4 + tig;
                 double    a[NT8];

@@ -504,11 +504,11 @@ def test_feature_split_kernel_still_covers_short_rows(ctx, oracle, monkeypatch, 
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# a handful of targets over short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh): 3 <= T <= 16, even D <= 256
+# a handful of targets over short rows: the row-split tensor-pipe kernel (vgrad_fr.cuh): 2 <= T <= 16, even D <= 256
 # ----------------------------------------------------------------------------------------------------------------
 FR_SHAPES = [(3000, 256, 10), (999, 100, 10), (77, 18, 5), (1, 64, 4), (63, 2, 3), (64, 4, 16), (65, 200, 16),
              (129, 128, 8), (500, 130, 3), (1000, 128, 7), (4099, 256, 16), (640, 254, 9), (2051, 66, 13),
-             (148 * 64 * 2 + 1, 32, 10)]
+             (148 * 64 * 2 + 1, 32, 10), (1000, 128, 2), (40, 2, 2)]
 
 
 @pytest.mark.parametrize("N,D,T", FR_SHAPES)
@@ -518,7 +518,7 @@ def test_short_rows_row_split_tensor_parity(ctx, oracle, N, D, T, loss_id):
     if loss_id.startswith("m-"):
         Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
     function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
-    assert function.describe().startswith("fr"), function.describe()  # the heuristic choice for D <= 256, T >= 3
+    assert function.describe().startswith("fr"), function.describe()  # the heuristic choice for D <= 256, T <= 16
     fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
     g2 = np.empty_like(x)
     assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
