@@ -90,6 +90,9 @@ def test_hot_kernels_keep_their_code_generation(library):
         "_ZN5nb20015vgrad_fd_kernelILi2ELi13ELi1ELb1EEEvNS_9fd_paramsE": 32,               # 784 x 10
         "_ZN5nb20015vgrad_fd_kernelILi1ELi32ELi2ELb1EEEvNS_9fd_paramsE": 0,                # 1024 x 8
         "_ZN5nb20015vgrad_ft_kernelILi2ELi2ELi8ELi1ELb1EEEvNS_9ft_paramsE": 0,             # 1024 x 2
+        "_ZN5nb20015vgrad_fr_kernelILi2ELi4ELi1ELb1EEEvNS_9fd_paramsE": 32,                # 256 x 10 (row-split)
+        "_ZN5nb20015vgrad_fr_kernelILi2ELi2ELi2ELb1EEEvNS_9fd_paramsE": 32,                # 100 x 10
+        "_ZN5nb20015vgrad_fr_kernelILi1ELi4ELi1ELb1EEEvNS_9fd_paramsE": 0,                 # 256 x 2..8
     }
     for name, limit in limits.items():
         assert name in stack, name
