@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(128) probe_read_kernel(const unsigned char* __
             sum += *reinterpret_cast<const double*>(stages + s * kTile + (tile & 31) * 8);
             if (next < tiles)
             {
+                // the load above before the refill below (generic proxy -> async proxy, see mbar_release_stage)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bars + s, kTile);
                 bulk_copy_g2s(stages + s * kTile, src + next * kTile, kTile, bars + s, policy);
                 next += gridDim.x;
