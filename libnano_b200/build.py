@@ -27,7 +27,7 @@ LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompil
 
 # translation units: the host layer + small kernels, four groups of single-target kernel variants, the tensor-pipe
 # kernels. They compile in parallel, and no kernel family's code depends on what else shares its module.
-UNITS = ["nb200_api.cu", "host_qp.cu", "kernels_t1_a.cu", "kernels_t1_b.cu", "kernels_t1_c.cu", "kernels_t1_d.cu", "kernels_mt.cu", "kernels_ft.cu", "kernels_fd.cu"]
+UNITS = ["nb200_api.cu", "host_qp.cu", "kernels_t1_a.cu", "kernels_t1_b.cu", "kernels_t1_c.cu", "kernels_t1_d.cu", "kernels_mt.cu", "kernels_ft.cu", "kernels_fd.cu", "kernels_fl.cu"]
 OBJ_DIR = os.path.join(CSRC, "build")
 
 

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "vgrad_fd.cuh"
+#include "vgrad_fl.cuh"
 #include "vgrad_fr.cuh"
 #include "vgrad_ft.cuh"
 #include "vgrad_mt.cuh"
@@ -52,7 +53,9 @@ using fd_kernel_t = void (*)(const fd_params);
 struct fd_variant
 {
     int         NT8, NS8, NSETS; // covers T <= 8 * NT8 and D <= (64 / NSETS) * NS8; NSETS < 0: the row-split kernel of
-                                 // vgrad_fr.cuh (short rows, D <= 64 * NS8) with -NSETS tiles per warp and group
+                                 // vgrad_fr.cuh (short rows, D <= 64 * NS8) with -NSETS tiles per warp and group;
+                                 // NSETS >= 10: the kernel of vgrad_fl.cuh (D <= 64 * NS8) with NSETS - 10 tiles per
+                                 // iteration
     int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / fr_header(TPW))
     fd_kernel_t grad;
     fd_kernel_t value;
@@ -95,4 +98,5 @@ const t1_variant* t1_group_d(int* count);
 const mt_variant* mt_variants(int* count);
 const ft_variant* ft_variants(int* count);
 const fd_variant* fd_variants(int* count);
+const fd_variant* fl_variants(int* count);
 } // namespace nb200

@@ -92,9 +92,24 @@ const t1_variant* const kT1Variants    = kT1Table.entries.data();
 const int               kNumT1Variants = static_cast<int>(kT1Table.entries.size());
 constexpr int           kNumT1Heuristic = 17; // entries scanned by the fall-back heuristic
 
-int               g_num_fd_variants = 0;
-const fd_variant* const kFdVariants    = fd_variants(&g_num_fd_variants);
-const int               kNumFdVariants = g_num_fd_variants;
+// (kernels_fd.cu: the row-split and the feature-split kernels; kernels_fl.cu: the feature-split kernel with the loss
+// spread over the lanes, NSETS >= 10)
+struct fd_table_t
+{
+    std::vector<fd_variant> entries;
+    fd_table_t()
+    {
+        for (const auto group : {fd_variants, fl_variants})
+        {
+            int               count = 0;
+            const fd_variant* first = group(&count);
+            entries.insert(entries.end(), first, first + count);
+        }
+    }
+};
+const fd_table_t        kFdTable;
+const fd_variant* const kFdVariants    = kFdTable.entries.data();
+const int               kNumFdVariants = static_cast<int>(kFdTable.entries.size());
 
 int               g_num_ft_variants = 0;
 const ft_variant* const kFtVariants    = ft_variants(&g_num_ft_variants);
@@ -181,17 +196,65 @@ struct fd_plan
 };
 
 // W (T x ld) and at least two stages of 8 padded rows must fit next to the header; false otherwise
+// lane_loss: 0 never the kernel of vgrad_fl.cuh, 1 where it wins (two target tiles), 2 wherever it fits
 bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan,
-             const bool row_split_ok = false)
+             const bool row_split_ok = false, const int lane_loss = 0)
 {
     static const bool fd_one_set = env_int("NB200_FD_ONE_SET", 0) != 0; // A/B knob (tools/gpu_round44.sh)
+    const int         fl_tpi     = env_int("NB200_FL_TPI", 0);          // A/B knob: tiles per iteration (0: by room)
     if (!(N > 0 && D > 0 && D % 2 == 0 && T >= 2))
     {
         return false;
     }
+    // the feature-split kernels with the loss spread over the lanes (vgrad_fl.cuh): rows longer than the row-split
+    // kernel takes; iterations of TPI 8-row tiles, one ring stage per tile. Both hold the TPI stages of an iteration;
+    // room for as many again in flight (at least two) is asked for. Shared rows are as short as the fragment loads
+    // allow (ld = 4 mod 8), and 512 bytes of slack follow the last stage (the last warps' slices may reach past ld).
+    const int fl_pipe = env_int("NB200_FL_PIPE", 1); // A/B knob: 0 without the pipelined kernel
+    // (second pass: the pipelined kernel with one tile per iteration and a single stage in flight, like vgrad_fd.cuh)
+    for (int v = 0; v < 2 * kNumFdVariants && lane_loss > 0 && !(row_split_ok && D <= 256); ++v)
+    {
+        const bool        tight = v >= kNumFdVariants;
+        const fd_variant& var   = kFdVariants[v % kNumFdVariants];
+        const bool        pipe  = var.NSETS >= 20;
+        const int         tpi   = var.NSETS - (pipe ? 20 : 10);
+        if (var.NSETS < 10 || 8 * var.NT8 < T || 64LL * var.NS8 < D || (lane_loss < 2 && var.NT8 < 2) ||
+            (fl_tpi > 0 && tpi != fl_tpi) || (pipe && fl_pipe == 0) || (tight && !(pipe && tpi == 1)))
+        {
+            continue;
+        }
+        const int64_t slice   = 8LL * var.NS8;
+        const int64_t ld      = (D + 3) / 8 * 8 + 4; // the smallest value = 4 (mod 8) that is >= D: conflict-free loads
+        const int64_t w_bytes = round_up(T * ld * 8, 128);
+        const int64_t x_bytes = kFdRows * ld * 8;
+        const int64_t stride  = round_up(x_bytes + round_up(kFdRows * T * 8, 128), 128);
+        const int64_t offset  = var.header + w_bytes;
+        const int64_t stages  = std::min<int64_t>(std::min<int64_t>(kFlMaxStages, env_int("NB200_FD_STAGES", kFlMaxStages)),
+                                                (smem_optin - 512 - offset) / stride);
+        if (stages < (tight ? 2 : std::max(2 * tpi, tpi + 2)))
+        {
+            continue;
+        }
+        plan.variant      = v % kNumFdVariants;
+        plan.slice        = static_cast<int>(slice);
+        plan.ld           = static_cast<int>(ld);
+        plan.stages       = static_cast<int>(stages);
+        plan.stage_stride = static_cast<int>(stride);
+        plan.y_offset     = static_cast<int>(x_bytes);
+        plan.w_offset     = var.header;
+        plan.stage_offset = static_cast<int>(offset);
+        plan.smem_bytes   = static_cast<int>(offset + stages * stride + 512);
+        plan.num_tiles    = (N + tpi * kFdRows - 1) / (tpi * kFdRows); // iterations
+        plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+        return plan.grid > 0;
+    }
     for (int v = 0; v < kNumFdVariants; ++v)
     {
         const fd_variant& var = kFdVariants[v];
+        if (var.NSETS >= 10)
+        {
+            continue;
+        }
         if (var.NSETS < 0)
         {
             // the row-split kernel (vgrad_fr.cuh): groups of 8 TPW tiles, one 8-row tile per ring stage, at least a
@@ -725,7 +788,7 @@ int setup_plan(nb200_obj* obj, const int forced_variant)
     // the CUDA-core kernel at these widths (256 x 2: 0.53 against 0.73 ms, 64 x 2: 1.34 against 2.60 at 2 GiB of X)
     const bool short_rows = D <= 256 && T >= 2 && T <= 16 && env_int("NB200_FR", 1) != 0;
     if (one_pass && forced_variant != -6 && (prefer_fd || short_rows || forced_variant == -5) &&
-        plan_fd(N, D, T, data->sm_count, data->smem_optin, handful, short_rows))
+        plan_fd(N, D, T, data->sm_count, data->smem_optin, handful, short_rows, env_int("NB200_FL", 1)))
     {
         const fd_variant& var = kFdVariants[handful.variant];
         NB200_CUDA_TRY(cudaFuncSetAttribute(var.grad, cudaFuncAttributeMaxDynamicSharedMemorySize, handful.smem_bytes));
@@ -2922,7 +2985,7 @@ int nb200_objective_describe(const nb200_obj* obj, char* buffer, const int64_t s
     else if (obj->use_fd)
     {
         const fd_variant& var = kFdVariants[obj->fd.variant];
-        text = std::string(var.NSETS < 0 ? "fr" : "fd") + " NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
+        text = std::string(var.NSETS < 0 ? "fr" : var.NSETS >= 20 ? "fl-pipe" : var.NSETS >= 10 ? "fl" : "fd") + " NT8=" + std::to_string(var.NT8) + " NS8=" + std::to_string(var.NS8) + " NSETS=" +
                std::to_string(var.NSETS) + " grid=" +
                std::to_string(obj->fd.grid) + " ld=" + std::to_string(obj->fd.ld) + " stages=" +
                std::to_string(obj->fd.stages) + " stage_bytes=" + std::to_string(obj->fd.stage_stride) +

@@ -482,7 +482,8 @@ def test_handful_of_targets_one_pass_tensor_parity(ctx, oracle, N, D, T, loss_id
         Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
     function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
     function.set_variant(-5)
-    assert function.describe().startswith(("fd", "fr")), function.describe()  # (short rows: the row-split kernel)
+    # (short rows: the row-split kernel; two target tiles: the lane-loss kernel)
+    assert function.describe().startswith(("fd", "fr", "fl")), function.describe()
     fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
     g2 = np.empty_like(x)
     assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
@@ -548,6 +549,48 @@ def test_short_rows_ragged_row_counts(ctx, oracle):
             assert rel_f(function(x), f_ref) <= PARITY
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# a handful of targets, rows of 256 .. 1024 features: the feature-split kernel with the loss spread over the lanes
+# (vgrad_fl.cuh); the heuristic choice for two target tiles (9 <= T <= 16), NB200_FL=2 also for T <= 8
+# ----------------------------------------------------------------------------------------------------------------
+FL_SHAPES = [(3000, 784, 10), (129, 512, 16), (2051, 832, 13), (65, 640, 15), (1000, 300, 9), (148 * 16 + 3, 258, 11),
+             (1, 384, 16), (4099, 1024, 8), (1537, 1000, 5), (2, 512, 6), (999, 320, 3), (777, 600, 2)]
+
+
+@pytest.mark.parametrize("pipelined", [1, 0])
+@pytest.mark.parametrize("tiles", [0, 1, 2])
+@pytest.mark.parametrize("N,D,T", FL_SHAPES)
+@pytest.mark.parametrize("loss_id", ["s-classnll", "mse", "m-logistic", "m-hinge", "mae"])
+def test_lane_loss_feature_split_tensor_parity(ctx, oracle, monkeypatch, N, D, T, loss_id, tiles, pipelined):
+    monkeypatch.setenv("NB200_FL", "2")  # (T <= 8 too)
+    monkeypatch.setenv("NB200_FL_TPI", str(tiles))  # tiles per iteration: by room / one / two
+    monkeypatch.setenv("NB200_FL_PIPE", str(pipelined))  # the pipelined kernel / the two-barrier kernel
+    X, Y, x = make_problem(N + 3 * D + T, N, D, T, is_classification(loss_id))
+    if loss_id.startswith("m-"):
+        Y = np.where(np.random.default_rng(N).uniform(-1, 1, (N, T)) < 0, -1.0, 1.0)
+    function = gpu_function(ctx, X, Y, loss_id, 0.1, 0.2)
+    function.set_variant(-5)
+    if not function.describe().startswith("fl"):
+        # (two tiles per iteration need room for four stages, the two-barrier kernel for three)
+        assert tiles == 2 or (pipelined == 0 and D > 800), function.describe()
+        pytest.skip("no room: " + function.describe())
+    fx, gx = check_against_oracle(oracle, function, X, Y, loss_id, x, 0.1, 0.2)
+    g2 = np.empty_like(x)
+    assert function(x, g2) == fx and np.array_equal(g2, gx)  # same input => same bits
+    function.set_variant(-3)
+    g3 = np.empty_like(x)
+    f3 = function(x, g3)
+    assert rel_f(f3, fx) <= 1e-13 and rel_g(g3, gx) <= 1e-13
+
+
+def test_lane_loss_kernel_can_be_switched_off(ctx, oracle, monkeypatch):
+    monkeypatch.setenv("NB200_FL", "0")
+    X, Y, x = make_problem(5, 1000, 784, 10, True)
+    function = gpu_function(ctx, X, Y, "s-classnll", 0.1, 0.2)
+    assert function.describe().startswith("fd"), function.describe()
+    check_against_oracle(oracle, function, X, Y, "s-classnll", x, 0.1, 0.2)
+
+
 def test_handful_of_targets_ragged_row_counts_and_heuristic(ctx, oracle):
     for D, T in ((300, 10), (784, 10), (512, 16)):
         rng = np.random.default_rng(D + T)
@@ -560,7 +603,8 @@ def test_handful_of_targets_ragged_row_counts_and_heuristic(ctx, oracle):
         for N in counts:
             X, Y = Xall[:N], Yall[:N]
             function = gpu_function(ctx, X, Y, "s-classnll", 0.0, 1e-2)
-            assert function.describe().startswith("fd"), function.describe()  # the heuristic choice from T = 5
+            # the heuristic choice from T = 5: two target tiles on the lane-loss kernel
+            assert function.describe().startswith("fl" if T > 8 else "fd"), function.describe()
             gx = np.empty_like(x)
             fx = function(x, gx)
             f_ref, g_ref = oracle.linear_vgrad(X, Y, "s-classnll", x, l2=1e-2)
