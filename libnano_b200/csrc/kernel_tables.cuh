@@ -56,7 +56,8 @@ struct fd_variant
                                  // vgrad_fr.cuh (short rows, D <= 64 * NS8) with -NSETS tiles per warp and group;
                                  // NSETS >= 10: the kernel of vgrad_fl.cuh (D <= 64 * NS8) with NSETS - 10 tiles per
                                  // iteration
-    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / fr_header(TPW))
+    int         header;   // bytes of the shared-memory header (fd_layout<NT8>::kHeader / fr_header(TPW) / ...)
+    int         threads;  // threads per CTA
     fd_kernel_t grad;
     fd_kernel_t value;
 };

@@ -6,10 +6,10 @@ namespace nb200
 namespace
 {
 #define NB200_FD_ENTRY(NT8, NS8, NSETS)                                                                                \
-    fd_variant{NT8, NS8, NSETS, fd_layout<NT8>::kHeader, vgrad_fd_kernel<NT8, NS8, NSETS, true>,                       \
+    fd_variant{NT8, NS8, NSETS, fd_layout<NT8>::kHeader, kFdThreads, vgrad_fd_kernel<NT8, NS8, NSETS, true>,                       \
                vgrad_fd_kernel<NT8, NS8, NSETS, false>}
 #define NB200_FR_ENTRY(NT8, NS8, TPW)                                                                                  \
-    fd_variant{NT8, NS8, -(TPW), fr_header(TPW), vgrad_fr_kernel<NT8, NS8, TPW, true>,                                 \
+    fd_variant{NT8, NS8, -(TPW), fr_header(TPW), kFdThreads, vgrad_fr_kernel<NT8, NS8, TPW, true>,                                 \
                vgrad_fr_kernel<NT8, NS8, TPW, false>}
 // the first entry that covers (T, D) is taken: short rows go to the row-split kernel (vgrad_fr.cuh) where the caller
 // allows it; for T <= 8 two alternating sets of four warps (each warp twice the columns)

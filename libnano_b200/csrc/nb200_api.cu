@@ -196,7 +196,7 @@ struct fd_plan
 };
 
 // W (T x ld) and at least two stages of 8 padded rows must fit next to the header; false otherwise
-// lane_loss: 0 never the kernel of vgrad_fl.cuh, 1 where it wins (two target tiles), 2 wherever it fits
+// lane_loss: 0 never the kernels of vgrad_fl.cuh, 1 where they win, 2 wherever they fit
 bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_count, const int smem_optin, fd_plan& plan,
              const bool row_split_ok = false, const int lane_loss = 0)
 {
@@ -207,46 +207,78 @@ bool plan_fd(const int64_t N, const int64_t D, const int64_t T, const int sm_cou
         return false;
     }
     // the feature-split kernels with the loss spread over the lanes (vgrad_fl.cuh): rows longer than the row-split
-    // kernel takes; iterations of TPI 8-row tiles, one ring stage per tile. Both hold the TPI stages of an iteration;
-    // room for as many again in flight (at least two) is asked for. Shared rows are as short as the fragment loads
-    // allow (ld = 4 mod 8), and 512 bytes of slack follow the last stage (the last warps' slices may reach past ld).
-    const int fl_pipe = env_int("NB200_FL_PIPE", 1); // A/B knob: 0 without the pipelined kernel
-    // (second pass: the pipelined kernel with one tile per iteration and a single stage in flight, like vgrad_fd.cuh)
-    for (int v = 0; v < 2 * kNumFdVariants && lane_loss > 0 && !(row_split_ok && D <= 256); ++v)
+    // kernel takes. Shared rows are as short as the fragment loads allow (ld = 4 mod 8), and 512 bytes of slack follow
+    // the last stage (the last warps' slices may reach past ld). Three forms, tried in the order that measured
+    // fastest (profiles/r02_lane_loss_sweep.jsonl): 'L2' / 'L1' = two barriers per iteration of two / one 8-row tiles
+    // (they hold the iteration's stages: room for as many again in flight is asked for, at least two), 'P' = the
+    // pipeline with the loss on its own warps (one tile per iteration, two stages in flight, one when nothing else fits).
+    //   rows up to 512 features: L2 (the per-iteration latency is shared by 16 rows), then P, then L1;
+    //   longer rows: P; one target tile (T <= 8) and 512 < D <= 800: vgrad_fd.cuh's two alternating warp sets stay.
+    // NB200_FL=2: wherever a form fits; NB200_FL_PIPE=0 / 2: never / always P first; NB200_FL_TPI: only that L form.
+    const int fl_pipe = env_int("NB200_FL_PIPE", 1);
+    if (lane_loss > 0 && T <= 16 && D > 256)
     {
-        const bool        tight = v >= kNumFdVariants;
-        const fd_variant& var   = kFdVariants[v % kNumFdVariants];
-        const bool        pipe  = var.NSETS >= 20;
-        const int         tpi   = var.NSETS - (pipe ? 20 : 10);
-        if (var.NSETS < 10 || 8 * var.NT8 < T || 64LL * var.NS8 < D || (lane_loss < 2 && var.NT8 < 2) ||
-            (fl_tpi > 0 && tpi != fl_tpi) || (pipe && fl_pipe == 0) || (tight && !(pipe && tpi == 1)))
+        const int   nt8 = T > 8 ? 2 : 1;
+        const char* order;
+        if (fl_pipe >= 2)
         {
-            continue;
+            order = "P21";
         }
-        const int64_t slice   = 8LL * var.NS8;
-        const int64_t ld      = (D + 3) / 8 * 8 + 4; // the smallest value = 4 (mod 8) that is >= D: conflict-free loads
-        const int64_t w_bytes = round_up(T * ld * 8, 128);
-        const int64_t x_bytes = kFdRows * ld * 8;
-        const int64_t stride  = round_up(x_bytes + round_up(kFdRows * T * 8, 128), 128);
-        const int64_t offset  = var.header + w_bytes;
-        const int64_t stages  = std::min<int64_t>(std::min<int64_t>(kFlMaxStages, env_int("NB200_FD_STAGES", kFlMaxStages)),
-                                                (smem_optin - 512 - offset) / stride);
-        if (stages < (tight ? 2 : std::max(2 * tpi, tpi + 2)))
+        else if (D <= 512)
         {
-            continue;
+            order = "2P1";
         }
-        plan.variant      = v % kNumFdVariants;
-        plan.slice        = static_cast<int>(slice);
-        plan.ld           = static_cast<int>(ld);
-        plan.stages       = static_cast<int>(stages);
-        plan.stage_stride = static_cast<int>(stride);
-        plan.y_offset     = static_cast<int>(x_bytes);
-        plan.w_offset     = var.header;
-        plan.stage_offset = static_cast<int>(offset);
-        plan.smem_bytes   = static_cast<int>(offset + stages * stride + 512);
-        plan.num_tiles    = (N + tpi * kFdRows - 1) / (tpi * kFdRows); // iterations
-        plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
-        return plan.grid > 0;
+        else if (nt8 == 2 || D > 800 || lane_loss >= 2)
+        {
+            order = "P21";
+        }
+        else
+        {
+            order = "";
+        }
+        for (const char* kind = order; *kind != '\0'; ++kind)
+        {
+            for (int tight = 0; tight < 2; ++tight)
+            {
+                for (int v = 0; v < kNumFdVariants; ++v)
+                {
+                    const fd_variant& var  = kFdVariants[v];
+                    const bool        pipe = var.NSETS >= 20;
+                    const int         tpi  = var.NSETS - (pipe ? 20 : 10);
+                    if (var.NSETS < 10 || var.NT8 != nt8 || 64LL * var.NS8 < D || pipe != (*kind == 'P') ||
+                        (!pipe && tpi != *kind - '0') || (!pipe && fl_tpi > 0 && tpi != fl_tpi) ||
+                        (pipe && fl_pipe == 0) || (tight == 1 && !pipe))
+                    {
+                        continue;
+                    }
+                    const int64_t slice   = 8LL * var.NS8;
+                    const int64_t ld      = (D + 3) / 8 * 8 + 4; // the smallest value = 4 (mod 8) that is >= D
+                    const int64_t w_bytes = round_up(T * ld * 8, 128);
+                    const int64_t x_bytes = kFdRows * ld * 8;
+                    const int64_t stride  = round_up(x_bytes + round_up(kFdRows * T * 8, 128), 128);
+                    const int64_t offset  = var.header + w_bytes;
+                    const int64_t stages =
+                        std::min<int64_t>(std::min<int64_t>(kFlMaxStages, env_int("NB200_FD_STAGES", kFlMaxStages)),
+                                          (smem_optin - 512 - offset) / stride);
+                    if (stages < (tight == 1 ? 2 : std::max(2 * tpi, tpi + 2)))
+                    {
+                        continue;
+                    }
+                    plan.variant      = v;
+                    plan.slice        = static_cast<int>(slice);
+                    plan.ld           = static_cast<int>(ld);
+                    plan.stages       = static_cast<int>(stages);
+                    plan.stage_stride = static_cast<int>(stride);
+                    plan.y_offset     = static_cast<int>(x_bytes);
+                    plan.w_offset     = var.header;
+                    plan.stage_offset = static_cast<int>(offset);
+                    plan.smem_bytes   = static_cast<int>(offset + stages * stride + 512);
+                    plan.num_tiles    = (N + tpi * kFdRows - 1) / (tpi * kFdRows); // iterations
+                    plan.grid         = static_cast<int>(std::min<int64_t>(plan.num_tiles, sm_count));
+                    return plan.grid > 0;
+                }
+            }
+        }
     }
     for (int v = 0; v < kNumFdVariants; ++v)
     {
@@ -1160,7 +1192,7 @@ int enqueue_eval(nb200_obj* obj, const double* x_dev, const bool want_grad, cons
         f.stage_offset = obj->fd.stage_offset;
         f.loss         = obj->loss;
         f.loss_param   = obj->loss_param;
-        (want_grad ? var.grad : var.value)<<<obj->fd.grid, kFdThreads, obj->fd.smem_bytes, obj->stream>>>(f);
+        (want_grad ? var.grad : var.value)<<<obj->fd.grid, var.threads, obj->fd.smem_bytes, obj->stream>>>(f);
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;
         status = timing_end(obj);
@@ -3283,7 +3315,7 @@ static int vgrad_batch_impl(nb200_obj* obj, const int64_t K, const double* x, co
         q.stage_offset = bs.fd.stage_offset;
         q.loss         = obj->loss;
         q.loss_param   = obj->loss_param;
-        (grad ? one.grad : one.value)<<<bs.fd.grid, kFdThreads, bs.fd.smem_bytes, st>>>(q);
+        (grad ? one.grad : one.value)<<<bs.fd.grid, one.threads, bs.fd.smem_bytes, st>>>(q);
         NB200_CUDA_TRY(cudaGetLastError());
         obj->launches += 1;
         status = timing_end(obj);

@@ -2,13 +2,13 @@
 # One GPU: parity of the lane-loss kernels (vgrad_fl.cuh), then the A/B sweep against the kernels they replace.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "lane_loss or handful" > gpurun_out/fl_tests.log 2>&1
+timeout 240 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "lane_loss or handful or feature_split" > gpurun_out/fl_tests.log 2>&1
 echo "fl tests rc=$?"; tail -5 gpurun_out/fl_tests.log
 SHAPES="784,10,s-classnll;512,16,s-classnll;640,12,s-classnll;384,10,s-classnll;832,13,mse;1024,8,s-classnll;768,8,s-classnll;512,8,s-classnll;1000,5,s-classnll;512,6,m-logistic;320,4,s-classnll"
 : > gpurun_out/fl_sweep.jsonl
-for mode in "0 0 1" "2 0 1" "2 1 1" "2 0 0" "2 1 0"; do
+for mode in ${FL_MODES:-"1 0 1" "2 0 2"}; do
   set -- $mode
   echo "{\"NB200_FL\": $1, \"NB200_FL_TPI\": $2, \"NB200_FL_PIPE\": $3}" >> gpurun_out/fl_sweep.jsonl
-  NB200_FL=$1 NB200_FL_TPI=$2 NB200_FL_PIPE=$3 timeout 300 python tools/sweep_multi.py --shapes "$SHAPES" --gib 2 --seconds 0.5 >> gpurun_out/fl_sweep.jsonl 2> gpurun_out/fl_sweep.err
+  NB200_FL=$1 NB200_FL_TPI=$2 NB200_FL_PIPE=$3 timeout 120 python tools/sweep_multi.py --shapes "$SHAPES" --gib 2 --seconds 0.5 >> gpurun_out/fl_sweep.jsonl 2> gpurun_out/fl_sweep.err
   echo "sweep $mode rc=$?"
 done
