@@ -516,6 +516,54 @@ def fp64_peaks(h, ctx):
     return peaks
 
 
+def bench_handful_of_targets(h, nb, ctx, peaks, hbm_peak, steps=20, warmup=5):
+    """Not a BASELINE config: the one-pass tensor-pipe kernels for a handful of targets, softmax over
+    2 GiB of X per shape. Two ceilings per case: X read once from HBM, and the fp64 tensor pipe with the targets padded
+    to whole m8n8k4 tiles (T = 10 occupies 16 columns)."""
+    import oracle
+
+    torch = h.torch
+    cases = []
+    for D, T in ((784, 10), (512, 16), (1024, 8)):
+        N = (1 << 31) // (8 * D)
+        data = nb.Dataset.synth(ctx, nb.SYNTH_MULTICLASS, N, D, T=T, seed=SEED)
+        function = nb.LinearFunction(data, nb.Loss("s-classnll"), 0.0, L2REG)
+        function.set_stream(torch.cuda.current_stream().cuda_stream)
+        n = function.size()
+        x = np.random.default_rng(0).uniform(-1.0, 1.0, n) / np.sqrt(D)
+        x_dev = torch.from_numpy(x).cuda()
+        g_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+        f_dev = torch.empty(1, dtype=torch.float64, device="cuda")
+
+        def step():
+            function.vgrad_device(x_dev.data_ptr(), g_dev.data_ptr(), f_dev.data_ptr())
+
+        burst = h.region(step, function, steps, warmup, settle=0.5)
+        ms = burst["ms"] / steps
+        padded = 4.0 * N * D * ((T + 7) // 8 * 8)
+        entry = {"features": D, "targets": T, "rows": N, "loss": "s-classnll", "kernel": function.describe(),
+                 "ms": ms, "x_once_gbs": 8.0 * N * D / ms / 1e6, "frac_of_hbm_copy_peak": 8.0 * N * D / ms / 1e6 / hbm_peak,
+                 "tflops": 4.0 * N * D * T / ms / 1e9, "padded_tflops": padded / ms / 1e9,
+                 "frac_of_dmma_peak_padded": padded / ms / 1e9 / peaks["dmma_tflops"],
+                 "clocks": h.sampler.window(*burst["window"])}
+        sample_rows = 2048
+        Xs, Ys = data.read(0, sample_rows)
+        small = nb.LinearFunction(nb.Dataset.pin(ctx, Xs, Ys), nb.Loss("s-classnll"), 0.0, L2REG)
+        gx = np.empty(n)
+        fx = small(x, gx)
+        entry["parity"] = dict(oracle_parity(oracle, Xs, Ys, "s-classnll", x, 0.0, L2REG, fx, gx), rows=sample_rows,
+                               same_plan=small.describe().split(" ")[0] == function.describe().split(" ")[0])
+        small.close()
+        function.close()
+        data.close()
+        del x_dev, g_dev, f_dev
+        torch.cuda.empty_cache()
+        cases.append(entry)
+    return {"workload": "softmax linear models with a handful of classes, 2 GiB of X per shape, fp64 vgrad (one pass "
+                        "over X, both contractions on the fp64 tensor pipe)",
+            "metric": "vgrad ms", "unit": "ms", "higher_is_better": False, "steps": steps, "cases": cases}
+
+
 def bench_config3(h, nb, ctx, peaks, steps=5, warmup=3):
     """BASELINE configs[2]: softmax cross-entropy, 2^22 x 2048 x 100 fp64 — a dense contraction on the FP64 tensor pipe
     (mma.sync m8n8k4 f64; tcgen05 has no fp64 kind). flops_alg = 4*N*D*T per vgrad."""
@@ -834,6 +882,7 @@ def run_b200(args):
         configs["cfg3"] = bench_config3(h, nb, ctx, peaks)
         configs["cfg5"] = bench_streaming_config(h, nb, ctx, "cfg5", "s-hinge", 1 << 24, 512, 1e-2, 0.0, peak,
                                                  peak_source, args.steps, args.warmup)
+        configs["handful_of_targets"] = bench_handful_of_targets(h, nb, ctx, peaks, peak)
         line["configs"] = configs
         bad = [name for name, entry in configs.items()
                if not all(case.get("parity", {}).get("ok", True) for case in entry.get("cases", [entry]))

@@ -819,23 +819,30 @@ __global__ void __launch_bounds__(fp_threads(NT8), 1) vgrad_fp_kernel(const fd_p
         }
     }
     auto backward_previous = [&](const uint32_t parity) {
+        // (ncu: a shared-memory load takes a few hundred cycles here — the eight warps' fragment loads queue in front
+        // of it —, and the first DMMA behind each of the A fragments holds ~5 % of the consumers' stall samples; ptxas
+        // orders the 52 DMMAs by A fragment whatever the source order is)
         const double* dl_prev = dl_tiles + parity * (kFdRows * kFdLdd);
+        double        a[2][NT8];
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
         {
-            double a[NT8];
 #pragma unroll
             for (int mt = 0; mt < NT8; ++mt)
             {
-                a[mt] = dl_prev[(kk * 4 + tig) * kFdLdd + mt * 8 + g];
+                a[kk][mt] = dl_prev[(kk * 4 + tig) * kFdLdd + mt * 8 + g];
             }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+        {
 #pragma unroll
             for (int ns = 0; ns < NS8; ++ns)
             {
 #pragma unroll
                 for (int mt = 0; mt < NT8; ++mt)
                 {
-                    dmma_m8n8k4(gacc[mt][ns][0], gacc[mt][ns][1], a[mt], xb[kk][ns]);
+                    dmma_m8n8k4(gacc[mt][ns][0], gacc[mt][ns][1], a[kk][mt], xb[kk][ns]);
                 }
             }
         }

@@ -74,6 +74,18 @@ def test_register_hand_over_matches_the_allocation(library):
             assert int(regs) <= 255 and int(regs) * threads <= 65536 + 255, (ncw, regs)
 
 
+def test_lane_loss_pipeline_register_requests_fit_the_pool(library):
+    # vgrad_fp_kernel (vgrad_fl.cuh): consumers 208 / 192 registers, the producer, loss and value warps 80 / 64; the
+    # pool setmaxnreg moves registers in is threads x the launch allocation — a request beyond it blocks for ever
+    # (measured the hard way: a 21-minute hang on the B200)
+    out = subprocess.run(["cuobjdump", "-res-usage", library._name], capture_output=True, text=True).stdout
+    found = re.findall(r"vgrad_fp_kernelILi(\d+)ELi\d+ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
+    assert len(found) >= 20
+    for nt8, regs in found:
+        threads, consumer, other = (384, 208, 80) if nt8 == "1" else (512, 192, 64)
+        assert 256 * consumer + (threads - 256) * other <= threads * int(regs), (nt8, regs)
+
+
 def test_hot_kernels_keep_their_code_generation(library):
     # guards against silent code-generation regressions of the kind found in round 1 (one translation unit under
     # -split-compile: adding unrelated kernels changed mt_backward_kernel's SASS and cost config 3 15 %): the hot
@@ -93,6 +105,9 @@ def test_hot_kernels_keep_their_code_generation(library):
         "_ZN5nb20015vgrad_fr_kernelILi2ELi4ELi1ELb1EEEvNS_9fd_paramsE": 32,                # 256 x 10 (row-split)
         "_ZN5nb20015vgrad_fr_kernelILi2ELi2ELi2ELb1EEEvNS_9fd_paramsE": 32,                # 100 x 10
         "_ZN5nb20015vgrad_fr_kernelILi1ELi4ELi1ELb1EEEvNS_9fd_paramsE": 0,                 # 256 x 2..8
+        "_ZN5nb20015vgrad_fp_kernelILi2ELi13ELb1EEEvNS_9fd_paramsE": 64,                   # 784 x 10 (lane-loss pipeline)
+        "_ZN5nb20015vgrad_fp_kernelILi1ELi16ELb1EEEvNS_9fd_paramsE": 0,                    # 1024 x 8
+        "_ZN5nb20015vgrad_fl_kernelILi2ELi8ELi2ELb1EEEvNS_9fd_paramsE": 0,                 # 512 x 16 (two barriers)
     }
     for name, limit in limits.items():
         assert name in stack, name
