@@ -3142,7 +3142,7 @@ int nb200_cgd_minimize(nb200_obj* obj, double* x, const int64_t n, const int bet
 static bool plan_fd_batch(const int64_t N, const int64_t D, const int64_t Kp, const int sm_count, const int smem_optin,
                           fd_plan& plan)
 {
-    return Kp <= 16 && D >= 200 && plan_fd(N, D, Kp, sm_count, smem_optin, plan);
+    return Kp <= 16 && D >= 200 && plan_fd(N, D, Kp, sm_count, smem_optin, plan, false, env_int("NB200_FL", 1));
 }
 
 static int ensure_batch(nb200_obj* obj, const int64_t Kp)

@@ -30,7 +30,8 @@ KEEP = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
 ]
-NAMES = ("t1_2p23x1024", "t1_2p20x1024", "t1_2p24x512", "mt_262144x2048x100", "mt_forward", "mt_backward")  # gpu_ncu.sh
+NAMES = ("t1_2p23x1024", "t1_2p20x1024", "t1_2p24x512", "mt_262144x2048x100", "mt_forward", "mt_backward",  # gpu_ncu.sh
+         "fp_784x10", "fl_512x16")  # gpu_ncu_fl.sh
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -76,14 +77,16 @@ def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--round", default="r02")
     parser.add_argument("--src", default=os.path.join(ROOT, "gpurun_out"))
+    parser.add_argument("--only", default="", help="comma-separated capture names (default: all of NAMES)")
     args = parser.parse_args()
+    names = tuple(args.only.split(",")) if args.only else NAMES
     prof = os.path.join(ROOT, "profiles")
     traffic_path = os.path.join(prof, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else []
     for name in sorted(os.listdir(args.src)):
         path = os.path.join(args.src, name)
         m = re.fullmatch(r"ncu_(.+)_raw\.csv", name)
-        if m and m.group(1) in NAMES:
+        if m and m.group(1) in names:
             dst = os.path.join(prof, f"{args.round}_ncu_full_{m.group(1)}.csv")
             header, units, body = raw_extract(path, dst)
             print("wrote", dst)
@@ -105,11 +108,11 @@ def main():
                 else:
                     traffic.append(entry)
         m = re.fullmatch(r"ncu_(.+)_source\.csv", name)
-        if m and m.group(1) in NAMES:
+        if m and m.group(1) in names:
             dst = os.path.join(prof, f"{args.round}_ncu_{m.group(1)}_source_top.csv")
             source_extract(path, dst)
             print("wrote", dst)
-        if name == "ncu_launches_bench.csv":
+        if name == "ncu_launches_bench.csv" and not args.only:
             shutil.copy(path, os.path.join(prof, f"{args.round}_launches_bench.csv"))
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print("updated", traffic_path)
