@@ -761,7 +761,10 @@ def test_full_size_known_answers_at_zero(ctx, N, D, T, loss_id, kind):
 @pytest.mark.parametrize("N,D,T,loss_id,kind,repeats", [
     (128 * 148 * 16, 2048, 100, "s-classnll", "multiclass", 60),   # tensor-map forward, 3 stages, 16 tiles per CTA
     (1 << 20, 2048, 128, "s-classnll", "multiclass", 8),           # tensor-map forward, 2 stages, T = 128
-    (1 << 21, 784, 10, "s-classnll", "multiclass", 20),            # one-pass tensor-pipe kernel
+    (1 << 21, 784, 10, "s-classnll", "multiclass", 20),            # one-pass tensor-pipe kernel (lane-loss pipeline)
+    (1 << 21, 512, 16, "s-classnll", "multiclass", 20),            # ... two barriers, two tiles per iteration
+    (1 << 20, 1024, 8, "m-logistic", "multiclass", 20),            # ... pipeline, one target tile, two stages
+    (1 << 21, 768, 8, "s-classnll", "multiclass", 12),             # ... two alternating warp sets (vgrad_fd.cuh)
     (1 << 22, 256, 10, "s-classnll", "multiclass", 20),            # ... its row-split cousin for short rows
     (1 << 22, 1024, 1, "s-logistic", "classification", 20),        # single-target kernel
 ])

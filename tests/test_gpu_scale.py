@@ -205,8 +205,9 @@ def test_full_size_properties(ctx, oracle, N, D, loss_id):
     assert function(x, g2) == fx and np.array_equal(g2, gx)
 
 
-@pytest.mark.parametrize("N,D,T,path", [(1 << 18, 2048, 100, "dmma"), (1 << 20, 784, 10, "fd"), (1 << 21, 512, 2, "ft"),
-                                        (1 << 20, 1024, 8, "fd"), (1 << 20, 1000, 4, "ft")])
+@pytest.mark.parametrize("N,D,T,path", [(1 << 18, 2048, 100, "dmma"), (1 << 20, 784, 10, "fl-pipe"), (1 << 21, 512, 2, "ft"),
+                                        (1 << 20, 1024, 8, "fl-pipe"), (1 << 20, 1000, 4, "ft"),
+                                        (1 << 20, 512, 16, "fl NT8=2 NS8=8 NSETS=12"), (1 << 20, 768, 8, "fd")])
 def test_full_size_properties_many_targets(ctx, oracle, N, D, T, path):
     # the multi-target paths at sizes the oracle cannot hold: BASELINE config 3's width (tensor-pipe pair) and the
     # one-pass kernels; same size-independent properties as above
