@@ -22,9 +22,7 @@
 // No predicates in the two contraction loops: stage rows past the data hold zeros or stale (finite) rows — their
 // outputs are masked in the loss step and their dL is 0 —, and W rows past T read whatever follows W in shared memory:
 // they only reach output columns >= T, which the loss step never looks at (selects, not products).
-// The softmax VALUE (a logarithm per row) is not on the way to dL: the rows' (sum exp, dot, max) go to one warp of the
-// producer warpgroup, which turns them into the loss while the consumers multiply.
-// Shared memory: barriers | partial outputs [8 warps][8 TPI][TPS] | dL [8 TPI][kFdLdd] | row statistics | W [T][ld] | stages.
+// Shared memory: barriers | partial outputs [8 warps][8 TPI][TPS] | dL [8 TPI][kFdLdd] | W [T][ld] | stages.
 // Same fd_params / launch code / partial rows as vgrad_fd.cuh (reduce_partials_kernel + finish_kernel fold them).
 #pragma once
 
@@ -33,7 +31,7 @@
 namespace nb200
 {
 constexpr int kFlMaxStages = 8;
-constexpr int kFlExchange  = 256; // after full [8] | empty [8] | stats_ready | stats_free
+constexpr int kFlExchange  = 128; // after full [8] | empty [8]
 
 __host__ __device__ constexpr int fl_tps(const int nt8)
 {
@@ -45,13 +43,9 @@ __host__ __device__ constexpr int fl_dl_offset(const int nt8, const int tpi)
     const int exchange = kFdWarps * kFdRows * tpi * fl_tps(nt8) * 8;
     return kFlExchange + (exchange < 3 * kFdWarps * 32 * 8 ? 3 * kFdWarps * 32 * 8 : exchange);
 }
-__host__ __device__ constexpr int fl_stats_offset(const int nt8, const int tpi)
-{
-    return fl_dl_offset(nt8, tpi) + kFdRows * tpi * kFdLdd * 8; // row statistics [8 TPI][4], then the value warp's sums [32]
-}
 __host__ __device__ constexpr int fl_header(const int nt8, const int tpi)
 {
-    return (fl_stats_offset(nt8, tpi) + kFdRows * tpi * 4 * 8 + 32 * 8 + 127) / 128 * 128;
+    return (fl_dl_offset(nt8, tpi) + kFdRows * tpi * kFdLdd * 8 + 127) / 128 * 128;
 }
 
 #ifdef __CUDACC__
@@ -94,13 +88,6 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
     uint64_t* empty_bar = full_bar + kFlMaxStages;
     double*   exchange  = reinterpret_cast<double*>(smem + kFlExchange);
     double*   dl_tile   = reinterpret_cast<double*>(smem + fl_dl_offset(NT8, TPI));
-    // softmax: the rows' (sum exp, dot, max) go to a warp of the producer warpgroup, which turns them into the loss —
-    // the logarithm is not on the way to dL, so it leaves the chain the tensor pipe waits for
-    uint64_t* stats_ready = full_bar + 2 * kFlMaxStages;
-    uint64_t* stats_free  = stats_ready + 1;
-    double*   row_stats   = reinterpret_cast<double*>(smem + fl_stats_offset(NT8, TPI)); // [RI][4]
-    double*   value_sums  = row_stats + RI * 4;                                          // [32]
-    const bool softmax    = p.loss == LOSS_CLASSNLL && p.y_broadcast == 0; // (batched single-output models: elementwise)
     double*   w_s       = reinterpret_cast<double*>(smem + p.w_offset);
 
     const int warp = threadIdx.x >> 5;
@@ -118,8 +105,6 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, kFdWarps);
         }
-        mbar_init(stats_ready, kFdWarps);
-        mbar_init(stats_free, 1);
         mbar_fence_init();
     }
     // the stages start as zeros (rows that are never copied and the pad columns [D, ld) multiply as zero), then W
@@ -147,36 +132,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
     if (warp >= kFdWarps)
     {
         // ===== producer warpgroup: one warp feeds the ring, one stage per 8-row tile, one bulk copy per row =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
-        if (warp == kFdWarps + 1)
-        {
-            // ===== value warp (softmax only): lane r < 8 TPI owns row r of every iteration — classnll.h:19-37:
-            // log(sum exp(o - max)) - 0.5 (1 + y) . o + max =====
-            double   fsum = 0.0;
-            uint32_t par  = 0;
-            for (int64_t it = blockIdx.x; softmax && it < iterations; it += gridDim.x)
-            {
-                mbar_wait(stats_ready, par);
-                double sumexp = 1.0, dot = 0.0, omax = 0.0;
-                if (lane < RI)
-                {
-                    sumexp = row_stats[lane * 4 + 0];
-                    dot    = row_stats[lane * 4 + 1];
-                    omax   = row_stats[lane * 4 + 2];
-                }
-                __syncwarp();
-                if (lane == 0)
-                {
-                    mbar_arrive(stats_free);
-                }
-                const double value = __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                fsum += (lane < RI && (it * TPI) * kFdRows + lane < p.N) ? value : 0.0;
-                par ^= 1u;
-            }
-            value_sums[lane] = (lane < RI) ? fsum : 0.0;
-            named_bar_sync(3, (kFdWarps + 1) * 32); // with the consumers' last step
-            return;
-        }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
         if (warp != kFdWarps)
         {
             return;
@@ -218,8 +174,8 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
         return;
     }
 
-    // ===== consumer warps ===== (registers: 256 x 224 + 128 x 56 = the 384 x 168 the launch allocated)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(224));
+    // ===== consumer warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
     const int c0 = warp * p.slice; // first column of this warp's slice (forward: K range, backward: N range)
     // k-steps of this warp in the forward: the shared rows are ld (= 4 mod 8, >= D) doubles long, the columns [D, ld)
     // are zero in X and W, and the slices of the last warps may reach past ld (backward: those columns are never stored;
@@ -250,7 +206,6 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
 
     int      stage_index = 0;
     uint32_t phase       = 0;
-    uint32_t stats_par   = 0;
     for (int64_t it = blockIdx.x; it < iterations; it += gridDim.x)
     {
         const unsigned char* stage[TPI];
@@ -372,29 +327,18 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
             }
             const double y  = el_ok ? (p.y_broadcast ? ys[r_g] : ys[r_g * T + lt]) : 0.0;
             double       dl = 0.0;
-            if (softmax)
+            if (p.loss == LOSS_CLASSNLL && p.y_broadcast == 0) // (batched single-output models: elementwise)
             {
-                // classnll.h:19-37: the TP lanes of a group hold the whole row; dL = softmax - 0.5 (1 + y), the value is
-                // left to the value warp
+                // classnll.h:19-37: the TP lanes of a group hold the whole row
                 const double omax   = group_max<TP>(el_ok ? o : -INFINITY);
                 const double ex     = el_ok ? exp(__dsub_rn(o, omax)) : 0.0;
                 const double sumexp = group_sum<TP>(ex);
                 const double dot    = group_sum<TP>(el_ok ? __dmul_rn(__dadd_rn(1.0, y), o) : 0.0);
-                const double grad   = __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y)));
-                dl                  = (GRAD && el_ok) ? grad : 0.0;
-                if (lane_on && lt == 0)
-                {
-                    mbar_wait(stats_free, stats_par ^ 1u); // the value warp has read the previous iteration's rows
-                    row_stats[r_it * 4 + 0] = sumexp;
-                    row_stats[r_it * 4 + 1] = dot;
-                    row_stats[r_it * 4 + 2] = omax;
-                }
-                __syncwarp();
-                if (lane == 0)
-                {
-                    mbar_arrive(stats_ready);
-                }
-                stats_par ^= 1u;
+                // (straight-line: the logarithm of the value and the division of the gradient overlap)
+                const double value = __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
+                const double grad  = __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y)));
+                fsum += (row_ok && lt == 0) ? value : 0.0;
+                dl = (GRAD && el_ok) ? grad : 0.0;
             }
             else
             {
@@ -491,15 +435,10 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
     fold[0 * kFdWarps * 32 + warp * 32 + lane] = (lane_on && lt == 0) ? fsum : 0.0;
     fold[1 * kFdWarps * 32 + warp * 32 + lane] = lane_on ? gbsum : 0.0;
     fold[2 * kFdWarps * 32 + warp * 32 + lane] = lane_on ? lsum : 0.0;
-    named_bar_sync(3, (kFdWarps + 1) * 32); // the consumers and the value warp
+    named_bar_sync(1, kFdWarps * 32);
     if (warp == 0 && lane < TP)
     {
         double f = 0.0, gb = 0.0, ls = 0.0;
-#pragma unroll
-        for (int r = 0; r < RI; ++r) // (the softmax values, row order)
-        {
-            f += value_sums[r];
-        }
         for (int q = 0; q < kFdWarps; ++q)
         {
 #pragma unroll

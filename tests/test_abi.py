@@ -84,11 +84,6 @@ def test_lane_loss_pipeline_register_requests_fit_the_pool(library):
     for nt8, regs in found:
         threads, consumer, other = (384, 208, 80) if nt8 == "1" else (512, 192, 64)
         assert 256 * consumer + (threads - 256) * other <= threads * int(regs), (nt8, regs)
-    # the two-barrier form: consumers 224, the producer warpgroup (producer + softmax value warp) 56
-    found = re.findall(r"vgrad_fl_kernelILi\d+ELi\d+ELi\d+ELb[01]E\w*:\s*\n\s*REG:(\d+)", out)
-    assert len(found) >= 40
-    for regs in found:
-        assert 256 * 224 + 128 * 56 <= 384 * int(regs), regs
 
 
 def test_hot_kernels_keep_their_code_generation(library):
@@ -112,7 +107,7 @@ def test_hot_kernels_keep_their_code_generation(library):
         "_ZN5nb20015vgrad_fr_kernelILi1ELi4ELi1ELb1EEEvNS_9fd_paramsE": 0,                 # 256 x 2..8
         "_ZN5nb20015vgrad_fp_kernelILi2ELi13ELb1EEEvNS_9fd_paramsE": 64,                   # 784 x 10 (lane-loss pipeline)
         "_ZN5nb20015vgrad_fp_kernelILi1ELi16ELb1EEEvNS_9fd_paramsE": 0,                    # 1024 x 8
-        "_ZN5nb20015vgrad_fl_kernelILi2ELi8ELi2ELb1EEEvNS_9fd_paramsE": 16,                # 512 x 16 (two barriers)
+        "_ZN5nb20015vgrad_fl_kernelILi2ELi8ELi2ELb1EEEvNS_9fd_paramsE": 0,                 # 512 x 16 (two barriers)
     }
     for name, limit in limits.items():
         assert name in stack, name
