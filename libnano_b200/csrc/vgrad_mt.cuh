@@ -197,12 +197,26 @@ __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, con
                 sumexp[j] = warp_allreduce_sum(sumexp[j]);
                 dot[j]    = warp_allreduce_sum(dot[j]);
             }
+            // every lane holds the R sums: lane j takes row j, so that the warp evaluates ONE logarithm and ONE
+            // reciprocal per step instead of R logarithms and R x TL divisions per lane (each a chain of dependent fp64
+            // instructions on the unit the DMMAs use), and the results go back by shuffles. exp(o - max) x (1 / sum)
+            // differs from the reference's quotient by at most one rounding (parity bar: 1e-12).
+            double mine = 1.0;
 #pragma unroll
             for (int j = 0; j < R; ++j)
             {
+                mine = (lane == j) ? sumexp[j] : mine;
+            }
+            const double my_log = log(mine);
+            const double my_rcp = __ddiv_rn(1.0, mine);
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const double lg  = __shfl_sync(0xffffffffu, my_log, j);
+                const double rcp = __shfl_sync(0xffffffffu, my_rcp, j);
                 if (live[j])
                 {
-                    fsum += __dadd_rn(__dsub_rn(log(sumexp[j]), __dmul_rn(0.5, dot[j])), omax[j]);
+                    fsum += __dadd_rn(__dsub_rn(lg, __dmul_rn(0.5, dot[j])), omax[j]);
                     if (GRAD)
                     {
                         const int64_t row = row_first + r0 + j;
@@ -213,7 +227,7 @@ __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, con
                             if (t < T)
                             {
                                 const double gv =
-                                    __dsub_rn(__ddiv_rn(ex[j][k], sumexp[j]), __dmul_rn(0.5, __dadd_rn(1.0, y[j][k])));
+                                    __dsub_rn(__dmul_rn(ex[j][k], rcp), __dmul_rn(0.5, __dadd_rn(1.0, y[j][k])));
                                 p.dL[row * dl_ld + t] = gv;
                                 gbacc[k] += gv;
                             }
