@@ -180,15 +180,14 @@ __device__ __forceinline__ void mt_epilogue_rows(const mt_forward_params& p, con
 #pragma unroll
                 for (int k = 0; k < TL; ++k)
                 {
-                    const int t = lane + 32 * k;
-                    ex[j][k]    = 0.0;
-                    if (t < T)
-                    {
-                        const double o = orow[t];
-                        ex[j][k]       = exp(__dsub_rn(o, omax[j]));
-                        sumexp[j] += ex[j][k];
-                        dot[j] += __dmul_rn(__dadd_rn(1.0, y[j][k]), o);
-                    }
+                    // (no branch: the R x TL exponentials of a lane are independent chains the compiler interleaves;
+                    // targets past T enter as -inf -> 0, and y is 0 there)
+                    const int    t  = lane + 32 * k;
+                    const bool   in = t < T;
+                    const double o  = orow[in ? t : 0];
+                    ex[j][k]        = exp_nonpositive(in ? __dsub_rn(o, omax[j]) : -INFINITY);
+                    sumexp[j] += ex[j][k];
+                    dot[j] += in ? __dmul_rn(__dadd_rn(1.0, y[j][k]), o) : 0.0;
                 }
             }
 #pragma unroll

@@ -98,7 +98,7 @@ def test_hot_kernels_keep_their_code_generation(library):
         "_ZN5nb20015vgrad_t1_kernelILi2ELi8ELi1ELi8ELi4ELi2ELb1EEEvNS_9t1_paramsE": 128,   # config 5 (33)
         "_ZN5nb20018mt_backward_kernelILi13EEEvNS_18mt_backward_paramsE": 0,               # config 3
         "_ZN5nb20017mt_forward_kernelILi13ELb1EEEvNS_17mt_forward_paramsE": 0,
-        "_ZN5nb20021mt_forward_tma_kernelILi13ELb1EEEvNS_17mt_forward_paramsE14CUtensorMap_st": 0,
+        "_ZN5nb20021mt_forward_tma_kernelILi13ELb1EEEvNS_17mt_forward_paramsE14CUtensorMap_st": 16,
         "_ZN5nb20015vgrad_fd_kernelILi2ELi13ELi1ELb1EEEvNS_9fd_paramsE": 32,               # 784 x 10
         "_ZN5nb20015vgrad_fd_kernelILi1ELi32ELi2ELb1EEEvNS_9fd_paramsE": 0,                # 1024 x 8
         "_ZN5nb20015vgrad_ft_kernelILi2ELi2ELi8ELi1ELb1EEEvNS_9ft_paramsE": 0,             # 1024 x 2
