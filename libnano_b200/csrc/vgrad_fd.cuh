@@ -388,34 +388,32 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
                 {
-                    ex[nt][j] = 0.0;
-                    if (nt * 8 + tig * 2 + j < T)
-                    {
-                        ex[nt][j] = exp(__dsub_rn(o[nt][j], omax));
-                        sumexp += ex[nt][j];
-                        dot += __dmul_rn(__dadd_rn(1.0, y[nt][j]), o[nt][j]);
-                    }
+                    // (no branch: the 2 NT8 exponentials of a lane are independent chains; targets past T enter as
+                    // -inf -> 0)
+                    const bool in = nt * 8 + tig * 2 + j < T;
+                    ex[nt][j]     = exp_nonpositive(in ? __dsub_rn(o[nt][j], omax) : -INFINITY);
+                    sumexp += ex[nt][j];
+                    dot += in ? __dmul_rn(__dadd_rn(1.0, y[nt][j]), o[nt][j]) : 0.0;
                 }
             }
             sumexp = quad_sum(sumexp);
             dot    = quad_sum(dot);
-            if (row_ok)
+            // one reciprocal per row instead of 2 NT8 divisions per lane (exp x (1 / sum): within one rounding of the
+            // reference's quotient); selects instead of branches around the logarithm and the gradient
+            const double value = __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
+            const double rcp   = __ddiv_rn(1.0, sumexp);
+            fsum += row_ok ? value : 0.0;
+            if (GRAD)
             {
-                fsum += __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                if (GRAD)
+#pragma unroll
+                for (int nt = 0; nt < NT8; ++nt)
                 {
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt)
+                    for (int j = 0; j < 2; ++j)
                     {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                        {
-                            if (nt * 8 + tig * 2 + j < T)
-                            {
-                                dl[nt][j] = __dsub_rn(__ddiv_rn(ex[nt][j], sumexp),
-                                                      __dmul_rn(0.5, __dadd_rn(1.0, y[nt][j])));
-                            }
-                        }
+                        const double gv =
+                            __dsub_rn(__dmul_rn(ex[nt][j], rcp), __dmul_rn(0.5, __dadd_rn(1.0, y[nt][j])));
+                        dl[nt][j] = (row_ok && nt * 8 + tig * 2 + j < T) ? gv : 0.0;
                     }
                 }
             }

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
             {
                 // classnll.h:19-37: the TP lanes of a group hold the whole row
                 const double omax   = group_max<TP>(el_ok ? o : -INFINITY);
-                const double ex     = el_ok ? exp(__dsub_rn(o, omax)) : 0.0;
+                const double ex     = exp_nonpositive(el_ok ? __dsub_rn(o, omax) : -INFINITY); // (straight-line)
                 const double sumexp = group_sum<TP>(ex);
                 const double dot    = group_sum<TP>(el_ok ? __dmul_rn(__dadd_rn(1.0, y), o) : 0.0);
                 // (straight-line: the logarithm of the value and the division of the gradient overlap)
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(fp_threads(NT8), 1) vgrad_fp_kernel(const fd_p
             {
                 // the TP lanes of a group hold the whole row; dL = softmax - 0.5 (1 + y)
                 const double omax   = group_max<TP>(el_ok ? o : -INFINITY);
-                const double ex     = el_ok ? exp(__dsub_rn(o, omax)) : 0.0;
+                const double ex     = exp_nonpositive(el_ok ? __dsub_rn(o, omax) : -INFINITY); // (straight-line)
                 const double sumexp = group_sum<TP>(ex);
                 const double grad   = __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y)));
                 dl                  = (GRAD && el_ok) ? grad : 0.0;

@@ -372,13 +372,12 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
                     {
-                        ex[u][nt][j] = 0.0;
-                        if (nt * 8 + tig * 2 + j < T)
-                        {
-                            ex[u][nt][j] = exp(__dsub_rn(o[u][nt][j], omax[u]));
-                            sumexp[u] += ex[u][nt][j];
-                            dot[u] += __dmul_rn(__dadd_rn(1.0, y[u][nt][j]), o[u][nt][j]);
-                        }
+                        // (no branch: the 2 NT8 TPW exponentials of a lane are independent chains; targets past T
+                        // enter as -inf -> 0)
+                        const bool in = nt * 8 + tig * 2 + j < T;
+                        ex[u][nt][j]  = exp_nonpositive(in ? __dsub_rn(o[u][nt][j], omax[u]) : -INFINITY);
+                        sumexp[u] += ex[u][nt][j];
+                        dot[u] += in ? __dmul_rn(__dadd_rn(1.0, y[u][nt][j]), o[u][nt][j]) : 0.0;
                     }
                 }
                 sumexp[u] = quad_sum(sumexp[u]);
@@ -387,23 +386,22 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
 #pragma unroll
             for (int u = 0; u < TPW; ++u)
             {
-                if (row_ok[u])
+                // one reciprocal per row instead of 2 NT8 divisions per lane (exp x (1 / sum): within one rounding of
+                // the reference's quotient); selects instead of branches around the logarithm and the gradient
+                const double value = __dadd_rn(__dsub_rn(log(sumexp[u]), __dmul_rn(0.5, dot[u])), omax[u]);
+                const double rcp   = __ddiv_rn(1.0, sumexp[u]);
+                fsum += row_ok[u] ? value : 0.0;
+                if (GRAD)
                 {
-                    fsum += __dadd_rn(__dsub_rn(log(sumexp[u]), __dmul_rn(0.5, dot[u])), omax[u]);
-                    if (GRAD)
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt)
                     {
 #pragma unroll
-                        for (int nt = 0; nt < NT8; ++nt)
+                        for (int j = 0; j < 2; ++j)
                         {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-                            {
-                                if (nt * 8 + tig * 2 + j < T)
-                                {
-                                    dl[u][nt][j] = __dsub_rn(__ddiv_rn(ex[u][nt][j], sumexp[u]),
-                                                             __dmul_rn(0.5, __dadd_rn(1.0, y[u][nt][j])));
-                                }
-                            }
+                            const double gv = __dsub_rn(__dmul_rn(ex[u][nt][j], rcp),
+                                                        __dmul_rn(0.5, __dadd_rn(1.0, y[u][nt][j])));
+                            dl[u][nt][j] = (row_ok[u] && nt * 8 + tig * 2 + j < T) ? gv : dl[u][nt][j];
                         }
                     }
                 }
