@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
         bias[nt][1] = (t + 1 < T) ? p.b[t + 1] : 0.0;
     }
     double  fsum = 0.0;          // loss of the rows g this lane has seen (identical on the 4 lanes of a quad)
+    log_product logs;            // softmax: the rows' sums of exponentials, multiplied up (loss.cuh)
     double  gbsum[NT8][2];       // sum over rows of dL[g][8 nt + 2 tig + j]
     double  lsum[NT8][2];        // per-target loss sums (batched models)
 #pragma unroll
@@ -400,9 +401,11 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
             dot    = quad_sum(dot);
             // one reciprocal per row instead of 2 NT8 divisions per lane (exp x (1 / sum): within one rounding of the
             // reference's quotient); selects instead of branches around the logarithm and the gradient
-            const double value = __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-            const double rcp   = __ddiv_rn(1.0, sumexp);
-            fsum += row_ok ? value : 0.0;
+            // (the logarithm of the value is taken once per kLogEvery rows: loss.cuh, log_product)
+            const double rcp = __ddiv_rn(1.0, sumexp);
+            fsum += row_ok ? __dsub_rn(omax, __dmul_rn(0.5, dot)) : 0.0;
+            logs.product *= row_ok ? sumexp : 1.0;
+            log_product_flush(logs, 1, fsum);
             if (GRAD)
             {
 #pragma unroll
@@ -495,6 +498,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fd_kernel(const fd_params
     double*    out_gw  = batched ? p.partials_gw + static_cast<int64_t>(blockIdx.x) * T * D : out + 1 + T;
 
     // loss and dL sums of this warp's set: fold the 8 row slots (g) in order; every warp of a set carries the same
+    fsum += log(logs.product); // (1 when nothing is pending)
     double f = (tig == 0) ? fsum : 0.0;
     f += __shfl_xor_sync(0xffffffffu, f, 4);
     f += __shfl_xor_sync(0xffffffffu, f, 8);

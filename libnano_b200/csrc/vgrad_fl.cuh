@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
     const bool   t_ok    = lane_on && lt < T;
     const double my_bias = t_ok ? p.b[lt] : 0.0;
     double       fsum    = 0.0; // losses of this lane's rows (kept by the lanes with lt == 0)
+    log_product  logs;          // softmax: the rows' sums of exponentials, multiplied up (loss.cuh)
     double       gbsum   = 0.0; // sum over this lane's rows of dL[row][lt]
     double       lsum    = 0.0; // per-target loss sums (batched models)
 
@@ -334,10 +335,11 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
                 const double ex     = exp_nonpositive(el_ok ? __dsub_rn(o, omax) : -INFINITY); // (straight-line)
                 const double sumexp = group_sum<TP>(ex);
                 const double dot    = group_sum<TP>(el_ok ? __dmul_rn(__dadd_rn(1.0, y), o) : 0.0);
-                // (straight-line: the logarithm of the value and the division of the gradient overlap)
-                const double value = __dadd_rn(__dsub_rn(log(sumexp), __dmul_rn(0.5, dot)), omax);
-                const double grad  = __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y)));
-                fsum += (row_ok && lt == 0) ? value : 0.0;
+                // (the logarithm of the value is taken once per kLogEvery rows: loss.cuh, log_product)
+                const double grad = __dsub_rn(__ddiv_rn(ex, sumexp), __dmul_rn(0.5, __dadd_rn(1.0, y)));
+                fsum += (row_ok && lt == 0) ? __dsub_rn(omax, __dmul_rn(0.5, dot)) : 0.0;
+                logs.product *= (row_ok && lt == 0) ? sumexp : 1.0;
+                log_product_flush(logs, 1, fsum);
                 dl = (GRAD && el_ok) ? grad : 0.0;
             }
             else
@@ -431,7 +433,8 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fl_kernel(const fd_params
     }
     // loss / dL / per-target loss sums: every lane parks its sums, warp 0 folds them in (warp, row) order
     // (the last barrier of the loop is behind every read of the exchange area)
-    double* fold = exchange; // [3][8 warps][32 lanes]
+    fsum += log(logs.product); // (1 when nothing is pending)
+    double* fold = exchange;   // [3][8 warps][32 lanes]
     fold[0 * kFdWarps * 32 + warp * 32 + lane] = (lane_on && lt == 0) ? fsum : 0.0;
     fold[1 * kFdWarps * 32 + warp * 32 + lane] = lane_on ? gbsum : 0.0;
     fold[2 * kFdWarps * 32 + warp * 32 + lane] = lane_on ? lsum : 0.0;

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
         bias[nt][1] = (t + 1 < T) ? p.b[t + 1] : 0.0;
     }
     double fsum = 0.0;    // loss of the rows g of this warp's tiles (identical on the 4 lanes of a quad)
+    log_product logs;     // softmax: the rows' sums of exponentials, multiplied up (loss.cuh)
     double gbsum[NT8][2]; // sum over this warp's rows of dL[g][8 nt + 2 tig + j]
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt)
@@ -388,9 +389,10 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
             {
                 // one reciprocal per row instead of 2 NT8 divisions per lane (exp x (1 / sum): within one rounding of
                 // the reference's quotient); selects instead of branches around the logarithm and the gradient
-                const double value = __dadd_rn(__dsub_rn(log(sumexp[u]), __dmul_rn(0.5, dot[u])), omax[u]);
-                const double rcp   = __ddiv_rn(1.0, sumexp[u]);
-                fsum += row_ok[u] ? value : 0.0;
+                // (the logarithm of the value is taken once per kLogEvery rows: loss.cuh, log_product)
+                const double rcp = __ddiv_rn(1.0, sumexp[u]);
+                fsum += row_ok[u] ? __dsub_rn(omax[u], __dmul_rn(0.5, dot[u])) : 0.0;
+                logs.product *= row_ok[u] ? sumexp[u] : 1.0;
                 if (GRAD)
                 {
 #pragma unroll
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
                     }
                 }
             }
+            log_product_flush(logs, TPW, fsum);
         }
         else
         {
@@ -478,6 +481,7 @@ __global__ void __launch_bounds__(kFdThreads, 1) vgrad_fr_kernel(const fd_params
     double* out_gw = out + 1 + T;
 
     // loss and dL sums: fold the 8 row slots (g) of every warp in order, then the warps in warp order
+    fsum += log(logs.product); // (1 when nothing is pending)
     double f = (tig == 0) ? fsum : 0.0;
     f += __shfl_xor_sync(0xffffffffu, f, 4);
     f += __shfl_xor_sync(0xffffffffu, f, 8);
