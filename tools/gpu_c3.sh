@@ -1,6 +1,5 @@
 #!/bin/bash
-# One GPU: the many-target pair after an epilogue change — parity of the tensor-pipe paths, then config 3 (A/B against
-# the previous library when tools/bin/libnb200_base.so is there: NB200_LIB picks the library)
+# One GPU: the many-target pair after an epilogue change — parity of the tensor-pipe paths, then config 3 twice
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_ref_golden.py -x -q -m gpu -k "many_target or multi_target or config3 or golden or extreme or large_output" > gpurun_out/c3_tests.log 2>&1
