@@ -822,9 +822,7 @@ __global__ void __launch_bounds__(fp_threads(NT8), 1) vgrad_fp_kernel(const fd_p
         }
     }
     auto backward_previous = [&](const uint32_t parity) {
-        // (ncu: a shared-memory load takes a few hundred cycles here — the eight warps' fragment loads queue in front
-        // of it —, and the first DMMA behind each of the A fragments holds ~5 % of the consumers' stall samples; ptxas
-        // orders the 52 DMMAs by A fragment whatever the source order is)
+        // (ptxas orders the 2 NT8 NS8 DMMAs by A fragment whatever the source order is)
         const double* dl_prev = dl_tiles + parity * (kFdRows * kFdLdd);
         double        a[2][NT8];
 #pragma unroll
