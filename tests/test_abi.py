@@ -123,6 +123,12 @@ def test_hot_kernels_keep_their_code_generation(library):
                            "_ZN5nb20021mt_forward_tma_kernelILi13ELb1EEEvNS_17mt_forward_paramsE14CUtensorMap_st",
                            library._name], capture_output=True, text=True).stdout
     assert "UTMALDG.2D" in sass and "DMMA.8x8x4" in sass
+    # the lane-loss pipeline: bulk copies into the ring, mbarrier hand-overs, the fp64 tensor pipe, register hand-over —
+    # and the straight-line exponential (no call into the library routine's slow path from the softmax step)
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN5nb20015vgrad_fp_kernelILi2ELi13ELb1EEEvNS_9fd_paramsE",
+                           library._name], capture_output=True, text=True).stdout
+    for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "DMMA.8x8x4", "USETMAXREG"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_gpu_means_loud_failure_not_fallback(library):
